@@ -1,0 +1,140 @@
+/*
+ * rst_b200.h -- C ABI of the B200-native stylization hot path (librst_sm100.so).
+ *
+ * The reference (singinwhale/realtime-style-transfer) has no FFI of its own: its boundary is the
+ * Python model-builder surface.  Each entry point below names the reference
+ * interface it stands in for (paths relative to the reference repository).  Plain pointers and
+ * sizes only; no torch / CUDA types in the signatures (streams are passed as void* holding a
+ * cudaStream_t, NULL = the legacy default stream).
+ *
+ * Conventions: tensors are dense NHWC float32 at the boundary, like the reference's numpy/TF
+ * tensors.  "d_" pointers are device memory on the context's GPU, "h_" pointers are host memory.
+ * Every call returns 0 (RST_OK) or an error code; rst_last_error() gives the message.
+ * One context per GPU / per thread; no call allocates device memory after rst_commit_weights().
+ */
+#ifndef RST_B200_H
+#define RST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rst_ctx rst_ctx;
+
+enum rst_status {
+    RST_OK = 0,
+    RST_ERR_INVALID = 1,     /* bad argument / shape (the reference raises ValueError / assert) */
+    RST_ERR_CUDA = 2,        /* CUDA runtime or driver failure */
+    RST_ERR_STATE = 3,       /* call order violated (e.g. forward before weights committed) */
+    RST_ERR_UNSUPPORTED = 4  /* valid in the reference, not built here yet */
+};
+
+enum rst_precision {
+    RST_PRECISION_FP32 = 0,  /* CUDA-core fp32 path, bar: max abs err <= 1e-4 vs the oracle */
+    RST_PRECISION_BF16 = 1   /* tcgen05 bf16 path (fp32 accumulate), bar: <= 2e-2 relative */
+};
+
+enum rst_extractor {         /* stylePrediction.StyleFeatureExtractor, stylePrediction.py:19-22 */
+    RST_EXTRACTOR_NONE = 0,
+    RST_EXTRACTOR_DUMMY = 1,
+    RST_EXTRACTOR_MOBILE_NET = 2
+};
+
+/* Mirrors the arguments of create_style_transfer_model (models/styleTransfer.py:213-214) plus the
+ * style-predictor choice of create_style_prediction_model (models/stylePrediction.py:25-26). */
+typedef struct rst_config {
+    int32_t in_h, in_w, in_c;          /* content input_shape (rows, cols, G-buffer channels)     */
+    int32_t out_h, out_w;              /* output_shape rows, cols (3 channels implied)            */
+    int32_t bottleneck_res_y;
+    int32_t bottleneck_num_filters;
+    int32_t num_styles;                /* 1, or 2 for the weight-map blend (styleTransfer.py:36-44) */
+    int32_t max_batch;                 /* workspace is sized for this many frames per call        */
+    int32_t precision;                 /* enum rst_precision                                      */
+    int32_t extractor;                 /* enum rst_extractor                                      */
+    int32_t style_h, style_w;          /* style image rows, cols (3 channels implied)             */
+    int32_t predictor_num_params;      /* only when in_h == 0: predictor-only context, P = this    */
+} rst_config;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+const char* rst_version(void);
+/* Builds the layer plan and allocates all device workspaces (replaces the Keras graph construction in
+ * styleTransfer.py:213-332 / styleTransferInferenceModel.py:9-48). */
+int rst_create(const rst_config* cfg, int device, rst_ctx** out_ctx);
+int rst_destroy(rst_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed rst_create on this thread. */
+const char* rst_last_error(const rst_ctx* ctx);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+/* num_style_parameters returned by create_style_transfer_model (styleTransfer.py:278-279, :332). */
+int rst_num_style_params(const rst_ctx* ctx);
+int rst_num_contract_blocks(const rst_ctx* ctx);   /* styleTransfer.py:217 */
+int rst_num_expand_blocks(const rst_ctx* ctx);     /* styleTransfer.py:258 */
+/* Enumerate the variables the model owns (Keras layouts: Conv2D kernel (kh,kw,in,out),
+ * Conv2DTranspose kernel (kh,kw,out,in)). */
+int rst_weight_count(const rst_ctx* ctx);
+const char* rst_weight_name(const rst_ctx* ctx, int index);
+int rst_weight_shape(const rst_ctx* ctx, int index, int64_t* shape4, int* ndim);
+
+/* ---- weights (stands in for model.load_weights / set_weights, predict_using_checkpoint.py:84) -- */
+int rst_set_weight(rst_ctx* ctx, const char* name, const float* h_data, const int64_t* shape, int ndim);
+int rst_get_weight(const rst_ctx* ctx, const char* name, float* h_data, int64_t capacity_elems);
+/* Uploads, folds inference BatchNorm into per-channel affines and packs the bf16 operand layouts. */
+int rst_commit_weights(rst_ctx* ctx);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* transfer.predict({'content','style_params'[,'style_weights']}) (predict_video_using_checkpoint.py:93-96,
+ * models/styleTransfer.py:305-329).  d_content (B,in_h,in_w,in_c), d_style_params (B,S,P),
+ * d_style_weights (B,out_h,out_w,S-1) or NULL when S==1, d_out (B,out_h,out_w,3) fp32 in (0,1). */
+int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const float* d_style_params,
+                         const float* d_style_weights, float* d_out, int batch, void* stream);
+/* Same with HOST buffers: H2D copies, forward, D2H copy and a stream synchronise inside. */
+int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
+                              const float* h_style_weights, float* h_out, int batch);
+/* style_predictor(style_image) (models/stylePrediction.py:25-75): d_style (B,style_h,style_w,3) in [0,1]
+ * -> d_params (B,P). */
+int rst_predict_style(rst_ctx* ctx, const float* d_style, float* d_params, int batch, void* stream);
+int rst_predict_style_host(rst_ctx* ctx, const float* h_style, float* h_params, int batch);
+/* inference.predict({'content','style'[,'style_weights']}) (models/styleTransferInferenceModel.py:24-39):
+ * h_style (B,S,style_h,style_w,3); predictor per style, then the transfer net. */
+int rst_inference_forward_host(rst_ctx* ctx, const float* h_content, const float* h_style,
+                               const float* h_style_weights, float* h_out, int batch);
+
+/* Copy one intermediate activation of the LAST forward (as fp32 NHWC) for layer-level parity tests.
+ * Names follow the oracle's taps: "contract_start", "residual_block_0/conv0/relu", "expand_0", ...
+ * Returns the element count through *elems; d_out may be NULL to query the size. */
+int rst_debug_enable_taps(rst_ctx* ctx, int enable);
+int rst_debug_tap(rst_ctx* ctx, const char* name, float* h_out, int64_t capacity_elems, int64_t* elems);
+/* Number of kernels of this library launched by the last hot-path call (bench.py "gpu_launches"). */
+int64_t rst_last_launch_count(const rst_ctx* ctx);
+/* Average device time (ms, CUDA events on the launch stream) of named kernel groups accumulated since
+ * rst_profile_reset: used by bench.py for the live roofline measurement. */
+int rst_profile_enable(rst_ctx* ctx, int enable);
+int rst_profile_reset(rst_ctx* ctx);
+int rst_profile_get(rst_ctx* ctx, const char* group, double* total_ms, int64_t* launches);
+int rst_profile_group_count(rst_ctx* ctx);
+const char* rst_profile_group_name(rst_ctx* ctx, int index);
+
+/* ---- stand-alone operators (device pointers; used by the parity tests, one reference op each) --- */
+/* Message of the last failed rst_op_* call on this thread. */
+const char* rst_op_last_error(void);
+/* tf.keras.layers.Conv2D / Conv2DTranspose with padding='same' (styleTransfer.py:170-172, :194-199, :115-119).
+ * kernel layout: Conv2D (kh,kw,ci,co); transposed!=0: (kh,kw,co,ci).  act: 0 none, 1 relu, 4 sigmoid. */
+int rst_op_conv2d(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y,
+                  int batch, int h, int w, int ci, int co, int kh, int kw, int stride,
+                  int transposed, int act, int precision, void* stream);
+/* ConditionalInstanceNormalization.call (styleTransfer.py:57-71) incl. _apply_style_weights (:36-44).
+ * d_params (B,S,2F) = [scale F | bias F] per style; d_weights (B,H,W,S) or NULL when S==1. */
+int rst_op_cin(const float* d_x, const float* d_params, const float* d_weights, float* d_y,
+               int batch, int h, int w, int f, int num_styles, int act, void* stream);
+/* _apply_style_weights alone (styleTransfer.py:36-44): weights (B,H,W,2), params (B,1,2,F) -> (B,H,W,F). */
+int rst_op_apply_style_weights(const float* d_weights, const float* d_params, float* d_out,
+                               int batch, int h, int w, int f, void* stream);
+/* get_gram_matrix_model (styleLoss.py:11-18): (B,H,W,C) -> (B,C,C), divided by H*W. */
+int rst_op_gram(const float* d_x, float* d_gram, int batch, int h, int w, int c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RST_B200_H */

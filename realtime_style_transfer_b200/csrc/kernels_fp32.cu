@@ -1,0 +1,488 @@
+// Generic fp32 kernels (CUDA cores): direct convolution as an implicit GEMM, depthwise convolution,
+// instance-norm moments / apply, pooling, style-weight blend, Gram matrix.
+// These serve the RST_PRECISION_FP32 path (bar: 1e-4 abs vs the oracle), the style predictor and
+// every layer the tensor-core path does not cover yet.  NHWC throughout.
+#include "rst_internal.cuh"
+
+namespace rst {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv2d / conv2d_transpose, padding='same' semantics supplied by the caller as pad_t/pad_l.
+// GEMM view: M = B*Ho*Wo output pixels, N = Co, K = kh*kw*Ci.  BMxBN tile per CTA, BK = 16.
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const ConvF32 p) {
+    constexpr int BK = 16;
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int A_ROWS = NT / BK;          // pixel rows gathered per pass
+    constexpr int A_PASSES = BM / A_ROWS;
+    constexpr int B_ROWS = NT / BN;          // k rows loaded per pass
+    constexpr int B_PASSES = (BK + B_ROWS - 1) / B_ROWS;
+    static_assert(NT % BK == 0 && BM % A_ROWS == 0 && NT % BN == 0, "tile/loader mismatch");
+
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+
+    const int tid = threadIdx.x;
+    const long long M = (long long)p.B * p.Ho * p.Wo;
+    const int K = p.kh * p.kw * p.Ci;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    const int a_k = tid % BK;
+    const int a_r = tid / BK;
+    int a_n[A_PASSES], a_oy[A_PASSES], a_ox[A_PASSES];
+#pragma unroll
+    for (int j = 0; j < A_PASSES; ++j) {
+        long long m = m0 + a_r + j * A_ROWS;
+        if (m < M) {
+            int ox = (int)(m % p.Wo);
+            long long t = m / p.Wo;
+            a_ox[j] = ox;
+            a_oy[j] = (int)(t % p.Ho);
+            a_n[j] = (int)(t / p.Ho);
+        } else {
+            a_n[j] = -1; a_oy[j] = 0; a_ox[j] = 0;
+        }
+    }
+    const int b_c = tid % BN;
+    const int b_r = tid / BN;
+
+    const int tx = tid % (BN / TN);
+    const int ty = tid / (BN / TN);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // ---- gather A (im2col on the fly) ----
+        {
+            const int kk = k0 + a_k;
+            int ky = 0, kx = 0, ci = 0;
+            const bool kvalid = kk < K;
+            if (kvalid) {
+                int tap = kk / p.Ci;
+                ci = kk - tap * p.Ci;
+                ky = tap / p.kw;
+                kx = tap - ky * p.kw;
+            }
+#pragma unroll
+            for (int j = 0; j < A_PASSES; ++j) {
+                float v = 0.f;
+                if (kvalid && a_n[j] >= 0) {
+                    int iy, ix;
+                    bool ok;
+                    if (!p.transposed) {
+                        iy = a_oy[j] * p.stride - p.pad_t + ky;
+                        ix = a_ox[j] * p.stride - p.pad_l + kx;
+                        ok = iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi;
+                    } else {
+                        int ty_ = a_oy[j] + p.pad_t - ky;
+                        int tx_ = a_ox[j] + p.pad_l - kx;
+                        ok = ty_ >= 0 && tx_ >= 0 && (ty_ % p.stride) == 0 && (tx_ % p.stride) == 0;
+                        iy = ty_ / p.stride;
+                        ix = tx_ / p.stride;
+                        ok = ok && iy < p.Hi && ix < p.Wi;
+                    }
+                    if (ok) {
+                        v = __ldg(p.x + (((long long)a_n[j] * p.Hi + iy) * p.Wi + ix) * p.Ci + ci);
+                        v = v * p.in_scale + p.in_shift;
+                    }
+                }
+                As[a_k][a_r + j * A_ROWS] = v;
+            }
+        }
+        // ---- load B (weights) ----
+#pragma unroll
+        for (int j = 0; j < B_PASSES; ++j) {
+            int r = b_r + j * B_ROWS;
+            if (r < BK) {
+                int kk = k0 + r;
+                int co = n0 + b_c;
+                float v = 0.f;
+                if (kk < K && co < p.Co) {
+                    int tap = kk / p.Ci;
+                    int ci = kk - tap * p.Ci;
+                    v = __ldg(p.w + tap * p.w_tap + ci * p.w_ci + co * p.w_co);
+                }
+                Bs[r][b_c] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        long long m = m0 + ty * TM + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int co = n0 + tx * TN + j;
+            if (co >= p.Co) continue;
+            float v = acc[i][j];
+            if (p.bias) v += __ldg(p.bias + co);
+            v = apply_act(v, p.act1);
+            if (p.post_scale) v = v * __ldg(p.post_scale + co) + __ldg(p.post_shift + co);
+            v = apply_act(v, p.act2);
+            long long o = m * p.Co + co;
+            if (p.residual) v += __ldg(p.residual + o);
+            p.y[o] = v;
+        }
+    }
+}
+
+cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
+    long long M = (long long)p.B * p.Ho * p.Wo;
+    if (M == 0) return cudaSuccess;
+    if (p.Co > 16) {
+        dim3 grid((unsigned)((M + 63) / 64), (unsigned)ceil_div(p.Co, 64));
+        conv_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
+    } else {
+        dim3 grid((unsigned)((M + 127) / 128), 1);
+        conv_f32_kernel<128, 16, 4, 2><<<grid, 256, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise conv (Keras DepthwiseConv2D, MobileNetV3 blocks).  One thread per output element.
+// ---------------------------------------------------------------------------------------------
+__global__ void depthwise_f32_kernel(const DepthwiseF32 p, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c = (int)(idx % p.C);
+    long long t = idx / p.C;
+    int ox = (int)(t % p.Wo);
+    t /= p.Wo;
+    int oy = (int)(t % p.Ho);
+    int n = (int)(t / p.Ho);
+    float acc = 0.f;
+    for (int ky = 0; ky < p.k; ++ky) {
+        int iy = oy * p.stride - p.pad_t + ky;
+        if (iy < 0 || iy >= p.Hi) continue;
+        for (int kx = 0; kx < p.k; ++kx) {
+            int ix = ox * p.stride - p.pad_l + kx;
+            if (ix < 0 || ix >= p.Wi) continue;
+            acc = fmaf(__ldg(p.x + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.C + c),
+                       __ldg(p.w + (ky * p.k + kx) * p.C + c), acc);
+        }
+    }
+    if (p.post_scale) acc = acc * __ldg(p.post_scale + c) + __ldg(p.post_shift + c);
+    p.y[idx] = apply_act(acc, p.act);
+}
+
+cudaError_t launch_depthwise_f32(const DepthwiseF32& p, cudaStream_t s) {
+    long long total = (long long)p.B * p.Ho * p.Wo * p.C;
+    if (total == 0) return cudaSuccess;
+    depthwise_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p, total);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-(n,c) sum / sum of squares over the H*W pixels, double accumulation
+// ---------------------------------------------------------------------------------------------
+__global__ void moments_f32_kernel(const float* __restrict__ x, double* __restrict__ stats, int P, int C,
+                                   int pix_per_block) {
+    extern __shared__ double sm[];
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(P, p0 + pix_per_block);
+    const float* xb = x + (long long)n * P * C;
+    if (C <= (int)blockDim.x) {
+        const int G = blockDim.x / C;
+        const int c = threadIdx.x % C;
+        const int g = threadIdx.x / C;
+        double s = 0.0, q = 0.0;
+        if (g < G) {
+            for (int pp = p0 + g; pp < p1; pp += G) {
+                double v = (double)__ldg(xb + (long long)pp * C + c);
+                s += v;
+                q += v * v;
+            }
+        }
+        sm[threadIdx.x] = s;
+        sm[blockDim.x + threadIdx.x] = q;
+        __syncthreads();
+        if (g == 0) {
+            for (int j = 1; j < G; ++j) {
+                s += sm[j * C + c];
+                q += sm[blockDim.x + j * C + c];
+            }
+            atomicAdd(&stats[((long long)n * C + c) * 2 + 0], s);
+            atomicAdd(&stats[((long long)n * C + c) * 2 + 1], q);
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            double s = 0.0, q = 0.0;
+            for (int pp = p0; pp < p1; ++pp) {
+                double v = (double)__ldg(xb + (long long)pp * C + c);
+                s += v;
+                q += v * v;
+            }
+            atomicAdd(&stats[((long long)n * C + c) * 2 + 0], s);
+            atomicAdd(&stats[((long long)n * C + c) * 2 + 1], q);
+        }
+    }
+}
+
+cudaError_t launch_moments_f32(const float* x, double* stats, int B, int P, int C, cudaStream_t s) {
+    if (B == 0 || P == 0) return cudaSuccess;
+    int threads = C <= 256 ? C * (256 / C) : 256;
+    int pix_per_block = 2048;
+    dim3 grid((unsigned)ceil_div(P, pix_per_block), (unsigned)B);
+    moments_f32_kernel<<<grid, threads, 2 * threads * sizeof(double), s>>>(x, stats, P, C, pix_per_block);
+    return cudaGetLastError();
+}
+
+__global__ void zero_f64_kernel(double* p, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+cudaError_t launch_zero_f64(double* p, long long n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    zero_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n);
+    return cudaGetLastError();
+}
+
+__global__ void stats_to_mean_kernel(const double* stats, float* mean, long long n, double invP) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mean[i] = (float)(stats[i * 2] * invP);
+}
+cudaError_t launch_stats_to_mean(const double* stats, float* mean, int B, int P, int C, cudaStream_t s) {
+    long long n = (long long)B * C;
+    if (n == 0) return cudaSuccess;
+    stats_to_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(stats, mean, n, 1.0 / (double)P);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// conditional instance norm apply; follows the reference's operation order:
+//   xh = x*inv + (-mean*inv);  y = bias + xh*scale   (styleTransfer.py:65-68)
+// ---------------------------------------------------------------------------------------------
+template <bool XBF, bool YBF>
+__global__ void cin_apply_kernel(const CinApply p, int pix_per_block) {
+    extern __shared__ float smf[];
+    const int C = p.C;
+    float* s_inv = smf;              // [C]
+    float* s_nmi = smf + C;          // [C]   -mean*inv
+    float* s_scale = smf + 2 * C;    // [S][C]
+    float* s_bias = s_scale + p.num_styles * C;
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sum = p.stats[((long long)n * C + c) * 2 + 0];
+        double sq = p.stats[((long long)n * C + c) * 2 + 1];
+        double mean = sum / (double)p.P;
+        double var = sq / (double)p.P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float inv = rsqrtf((float)var + p.eps);
+        s_inv[c] = inv;
+        s_nmi[c] = -(float)mean * inv;
+        for (int st = 0; st < p.num_styles; ++st) {
+            const float* ps = p.params + n * p.param_bstride + st * p.param_sstride;
+            s_scale[st * C + c] = ps[p.scale_off + c];
+            s_bias[st * C + c] = ps[p.bias_off + c];
+        }
+    }
+    __syncthreads();
+    const long long base = (long long)n * p.P * C;
+    const long long e0 = (long long)blockIdx.x * pix_per_block * C;
+    const long long e1 = min((long long)p.P * C, e0 + (long long)pix_per_block * C);
+    const bool blend = p.num_styles == 2 && p.weights != nullptr;
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        int c = (int)(e % C);
+        float xv;
+        if (XBF) xv = __bfloat162float(((const __nv_bfloat16*)p.x)[base + e]);
+        else xv = ((const float*)p.x)[base + e];
+        float scale, bias;
+        if (blend) {
+            long long pix = e / C;
+            const float* w = p.weights + ((long long)n * p.P + pix) * 2;
+            float w0 = __ldg(w), w1 = __ldg(w + 1);
+            // reduce_sum over the style axis of params*weights (styleTransfer.py:41-42)
+            scale = s_scale[c] * w0 + s_scale[C + c] * w1;
+            bias = s_bias[c] * w0 + s_bias[C + c] * w1;
+        } else {
+            scale = s_scale[c];
+            bias = s_bias[c];
+        }
+        float xh = xv * s_inv[c] + s_nmi[c];
+        float v = bias + xh * scale;
+        v = apply_act(v, p.act);
+        if (p.residual) {
+            if (YBF) v += __bfloat162float(((const __nv_bfloat16*)p.residual)[base + e]);
+            else v += ((const float*)p.residual)[base + e];
+        }
+        if (YBF) ((__nv_bfloat16*)p.y)[base + e] = __float2bfloat16(v);
+        else ((float*)p.y)[base + e] = v;
+    }
+}
+
+cudaError_t launch_cin_apply(const CinApply& p, cudaStream_t s) {
+    if (p.B == 0 || p.P == 0) return cudaSuccess;
+    int pix_per_block = max(1, 16384 / p.C);
+    dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
+    size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
+    if (p.x_bf16 && p.y_bf16) cin_apply_kernel<true, true><<<grid, 256, smem, s>>>(p, pix_per_block);
+    else if (p.x_bf16) cin_apply_kernel<true, false><<<grid, 256, smem, s>>>(p, pix_per_block);
+    else if (p.y_bf16) cin_apply_kernel<false, true><<<grid, 256, smem, s>>>(p, pix_per_block);
+    else cin_apply_kernel<false, false><<<grid, 256, smem, s>>>(p, pix_per_block);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// style-weight handling
+// ---------------------------------------------------------------------------------------------
+// (pixels, S-1) -> (pixels, S) = [1 - sum(w), w...]   (styleTransfer.py:297-302)
+__global__ void weights_concat_kernel(const float* __restrict__ w_in, float* __restrict__ w_out, long long pixels,
+                                      int sm1) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    float sum = 0.f;
+    for (int k = 0; k < sm1; ++k) {
+        float v = w_in[i * sm1 + k];
+        sum += v;
+        w_out[i * (sm1 + 1) + 1 + k] = v;
+    }
+    w_out[i * (sm1 + 1)] = 1.f - sum;
+}
+cudaError_t launch_weights_concat(const float* w_in, float* w_out, long long pixels, int sm1, cudaStream_t s) {
+    if (pixels == 0) return cudaSuccess;
+    weights_concat_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, s>>>(w_in, w_out, pixels, sm1);
+    return cudaGetLastError();
+}
+
+template <bool MAX>
+__global__ void pool2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi, int C,
+                                 long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    int c = (int)(idx % C);
+    long long t = idx / C;
+    int ox = (int)(t % Wo);
+    t /= Wo;
+    int oy = (int)(t % Ho);
+    long long n = t / Ho;
+    const float* b = x + ((n * Hi + 2 * oy) * Wi + 2 * ox) * C + c;
+    float v00 = b[0], v01 = b[C], v10 = b[(long long)Wi * C], v11 = b[(long long)Wi * C + C];
+    y[idx] = MAX ? fmaxf(fmaxf(v00, v01), fmaxf(v10, v11)) : (v00 + v01 + v10 + v11) * 0.25f;
+}
+cudaError_t launch_avgpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
+    long long total = (long long)B * (Hi / 2) * (Wi / 2) * C;
+    if (total == 0) return cudaSuccess;
+    pool2_f32_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, Hi, Wi, C, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_maxpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
+    long long total = (long long)B * (Hi / 2) * (Wi / 2) * C;
+    if (total == 0) return cudaSuccess;
+    pool2_f32_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, Hi, Wi, C, total);
+    return cudaGetLastError();
+}
+
+__global__ void scale_channels_kernel(const float* __restrict__ x, const float* __restrict__ z,
+                                      float* __restrict__ y, long long PC, int C, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    long long n = idx / PC;
+    int c = (int)(idx % C);
+    y[idx] = x[idx] * __ldg(z + n * C + c);
+}
+cudaError_t launch_scale_channels(const float* x, const float* z, float* y, int B, int P, int C, cudaStream_t s) {
+    long long total = (long long)B * P * C;
+    if (total == 0) return cudaSuccess;
+    scale_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, z, y, (long long)P * C, C, total);
+    return cudaGetLastError();
+}
+
+// _apply_style_weights (styleTransfer.py:36-44): out[b,p,f] = sum_s w[b,p,s]*params[b,0,s,f], S == 2
+__global__ void apply_style_weights_kernel(const float* __restrict__ w, const float* __restrict__ params,
+                                           float* __restrict__ out, long long P, int F, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int f = (int)(idx % F);
+    long long bp = idx / F;
+    long long b = bp / P;
+    const float* pb = params + b * 2 * F;
+    out[idx] = pb[f] * w[bp * 2] + pb[F + f] * w[bp * 2 + 1];
+}
+cudaError_t launch_apply_style_weights(const float* w, const float* params, float* out, int B, long long P, int F,
+                                       cudaStream_t s) {
+    long long total = (long long)B * P * F;
+    if (total == 0) return cudaSuccess;
+    apply_style_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, params, out, P, F, total);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram matrix (styleLoss.py:11-18), fp32 CUDA-core version: G[b] = F^T F / P, split over pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void gram_f32_kernel(const float* __restrict__ x, float* __restrict__ g, int P, int C, int pix_per_split,
+                                float invP) {
+    __shared__ float Fc[32][33];
+    __shared__ float Fd[32][33];
+    const int c0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int splits = ceil_div(P, pix_per_split);
+    const int b = blockIdx.z / splits, sp = blockIdx.z % splits;
+    const int p0 = sp * pix_per_split, p1 = min(P, p0 + pix_per_split);
+    const float* xb = x + (long long)b * P * C;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int pp = p0; pp < p1; pp += 32) {
+        for (int r = ty; r < 32; r += 8) {
+            int pix = pp + r;
+            Fc[r][tx] = (pix < p1 && c0 + tx < C) ? xb[(long long)pix * C + c0 + tx] : 0.f;
+            Fd[r][tx] = (pix < p1 && d0 + tx < C) ? xb[(long long)pix * C + d0 + tx] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            float d = Fd[r][tx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(Fc[r][ty + 8 * i], d, acc[i]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = c0 + ty + 8 * i, d = d0 + tx;
+        if (c < C && d < C) atomicAdd(&g[((long long)b * C + c) * C + d], acc[i] * invP);
+    }
+}
+cudaError_t launch_gram_f32(const float* x, float* g, int B, int P, int C, cudaStream_t s) {
+    if (B == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(g, 0, (size_t)B * C * C * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+    int pix_per_split = 4096;
+    int splits = ceil_div(P, pix_per_split);
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(C, 32), (unsigned)(B * splits));
+    gram_f32_kernel<<<grid, dim3(32, 8), 0, s>>>(x, g, P, C, pix_per_split, 1.f / (float)P);
+    return cudaGetLastError();
+}
+
+}  // namespace rst

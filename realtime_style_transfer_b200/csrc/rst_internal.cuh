@@ -1,0 +1,96 @@
+// Internal declarations shared by the translation units of librst_sm100.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rst_b200.h"
+
+namespace rst {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_HSIGMOID = 3, ACT_SIGMOID = 4 };
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// TF 'SAME' padding for one spatial dim: returns output size, writes pad_before.
+inline int tf_same(int size, int k, int s, int* pad_before) {
+    int out = (size + s - 1) / s;
+    int total = (out - 1) * s + k - size;
+    if (total < 0) total = 0;
+    *pad_before = total / 2;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic fp32 direct convolution (CUDA cores).  Correctness anchor + the RST_PRECISION_FP32 path.
+// ---------------------------------------------------------------------------------------------
+struct ConvF32 {
+    const float* x = nullptr;        // (B,Hi,Wi,Ci)
+    const float* w = nullptr;        // indexed tap*w_tap + ci*w_ci + co*w_co
+    const float* bias = nullptr;     // (Co) or null
+    float* y = nullptr;              // (B,Ho,Wo,Co)
+    int B = 0, Hi = 0, Wi = 0, Ci = 0, Ho = 0, Wo = 0, Co = 0;
+    int kh = 1, kw = 1, stride = 1, pad_t = 0, pad_l = 0;
+    int transposed = 0;              // 1: input-gradient form, iy = (oy + pad_t - ky)/stride when exact
+    long long w_tap = 0, w_ci = 0, w_co = 0;
+    float in_scale = 1.f, in_shift = 0.f;   // applied to in-bounds inputs only (Keras Rescaling)
+    int act1 = ACT_NONE;                    // y = act2(post_scale*act1(acc+bias)+post_shift) + residual
+    const float* post_scale = nullptr;
+    const float* post_shift = nullptr;
+    int act2 = ACT_NONE;
+    const float* residual = nullptr;
+};
+cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s);
+
+struct DepthwiseF32 {
+    const float* x = nullptr; const float* w = nullptr;  // w (kh,kw,C)
+    float* y = nullptr;
+    int B = 0, Hi = 0, Wi = 0, C = 0, Ho = 0, Wo = 0, k = 3, stride = 1, pad_t = 0, pad_l = 0;
+    const float* post_scale = nullptr; const float* post_shift = nullptr;
+    int act = ACT_NONE;
+};
+cudaError_t launch_depthwise_f32(const DepthwiseF32& p, cudaStream_t s);
+
+// per-(n,c) moments over H*W: stats (B,C,2) doubles = [sum, sumsq]; must be zeroed first.
+cudaError_t launch_moments_f32(const float* x, double* stats, int B, int P, int C, cudaStream_t s);
+cudaError_t launch_zero_f64(double* p, long long n, cudaStream_t s);
+// out (B,C) = mean over pixels from stats
+cudaError_t launch_stats_to_mean(const double* stats, float* mean, int B, int P, int C, cudaStream_t s);
+
+// Conditional instance norm apply (styleTransfer.py:57-71):
+//   y = act(bias + (x*inv - mean*inv)*scale) [+ residual];  S==2 blends scale/bias per pixel.
+struct CinApply {
+    const void* x = nullptr;           // fp32 or bf16 (x_bf16)
+    void* y = nullptr;                 // fp32 or bf16 (y_bf16)
+    const void* residual = nullptr;    // same dtype as y, or null
+    const double* stats = nullptr;     // (B,C,2) [sum,sumsq]
+    const float* params = nullptr;     // element (b,s,j) at params[b*param_bstride + s*param_sstride + j]
+    long long param_bstride = 0, param_sstride = 0;
+    int scale_off = 0, bias_off = 0;   // offsets j of the scale / bias vectors inside a style's params
+    const float* weights = nullptr;    // (B,H,W,2) blend weights (S==2) or null
+    int B = 0, P = 0, C = 0, num_styles = 1, act = ACT_NONE;
+    int x_bf16 = 0, y_bf16 = 0;
+    float eps = 1e-5f;
+};
+cudaError_t launch_cin_apply(const CinApply& p, cudaStream_t s);
+
+// style-weight pyramid (styleTransfer.py:297-303, :335-345)
+cudaError_t launch_weights_concat(const float* w_in, float* w_out, long long pixels, int sm1, cudaStream_t s);
+cudaError_t launch_avgpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s);
+cudaError_t launch_maxpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s);
+cudaError_t launch_scale_channels(const float* x, const float* z, float* y, int B, int P, int C, cudaStream_t s);
+cudaError_t launch_apply_style_weights(const float* w, const float* params, float* out, int B, long long P, int F,
+                                       cudaStream_t s);
+cudaError_t launch_gram_f32(const float* x, float* g, int B, int P, int C, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// bf16 tensor-core path (conv_umma.cu)
+// ---------------------------------------------------------------------------------------------
+bool umma_init(std::string* err);   // resolves cuTensorMapEncodeTiled through the runtime
+
+}  // namespace rst

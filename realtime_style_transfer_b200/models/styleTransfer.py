@@ -1,0 +1,197 @@
+"""Style-conditioned transfer network -- host mirror of the reference's
+realtime_style_transfer/models/styleTransfer.py (same public names and argument meaning).
+
+``create_style_transfer_model`` returns ``(model, num_style_parameters)`` exactly like the reference
+(styleTransfer.py:213-214, :331-332).  The model's forward runs in librst_sm100.so:
+encoder convs + BatchNorm, five residual blocks with conditional instance normalisation, transposed
+conv decoder, sigmoid head, and the dual-style weight-map blend.
+"""
+from __future__ import annotations
+
+import logging
+import typing
+
+import numpy as np
+
+from .. import _native
+from .._plan import NUM_PARAMS_PER_FEATURE, TransferPlan
+from ._base import InputSpec, NativeModel, _is_torch_cuda, as_numpy
+
+log = logging.getLogger(__name__)
+
+
+class StyleParamStack:
+    """Running cursor over the last axis of the style-parameter tensor (styleTransfer.py:12-33)."""
+
+    def __init__(self, style_params, style_weights):
+        self.style_params = style_params
+        self.style_weights = style_weights
+        self.lower_bound = 0
+
+    def get_params(self, num_params):
+        lo = self.lower_bound
+        self.lower_bound = lo + num_params
+        return self.style_params[..., lo:lo + num_params]
+
+    def make_content_and_style_input(self, content, num_params):
+        inputs = {"content": content, "style_params": self.get_params(num_params)}
+        if self.style_weights is not None:
+            inputs["style_weights"] = self.style_weights
+        return inputs
+
+
+def _apply_style_weights(style_weights, style_params):
+    """Per-pixel blend of two styles' parameters (styleTransfer.py:36-44), computed on the GPU.
+
+    style_weights (B,H,W,2), style_params (B,1,2,F) -> (B,H,W,F); with any other style count the
+    parameters pass through untouched, as in the reference."""
+    params = as_numpy(style_params)
+    if params.shape[-2] != 2:
+        return params
+    import torch
+    weights = as_numpy(style_weights)
+    b, h, w, _ = weights.shape
+    f = params.shape[-1]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_w = torch.from_numpy(weights).to(dev)
+    d_p = torch.from_numpy(params.reshape(b, 2, f)).to(dev)
+    d_o = torch.empty((b, h, w, f), dtype=torch.float32, device=dev)
+    _native.op_apply_style_weights(d_w.data_ptr(), d_p.data_ptr(), d_o.data_ptr(), b, h, w, f,
+                                   torch.cuda.current_stream().cuda_stream)
+    return d_o.cpu().numpy()
+
+
+class ConditionalInstanceNormalization:
+    """Shape helpers of the reference layer (styleTransfer.py:47-92).  The layer owns no variables:
+    scale and bias arrive as style parameters; normalisation runs fused in the native forward."""
+    NumParamsPerFeature: int = NUM_PARAMS_PER_FEATURE
+
+    def __init__(self, num_feature_maps, num_styles, name, epsilon=1e-5):
+        self.name = f"ConditionalInstanceNormalization_{name}"
+        self.epsilon = epsilon
+        self.num_feature_maps = num_feature_maps
+        self.num_styles = num_styles
+
+    def __call__(self, inputs, activation=_native.ACT_NONE):
+        import torch
+        x = as_numpy(inputs["content"])
+        params = as_numpy(inputs["style_params"])            # (B,1,S,2F)
+        b, h, w, f = x.shape
+        s = params.shape[-2]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        d_x = torch.from_numpy(x).to(dev)
+        d_p = torch.from_numpy(params.reshape(b, s, 2 * f)).to(dev)
+        d_w = torch.from_numpy(as_numpy(inputs["style_weights"])).to(dev) if self.num_styles > 1 else None
+        d_y = torch.empty_like(d_x)
+        _native.op_cin(d_x.data_ptr(), d_p.data_ptr(), d_w.data_ptr() if d_w is not None else 0, d_y.data_ptr(),
+                       b, h, w, f, s, activation, torch.cuda.current_stream().cuda_stream)
+        return d_y.cpu().numpy()
+
+    def get_config(self):
+        return {"epsilon": self.epsilon, "num_feature_maps": self.num_feature_maps,
+                "num_styles": self.num_feature_maps}
+
+    @classmethod
+    def get_style_params_shape_and_num(cls, num_feature_maps, num_styles):
+        num_style_params = cls.NumParamsPerFeature * num_feature_maps
+        return (1, num_styles, num_style_params), num_style_params
+
+    @classmethod
+    def get_style_weights_shape(cls, content_shape: typing.Tuple, num_styles, multiplier=1) -> typing.Tuple:
+        shape = list(content_shape)
+        shape[-1] = num_styles
+        shape[-2] *= multiplier
+        shape[-3] *= multiplier
+        return tuple(shape)
+
+
+def calc_next_conv_dims(initial, filters, mult) -> typing.Tuple:
+    if len(initial) == 3:
+        return (int(initial[0] * mult), int(initial[1] * mult), filters)
+    return (initial[0], initial[1] * mult, initial[2] * mult, filters)
+
+
+class StyleTransferModel(NativeModel):
+    """Object returned by create_style_transfer_model; inputs dict {'content','style_params'[,'style_weights']}."""
+
+    def __init__(self, plan: TransferPlan, name: str, seed=None):
+        super().__init__(name)
+        self.plan = plan
+        self.num_style_parameters = plan.num_style_parameters
+        self._variables = plan.initial_weights(np.random.default_rng(seed))
+        self.input = {
+            "content": InputSpec(plan.input_shape, "content"),
+            "style_params": InputSpec((plan.num_styles, plan.num_style_parameters), "style_params"),
+        }
+        if plan.num_styles > 1:
+            self.input["style_weights"] = InputSpec(
+                ConditionalInstanceNormalization.get_style_weights_shape(plan.output_shape, plan.num_styles - 1),
+                "style_weights")
+        self.inputs = self.input
+        self.output_shape = (None,) + plan.output_shape
+
+    def _context_kwargs(self, max_batch):
+        p = self.plan
+        return dict(in_shape=p.input_shape, out_shape=p.output_shape, bottleneck_res_y=p.bottleneck_res_y,
+                    bottleneck_num_filters=p.filters, num_styles=p.num_styles)
+
+    def _check_inputs(self, inputs):
+        content = inputs["content"]
+        params = inputs["style_params"]
+        if tuple(content.shape[1:]) != self.plan.input_shape:
+            raise ValueError(f"content shape {tuple(content.shape)} incompatible with {self.input['content'].shape}")
+        if tuple(params.shape[1:]) != (self.plan.num_styles, self.num_style_parameters):
+            raise ValueError(f"style_params shape {tuple(params.shape)} incompatible with "
+                             f"{self.input['style_params'].shape}")
+        weights = inputs.get("style_weights") if self.plan.num_styles > 1 else None
+        if self.plan.num_styles > 1:
+            if weights is None:
+                raise ValueError("style_weights input required when num_styles > 1")
+            expect = self.plan.output_shape[:2] + (self.plan.num_styles - 1,)
+            assert tuple(weights.shape[1:]) == expect, \
+                f"Style weights must be the same dimensions as the output shape. {tuple(weights.shape)} vs. {expect}"
+        return content, params, weights
+
+    def __call__(self, inputs, training=False):
+        """numpy in -> numpy out (host path); torch CUDA tensors in -> torch CUDA tensor out (device path)."""
+        content, params, weights = self._check_inputs(inputs)
+        if _is_torch_cuda(content):
+            import torch
+            b = content.shape[0]
+            ctx = self._get_ctx(b)
+            content = content.contiguous().float()
+            params = params.contiguous().float().to(content.device)
+            weights = weights.contiguous().float().to(content.device) if weights is not None else None
+            out = torch.empty((b,) + self.plan.output_shape, dtype=torch.float32, device=content.device)
+            ctx.transfer_forward_device(content.data_ptr(), params.data_ptr(),
+                                        weights.data_ptr() if weights is not None else None, out.data_ptr(), b,
+                                        torch.cuda.current_stream(content.device).cuda_stream)
+            return out
+        return self.predict(inputs)
+
+    def predict(self, x, batch_size=None, verbose=0, **kwargs):
+        content, params, weights = self._check_inputs(x)
+        content, params = as_numpy(content), as_numpy(params)
+        weights = as_numpy(weights) if weights is not None else None
+        n = content.shape[0]
+        step = n if not batch_size else int(batch_size)
+        ctx = self._get_ctx(min(step, n) if n else 1)
+        outs = []
+        for i in range(0, n, max(step, 1)):
+            outs.append(ctx.transfer_forward_host(content[i:i + step], params[i:i + step],
+                                                  weights[i:i + step] if weights is not None else None))
+        if not outs:
+            return np.zeros((0,) + self.plan.output_shape, np.float32)
+        return np.concatenate(outs, axis=0) if len(outs) > 1 else outs[0]
+
+
+def create_style_transfer_model(input_shape, output_shape, bottleneck_res_y, bottleneck_num_filters, num_styles,
+                                name="StyleTransferModel"):
+    log.info(f"Using {num_styles} styles")
+    plan = TransferPlan(input_shape, output_shape, bottleneck_res_y, bottleneck_num_filters, num_styles)
+    log.info(f"Contracting with {plan.num_contract_blocks} blocks to "
+             f"{plan.bottleneck_hw[1]}x{plan.bottleneck_hw[0]}x{bottleneck_num_filters}")
+    log.info(f"expanding with {plan.num_expand_blocks} blocks to "
+             f"{output_shape[1]}x{output_shape[0]}x{output_shape[2]}")
+    model = StyleTransferModel(plan, name)
+    return model, plan.num_style_parameters

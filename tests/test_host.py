@@ -1,0 +1,201 @@
+"""CPU tests of the host-side mirror of the reference surface and of the C-ABI library's exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import realtime_style_transfer_b200 as rst
+from realtime_style_transfer_b200 import _native, mixed_precision
+from realtime_style_transfer_b200._plan import PredictorPlan, TransferPlan
+from realtime_style_transfer_b200.models import (stylePrediction, styleTransfer, styleTransferInferenceModel,
+                                                 styleTransferTrainingModel, styleLoss)
+from realtime_style_transfer_b200.shape_config import ShapeConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- ShapeConfig (shape_config.py:4-84) -------------------------------------------------------
+def test_shape_config_defaults_match_reference():
+    c = ShapeConfig()
+    assert c.num_styles == 1 and c.bottleneck_res_y == 120 and c.bottleneck_num_filters == 128
+    assert c.num_channels == 18 and c.output_shape == (480, 960, 3) and c.image_shape == (480, 960, 3)
+    assert c.input_shape == {"content": (480, 960, 18), "style": (1, 480, 960, 3)}
+    assert c.style_feature_extractor_type == stylePrediction.StyleFeatureExtractor.MOBILE_NET
+    assert c.with_depth_loss is True
+
+
+@pytest.mark.parametrize("n,names", [
+    (3, ["FinalImage"]),
+    (6, ["FinalImage", "BaseColor"]),
+    (17, ["FinalImage", "BaseColor", "AmbientOcclusion", "Metallic", "Specular", "Roughness", "ViewNormal",
+          "SceneDepth", "LightingModel"]),
+    (18, ["FinalImage", "BaseColor", "ShadowMask", "AmbientOcclusion", "Metallic", "Specular", "Roughness",
+          "ViewNormal", "SceneDepth", "LightingModel"]),
+])
+def test_channel_table(n, names):
+    c = ShapeConfig(num_channels=n)
+    assert [p[0] for p in c.channels] == names
+    assert c.num_channels == n == sum(p[1] for p in c.channels)
+
+
+def test_from_spec_and_sdr_and_two_styles():
+    c = ShapeConfig.from_spec("rst-960-120-128-17")
+    assert c.input_shape["content"] == (480, 960, 17) and c.spec() == "rst-960-120-128-17"
+    c = ShapeConfig.from_spec("rst-960-120-32-3", num_styles=2, hdr=False)
+    assert c.input_shape["content"] == (480, 960, 3)
+    assert c.input_shape["style"] == (2, 480, 960, 3) and c.input_shape["style_weights"] == (480, 960, 1)
+    c = ShapeConfig.from_spec("rst-1920-120-128-18")
+    assert c.output_shape == (960, 1920, 3)
+    el, gt = ShapeConfig(num_styles=2).get_dummy_input_element()
+    assert el["content"].shape == (1, 480, 960, 18) and el["style_weights"].shape == (1, 480, 960, 1)
+    assert gt["style"].shape == (1, 2, 480, 960, 3)
+
+
+# ---- plan / factories -------------------------------------------------------------------------
+def test_transfer_plan_geometries_of_the_reference_tests():
+    p = TransferPlan((480, 960, 17), (480, 960, 3), 120, 128, 1)
+    assert (p.num_contract_blocks, p.num_expand_blocks, p.num_style_parameters) == (2, 2, 2662)
+    p = TransferPlan((480, 960, 3), (1920, 3840, 3), 120, 128, 2)       # styleTransferInferenceModelTest.py:18-44
+    assert (p.num_contract_blocks, p.num_expand_blocks) == (2, 4)
+    p = TransferPlan((240, 480, 3), (480, 960, 3), 30, 4, 1)            # styleTransferTrainingModelTest.py:15-44
+    assert (p.num_contract_blocks, p.num_expand_blocks) == (3, 4)
+    v = TransferPlan((480, 960, 17), (480, 960, 3), 120, 128, 1).variables()
+    assert v["contract_start/conv/kernel"] == (9, 9, 17, 32)
+    assert v["residual_block_0/conv0/kernel"] == (3, 3, 32, 128)
+    assert v["expand_0/conv/kernel"] == (3, 3, 32, 128) and v["expand_last/conv/kernel"] == (9, 9, 3, 16)
+    assert sum(int(np.prod(s)) for s in v.values()) == 1464019 + 320
+
+
+def test_plans_agree_with_oracle_registry():
+    from oracle import rst_oracle as O
+    for args in [((480, 960, 17), (480, 960, 3), 120, 128, 1), ((240, 480, 3), (480, 960, 3), 30, 4, 1)]:
+        assert dict(TransferPlan(*args).variables()) == O.TransferSpec(*args).weight_shapes()
+    for ext in ("DUMMY", "MOBILE_NET"):
+        assert dict(PredictorPlan((480, 960, 3), ext, 742).variables()) == O.predictor_weight_shapes(ext, 742)
+
+
+def test_factories_keep_reference_signatures():
+    cfg = ShapeConfig.from_spec("rst-960-120-32-3", num_styles=2)
+    models = styleTransferInferenceModel.make_style_transfer_inference_model(
+        num_styles=cfg.num_styles,
+        style_predictor_factory_func=lambda n: stylePrediction.create_style_prediction_model(
+            cfg.input_shape["style"][1:], stylePrediction.StyleFeatureExtractor.DUMMY, n),
+        style_transfer_factory_func=lambda: styleTransfer.create_style_transfer_model(
+            cfg.input_shape["content"], cfg.output_shape, cfg.bottleneck_res_y, cfg.bottleneck_num_filters,
+            cfg.num_styles))
+    assert set(models.inputs) == {"content", "style", "style_weights"}
+    assert models.inference.output_shape == (None, 480, 960, 3)
+    assert models.transfer.input["style_params"].shape == (None, 2, 742)
+    assert models.inference.input["style"].shape == (None, 2, 480, 960, 3)
+    assert models.style_predictor.output_shape == (None, 742)
+    models.inference.trainable = False
+    models.inference.compile(run_eagerly=False)
+    with pytest.raises(ValueError):
+        stylePrediction.create_style_prediction_model((480, 960, 3), "NOT_AN_EXTRACTOR", 10)
+
+
+def test_initialisers_follow_reference():
+    m, _ = styleTransfer.create_style_transfer_model((480, 960, 3), (480, 960, 3), 120, 32, 1)
+    w = m.weights
+    res = w["residual_block_2/conv1/kernel"]
+    assert res.min() >= 0 and res.max() <= 0.05 and abs(res.mean() - 0.025) < 2e-3     # U(0, 0.05)
+    assert abs(w["contract_0/conv/kernel"].std() - 0.02) < 2e-3                          # N(0, 0.02)
+    assert not w["expand_last/conv/bias"].any() and (w["contract_1/bn/gamma"] == 1).all()
+    sp = stylePrediction.create_style_prediction_model((480, 960, 3), "DUMMY", 742)
+    assert (sp.weights["StylePredictor/bias"] == 0.5).all()
+    lim = np.sqrt(1.0 / 742)
+    assert np.abs(sp.weights["StyleNormPredictor/kernel"]).max() <= lim + 1e-7
+
+
+def test_set_weights_and_npz_roundtrip(tmp_path):
+    m, _ = styleTransfer.create_style_transfer_model((32, 64, 3), (32, 64, 3), 8, 4, 1)
+    new = {k: np.full_like(v, 0.25) for k, v in m.weights.items()}
+    m.set_weights(new)
+    path = m.save_weights(str(tmp_path / "w"))
+    m2, _ = styleTransfer.create_style_transfer_model((32, 64, 3), (32, 64, 3), 8, 4, 1)
+    status = m2.load_weights(path)
+    status.assert_nontrivial_match().assert_consumed()
+    assert all((m2.weights[k] == 0.25).all() for k in new)
+    with pytest.raises(ValueError):
+        m.set_weights({"contract_start/conv/kernel": np.zeros((3, 3, 3, 3), np.float32)})
+    with pytest.raises(ValueError):
+        m.set_weights({"nope": np.zeros(1, np.float32)})
+
+
+def test_style_param_stack_and_helpers():
+    stack = styleTransfer.StyleParamStack(np.arange(20).reshape(1, 1, 1, 20), None)
+    assert stack.get_params(4).tolist() == [[[[0, 1, 2, 3]]]]
+    assert stack.make_content_and_style_input("c", 6)["style_params"].shape == (1, 1, 1, 6)
+    assert stack.lower_bound == 10
+    cin = styleTransfer.ConditionalInstanceNormalization
+    assert cin.get_style_params_shape_and_num(128, 2) == ((1, 2, 256), 256)
+    assert cin.get_style_weights_shape((120, 240, 128), 2, multiplier=2) == (240, 480, 2)
+    assert styleTransfer.calc_next_conv_dims((480, 960, 17), 32, 0.25) == (120, 240, 32)
+
+
+def test_training_factory_and_loss_guards():
+    loss_model = styleLoss.StyleLossModelVGG((480, 960, 3))
+    assert loss_model.content_loss_factor == 1e4 and loss_model.style_loss_factor == 1e-3
+    assert loss_model.style_layers == ['block1_conv2', 'block2_conv2', 'block3_conv3', 'block4_conv3']
+    with pytest.raises(AssertionError):
+        styleLoss.make_style_loss_function(loss_model, (480, 960, 3), 2, with_depth_loss=False)
+    tm = styleTransferTrainingModel.make_style_transfer_training_model(
+        style_predictor_factory_func=lambda n: stylePrediction.create_style_prediction_model((480, 960, 3), "DUMMY", n),
+        style_transfer_factory_func=lambda: styleTransfer.create_style_transfer_model((240, 480, 3), (480, 960, 3), 30,
+                                                                                      4, num_styles=1),
+        style_loss_func_factory_func=lambda: styleLoss.make_style_loss_function(loss_model, (480, 960, 3), 1,
+                                                                                with_depth_loss=False))
+    assert tm.inference.output_shape == (None, 480, 960, 3)
+
+
+def test_mixed_precision_policy():
+    mixed_precision.set_global_policy("mixed_bfloat16")
+    assert mixed_precision.native_precision() == _native.PRECISION_BF16
+    mixed_precision.set_global_policy("float32")
+    assert mixed_precision.native_precision() == _native.PRECISION_FP32
+    with pytest.raises(ValueError):
+        mixed_precision.set_global_policy("float16")
+
+
+# ---- the C-ABI library ------------------------------------------------------------------------
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rst_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rst_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_native.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rst_b200.h but not exported"
+    assert sorted(_native.SIGNATURES) == declared, "ctypes signature table out of sync with the header"
+    lib.rst_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.rst_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m, p = styleTransfer.create_style_transfer_model((32, 64, 3), (32, 64, 3), 8, 4, 1)
+    with pytest.raises(_native.RstError):
+        m.predict({"content": np.zeros((1, 32, 64, 3), np.float32), "style_params": np.zeros((1, 1, p), np.float32)})
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, include or dlopen it."""
+    pkg = os.path.join(ROOT, "realtime_style_transfer_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|#include\s+[\"<][^\n]*oracle|oracle[/\\.]_ref|import_module\([^)]*oracle",
+                     re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), f"{f} reaches into oracle/"

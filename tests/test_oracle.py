@@ -1,0 +1,165 @@
+"""CPU tests of the oracle itself: golden vectors, an independent numpy restatement, shapes."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import naive_np, rst_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_known_answer_apply_style_weights():
+    """The reference's only numeric test (styleTransferTest.py:28-49): 7-decimal agreement."""
+    g = np.load(os.path.join(GOLDEN, "apply_style_weights_known_answer.npz"))
+    got = O.apply_style_weights(torch.as_tensor(g["style_weights"]), torch.as_tensor(g["style_params"])).numpy()
+    assert got.shape == (2, 10, 20, 6)
+    np.testing.assert_almost_equal(got, g["expected"], decimal=7)
+    # weights in the reference test deliberately leave [0,1]: no clamping / normalisation may happen
+    assert g["style_weights"].max() > 1.0 and g["style_weights"].min() < 0.0
+
+
+def test_apply_style_weights_passthrough_single_style():
+    p = torch.rand(2, 1, 1, 6)
+    assert O.apply_style_weights(None, p) is p
+
+
+def test_golden_tiny_transfer_is_stable():
+    g = np.load(os.path.join(GOLDEN, "tiny_transfer_fp64.npz"))
+    spec = O.TransferSpec((16, 32, 5), (16, 32, 3), 4, 8, 2)
+    weights = {k[3:]: g[k] for k in g.files if k.startswith("w::")}
+    out = O.transfer_forward(spec, weights, g["content"], g["style_params"], g["style_weights"],
+                             dtype=torch.float64).numpy()
+    np.testing.assert_allclose(out, g["output"], rtol=0, atol=1e-12)
+    out32 = O.transfer_forward(spec, weights, g["content"], g["style_params"], g["style_weights"]).numpy()
+    assert np.abs(out32 - g["output"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("h,w,k,s", [(6, 8, 3, 1), (6, 8, 3, 2), (7, 9, 3, 2), (12, 10, 9, 1), (10, 10, 9, 5),
+                                     (8, 6, 5, 2)])
+def test_conv_same_matches_naive(h, w, k, s):
+    rng = np.random.default_rng(h * 100 + k)
+    x = rng.standard_normal((2, h, w, 3)).astype(np.float32)
+    kern = rng.standard_normal((k, k, 3, 4)).astype(np.float32)
+    b = rng.standard_normal(4).astype(np.float32)
+    ref = naive_np.conv2d_same(x, kern, b, s)
+    got = O.conv2d_same(torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(kern, dtype=torch.float64),
+                        torch.as_tensor(b, dtype=torch.float64), s).numpy()
+    assert got.shape == ref.shape == (2, -(-h // s), -(-w // s), 4)
+    np.testing.assert_allclose(got, ref, atol=1e-10)
+
+
+@pytest.mark.parametrize("h,w,k,s", [(5, 6, 3, 2), (4, 4, 9, 1), (6, 5, 3, 1), (3, 4, 5, 2)])
+def test_conv_transpose_same_matches_naive(h, w, k, s):
+    rng = np.random.default_rng(h * 10 + k)
+    x = rng.standard_normal((2, h, w, 4)).astype(np.float32)
+    kern = rng.standard_normal((k, k, 3, 4)).astype(np.float32)     # (kh,kw,out,in)
+    b = rng.standard_normal(3).astype(np.float32)
+    ref = naive_np.conv2d_transpose_same(x, kern, b, s)
+    got = O.conv2d_transpose_same(torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(kern, dtype=torch.float64),
+                                  torch.as_tensor(b, dtype=torch.float64), s).numpy()
+    assert got.shape == ref.shape == (2, h * s, w * s, 3)
+    np.testing.assert_allclose(got, ref, atol=1e-10)
+
+
+def test_conv_transpose_is_gradient_of_conv():
+    """TF defines Conv2DTranspose as the input-gradient of Conv2D with the same padding."""
+    torch.manual_seed(0)
+    x = torch.randn(1, 8, 10, 3, dtype=torch.float64, requires_grad=True)     # forward-conv input (2H,2W,out)
+    kern = torch.randn(3, 3, 3, 5, dtype=torch.float64)                       # fwd conv: in=3, out=5
+    y = O.conv2d_same(x, kern, None, 2)                                       # (1,4,5,5)
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    # Conv2DTranspose kernel layout (kh,kw,out,in) == forward kernel (kh,kw,in_fwd,out_fwd)
+    got = O.conv2d_transpose_same(gy, kern, None, 2)
+    np.testing.assert_allclose(got.numpy(), gx.numpy(), atol=1e-10)
+
+
+def test_cin_matches_naive_and_normalises():
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((2, 6, 7, 5)) * 3 + 10).astype(np.float32)
+    scale = rng.standard_normal((2, 1, 1, 5)).astype(np.float32)
+    bias = rng.standard_normal((2, 1, 1, 5)).astype(np.float32)
+    ref = naive_np.cin(x, scale, bias)
+    got = O.cin(torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(scale, dtype=torch.float64),
+                torch.as_tensor(bias, dtype=torch.float64)).numpy()
+    np.testing.assert_allclose(got, ref, atol=1e-9)
+    unit = O.cin(torch.as_tensor(x, dtype=torch.float64), torch.ones(1, dtype=torch.float64),
+                 torch.zeros(1, dtype=torch.float64))
+    assert abs(float(unit.mean())) < 1e-9 and abs(float(unit.var(dim=(1, 2), unbiased=False).mean()) - 1) < 1e-4
+
+
+def test_gram_matches_naive():
+    x = np.random.default_rng(4).standard_normal((2, 5, 6, 7)).astype(np.float32)
+    np.testing.assert_allclose(O.gram_matrix(torch.as_tensor(x, dtype=torch.float64)).numpy(), naive_np.gram(x),
+                               atol=1e-10)
+
+
+def test_block_counts_keep_reference_float_expression():
+    # standard geometry and the reference tests' two other geometries
+    assert O.block_counts(480, 480, 120) == (2, 2)
+    assert O.block_counts(480, 1920, 120) == (2, 4)
+    assert O.block_counts(240, 480, 30) == (3, 4)
+    assert math.log2(480) - math.log2(120) < 2.0     # lands below the integer: ceil() is what makes it 2
+
+
+@pytest.mark.parametrize("spec_args,expected_p", [
+    (((480, 960, 17), (480, 960, 3), 120, 128, 1), 2662),
+    (((480, 960, 3), (480, 960, 3), 120, 32, 1), 742),
+    (((480, 960, 3), (1920, 3840, 3), 120, 128, 2), 20 * 128 + 2 * (32 + 16 + 8 + 4 + 3)),
+    (((240, 480, 3), (480, 960, 3), 30, 4, 1), 20 * 4 + 2 * (32 + 16 + 8 + 4 + 3)),
+])
+def test_num_style_parameters(spec_args, expected_p):
+    assert O.TransferSpec(*spec_args).num_style_parameters == expected_p
+
+
+def test_parameter_counts_match_survey():
+    spec = O.TransferSpec((480, 960, 17), (480, 960, 3), 120, 128, 1)
+    n = sum(int(np.prod(s)) for s in spec.weight_shapes().values())
+    assert n == 1464019 + 320
+    shapes = O.predictor_weight_shapes("MOBILE_NET", 2662)
+    body = sum(int(np.prod(s)) for k, s in shapes.items() if k.startswith("mobilenet/"))
+    assert body == 939120          # what Keras reports for MobileNetV3Small(include_top=False)
+    assert sum(int(np.prod(s)) for s in shapes.values()) - body == 326562
+
+
+def test_transfer_forward_shapes_and_range():
+    spec = O.TransferSpec((32, 64, 3), (64, 128, 3), 8, 4, 2)
+    assert (spec.n_contract, spec.n_expand) == (2, 3)
+    w = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(2, 32, 64, [("FinalImage", 3)])
+    params = np.random.default_rng(0).uniform(0.2, 1.0, (2, 2, spec.num_style_parameters)).astype(np.float32)
+    sw = O.synthetic_style_weights(2, 64, 128)
+    taps = {}
+    y = O.transfer_forward(spec, w, content, params, sw, taps=taps)
+    assert tuple(y.shape) == (2, 64, 128, 3) and y.dtype == torch.float32
+    assert float(y.min()) > 0 and float(y.max()) < 1
+    assert tuple(taps["contract_1"].shape) == (2, 8, 16, 32)
+    assert tuple(taps["expand_0"].shape) == (2, 16, 32, 32)
+
+
+def test_predictor_shapes():
+    w = O.init_predictor_weights("MOBILE_NET", 742)
+    x = np.random.default_rng(0).uniform(0, 1, (1, 64, 96, 3)).astype(np.float32)
+    W = {k: torch.as_tensor(v) for k, v in w.items()}
+    feat = O.mobilenet_v3_small(W, torch.as_tensor(x) * 2 - 1)
+    assert tuple(feat.shape) == (1, 2, 3, 576)
+    assert tuple(O.predictor_forward("MOBILE_NET", w, x).shape) == (1, 742)
+    wd = O.init_predictor_weights("DUMMY", 50)
+    assert tuple(O.predictor_forward("DUMMY", wd, x).shape) == (1, 50)
+    with pytest.raises(ValueError):
+        O.predictor_forward("NOPE", wd, x)
+
+
+def test_loss_is_per_sample_vector_and_zero_at_identity():
+    vgg = O.init_vgg16_weights()
+    img = np.random.default_rng(1).uniform(0, 1, (2, 32, 32, 3)).astype(np.float32)
+    out = O.style_loss_vgg(vgg, img, img, img[:, None])
+    assert tuple(out["loss"].shape) == (2,)
+    assert float(out["feature_loss"].abs().max()) == 0 and float(out["style_loss"].abs().max()) == 0
+    tv = O.total_variation(torch.as_tensor(img))
+    np.testing.assert_allclose(out["loss"].numpy(), 0.1 * tv.numpy(), rtol=1e-6)
+    with pytest.raises(AssertionError):
+        O.style_loss_vgg(vgg, img, img, np.stack([img, img], axis=1))
