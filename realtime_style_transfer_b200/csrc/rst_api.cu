@@ -881,6 +881,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
 
 extern "C" int rst_op_conv2d(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch, int h, int w,
                              int ci, int co, int kh, int kw, int stride, int transposed, int act, int precision, void* stream) {
+    if (batch == 0) return RST_OK;
     if (!d_x || !d_kernel || !d_y) return op_fail(RST_ERR_INVALID, "rst_op_conv2d: null tensor");
     if (batch < 0 || h <= 0 || w <= 0 || ci <= 0 || co <= 0 || kh <= 0 || kw <= 0 || stride <= 0)
         return op_fail(RST_ERR_INVALID, "rst_op_conv2d: bad dimension");
