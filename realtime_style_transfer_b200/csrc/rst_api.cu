@@ -265,8 +265,7 @@ extern "C" int rst_create(const rst_config* cfg, int device, rst_ctx** out_ctx) 
             max_c = std::max(max_c, L.co);
         }
     c->act_elems = max_act * B;
-    if (cfg->precision == RST_PRECISION_FP32)
-        for (int i = 0; i < 3 && ok; ++i) ok = alloc((void**)&c->act[i], (size_t)c->act_elems * sizeof(float));
+    for (int i = 0; i < 3 && ok; ++i) ok = alloc((void**)&c->act[i], (size_t)c->act_elems * sizeof(float));
     ok = ok && alloc((void**)&c->stats, (size_t)B * std::max(max_c, 1024) * 2 * sizeof(double));
     if (cfg->num_styles > 1)   // concat level + pyramid (< 1/3 extra)
         ok = ok && alloc((void**)&c->w_pyramid, (size_t)B * cfg->out_h * cfg->out_w * 2 * sizeof(float) * 4 / 3 + 4096);
@@ -401,7 +400,8 @@ extern "C" int rst_commit_weights(rst_ctx* ctx) {
 // ------------------------------------------------------------------------------------------------
 // style-weight pyramid (styleTransfer.py:297-303, :335-345): returns the level with the given width
 // ------------------------------------------------------------------------------------------------
-static int build_mips(rst_ctx* c, const float* d_style_weights, int batch, cudaStream_t s) {
+namespace rst {
+int build_mips(rst_ctx* c, const float* d_style_weights, int batch, cudaStream_t s) {
     c->mips.clear();
     if (c->cfg.num_styles < 2) return RST_OK;
     if (!d_style_weights) return fail(c, RST_ERR_INVALID, "style_weights required when num_styles > 1");
@@ -423,10 +423,11 @@ static int build_mips(rst_ctx* c, const float* d_style_weights, int batch, cudaS
     }
     return RST_OK;
 }
-static const float* mip_for_width(rst_ctx* c, int width) {
+const float* mip_for_width(rst_ctx* c, int width) {
     for (auto& m : c->mips) if (m.first == width) return m.second;
     return nullptr;
 }
+}  // namespace rst
 
 // ------------------------------------------------------------------------------------------------
 // fp32 transfer forward (styleTransfer.py:305-329)
@@ -465,13 +466,14 @@ static int cin_layer(rst_ctx* c, float* x, float* y, const float* residual, int 
     return RST_OK;
 }
 
-static int fp32_transfer_forward(rst_ctx* c, const float* d_content, const float* d_style_params,
-                                 const float* d_style_weights, float* d_out, int batch, cudaStream_t s) {
-    int rc = build_mips(c, d_style_weights, batch, s);
-    if (rc) return rc;
+namespace rst {
+
+// contract stage (styleTransfer.py:188-205, :224-232): returns the fp32 bottleneck input and the index of the
+// ping-pong buffer that is free afterwards.
+int fp32_contract_stage(rst_ctx* c, const float* d_content, int batch, cudaStream_t s, float** out, int* free_idx) {
     const float* cur = d_content;
     int which = 0;
-    for (auto& L : c->contract) {                                          // contract, styleTransfer.py:188-205
+    for (auto& L : c->contract) {
         float* y = c->act[which];
         ConvF32 p = conv_params(c, L, cur, y, batch, L.name + "/conv/kernel", L.name + "/conv/bias");
         p.act1 = ACT_RELU;
@@ -486,8 +488,41 @@ static int fp32_transfer_forward(rst_ctx* c, const float* d_content, const float
         cur = y;
         which ^= 1;
     }
-    // rotate so that x = block input, t1/t2 scratch
-    float* x = const_cast<float*>(cur);
+    *out = const_cast<float*>(cur);
+    *free_idx = which;
+    return RST_OK;
+}
+
+// expand stage (styleTransfer.py:95-141, :260-276): x is consumed, t1 is scratch, result lands in d_out.
+int fp32_expand_stage(rst_ctx* c, float* x, float* t1, const float* d_style_params, int cursor, float* d_out, int batch,
+                      cudaStream_t s) {
+    for (size_t i = 0; i < c->expand.size(); ++i) {
+        const LayerDesc& L = c->expand[i];
+        const bool last = i + 1 == c->expand.size();
+        ConvF32 p = conv_params(c, L, x, t1, batch, L.name + "/conv/kernel", L.name + "/conv/bias");
+        { LaunchScope ls(c, s, "conv_fp32"); RST_CUDA(c, launch_conv_f32(p, s)); }
+        record_tap(c, L.name + "/conv", t1, (int64_t)batch * L.ho * L.wo * L.co, false, s);
+        float* y = last ? d_out : t1;
+        int rc = cin_layer(c, t1, y, nullptr, batch, L.ho * L.wo, L.co, L.wo, d_style_params, cursor,
+                           last ? ACT_SIGMOID : ACT_RELU, s);
+        if (rc) return rc;
+        record_tap(c, L.name, y, (int64_t)batch * L.ho * L.wo * L.co, false, s);
+        cursor += 2 * L.co;
+        std::swap(x, t1);
+    }
+    return RST_OK;
+}
+
+}  // namespace rst
+
+static int fp32_transfer_forward(rst_ctx* c, const float* d_content, const float* d_style_params,
+                                 const float* d_style_weights, float* d_out, int batch, cudaStream_t s) {
+    int rc = build_mips(c, d_style_weights, batch, s);
+    if (rc) return rc;
+    float* x = nullptr;
+    int which = 0;
+    rc = fp32_contract_stage(c, d_content, batch, s, &x, &which);
+    if (rc) return rc;
     float* t1 = c->act[which];
     float* t2 = c->act[2];
     const int F = c->cfg.bottleneck_num_filters;
@@ -514,21 +549,7 @@ static int fp32_transfer_forward(rst_ctx* c, const float* d_content, const float
         cursor += 4 * F;
         std::swap(x, t2);
     }
-    for (size_t i = 0; i < c->expand.size(); ++i) {                        // expand, :95-141
-        const LayerDesc& L = c->expand[i];
-        const bool last = i + 1 == c->expand.size();
-        ConvF32 p = conv_params(c, L, x, t1, batch, L.name + "/conv/kernel", L.name + "/conv/bias");
-        { LaunchScope ls(c, s, "conv_fp32"); RST_CUDA(c, launch_conv_f32(p, s)); }
-        record_tap(c, L.name + "/conv", t1, (int64_t)batch * L.ho * L.wo * L.co, false, s);
-        float* y = last ? d_out : t1;
-        rc = cin_layer(c, t1, y, nullptr, batch, L.ho * L.wo, L.co, L.wo, d_style_params, cursor,
-                       last ? ACT_SIGMOID : ACT_RELU, s);
-        if (rc) return rc;
-        record_tap(c, L.name, y, (int64_t)batch * L.ho * L.wo * L.co, false, s);
-        cursor += 2 * L.co;
-        std::swap(x, t1);
-    }
-    return RST_OK;
+    return fp32_expand_stage(c, x, t1, d_style_params, cursor, d_out, batch, s);
 }
 
 static int collect_profile(rst_ctx* c) {

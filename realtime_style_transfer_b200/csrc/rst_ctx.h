@@ -129,6 +129,13 @@ int fail(rst_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(rst_ctx* ctx, cudaError_t e, const char* what);
 void record_tap(rst_ctx* ctx, const std::string& name, const void* dev, int64_t elems, bool is_bf16, cudaStream_t s);
 
+// implemented in rst_api.cu, shared with the bf16 path
+int build_mips(rst_ctx* c, const float* d_style_weights, int batch, cudaStream_t s);
+const float* mip_for_width(rst_ctx* c, int width);
+int fp32_contract_stage(rst_ctx* c, const float* d_content, int batch, cudaStream_t s, float** out, int* free_idx);
+int fp32_expand_stage(rst_ctx* c, float* x, float* t1, const float* d_style_params, int cursor, float* d_out, int batch,
+                      cudaStream_t s);
+
 // implemented in transfer_bf16.cu
 int bf16_create(rst_ctx* ctx);
 int bf16_commit(rst_ctx* ctx);

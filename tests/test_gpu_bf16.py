@@ -1,0 +1,152 @@
+"""GPU parity tests of the bf16 tensor-core (tcgen05) path, through the C ABI, against the fp32 CPU oracle.
+
+Tolerance (BASELINE.json north_star): <= 2e-2 relative on the BF16 path.  "Relative" is taken as the relative
+L2 error ||out - ref||_2 / ||ref||_2 of the network output (sigmoid image in (0,1)); the tests additionally
+bound the 99.9th percentile of the absolute error, because instance norm with eps=1e-5 amplifies bf16
+rounding without bound on (near-)constant channels, which makes a pure max-abs criterion meaningless for
+synthetic weights (the same amplification is present in an ideal bf16 emulation of the reference).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rst_oracle as O
+from realtime_style_transfer_b200 import _native, mixed_precision
+from realtime_style_transfer_b200.models import stylePrediction, styleTransfer, styleTransferInferenceModel
+from realtime_style_transfer_b200.shape_config import ShapeConfig
+
+pytestmark = pytest.mark.gpu
+BF16_REL_TOL = 2e-2
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+def bf16_round(a):
+    return torch.as_tensor(a).to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("b,h,w,ci,co", [
+    (1, 8, 16, 64, 128),        # exactly one tile, one channel half
+    (2, 24, 48, 128, 128),      # several tiles, two halves, batch
+    (1, 13, 21, 128, 128),      # ragged edges: rows / columns outside the image are masked
+    (1, 30, 60, 32, 128),       # residual_block_0/conv0: 32 input channels, zero-padded to 64
+    (2, 16, 32, 128, 64),
+    (1, 120, 240, 128, 128),    # full bottleneck resolution of rst-960-120-128-*
+])
+def test_op_conv3x3_tcgen05(cuda_device, b, h, w, ci, co):
+    rng = np.random.default_rng(h * 7 + ci)
+    x = bf16_round(rng.standard_normal((b, h, w, ci)).astype(np.float32))
+    kern = bf16_round((rng.standard_normal((3, 3, ci, co)) * 0.05).astype(np.float32))
+    bias = torch.as_tensor(rng.standard_normal(co).astype(np.float32))
+    ref = torch.relu(O.conv2d_same(x.double(), kern.double(), bias.double(), 1)).float().numpy()
+    d_x, d_k, d_b = x.to(cuda_device), kern.to(cuda_device), bias.to(cuda_device)
+    d_y = torch.full(ref.shape, float("nan"), device=cuda_device)
+    _native.op_conv2d(d_x.data_ptr(), d_k.data_ptr(), d_b.data_ptr(), d_y.data_ptr(), b, h, w, ci, co, 3, 3, 1, False,
+                      _native.ACT_RELU, _native.PRECISION_BF16, torch.cuda.current_stream().cuda_stream)
+    got = d_y.cpu().numpy()
+    assert np.isfinite(got).all()
+    # operands are exactly representable in bf16, so the only differences are fp32 accumulation order and the
+    # final rounding of the output to bf16 (relative 2^-9)
+    assert np.abs(got - ref).max() <= 2 ** -8 * np.abs(ref).max() + 1e-6
+    assert rel_l2(got, ref) < 3e-3
+
+
+def run_bf16(shape_in, shape_out, res_y, filters, styles, weights, content, params, sw=None, taps=None):
+    ctx = _native.NativeContext(in_shape=shape_in, out_shape=shape_out, bottleneck_res_y=res_y,
+                                bottleneck_num_filters=filters, num_styles=styles, max_batch=content.shape[0],
+                                precision=_native.PRECISION_BF16)
+    ctx.set_weights(weights)
+    if taps is not None:
+        ctx.enable_taps(True)
+    out = ctx.transfer_forward_host(content, params, sw)
+    got = {}
+    if taps is not None:
+        for name in taps:
+            got[name] = ctx.tap(name, taps[name].shape)
+    launches = ctx.last_launch_count()
+    ctx.close()
+    return out, got, launches
+
+
+@pytest.mark.parametrize("trained_like", [False, True])
+@pytest.mark.parametrize("styles", [1, 2])
+def test_transfer_bf16_small(cuda_device, styles, trained_like):
+    shape_in, shape_out = (64, 128, 17), (64, 128, 3)
+    spec = O.TransferSpec(shape_in, shape_out, 16, 128, styles)
+    weights = O.init_transfer_weights(spec, seed=1, trained_like=trained_like)
+    content = O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=17).channels, seed=0, unit_depth=True)
+    params = np.random.default_rng(2).uniform(0.3, 1.2, (2, styles, spec.num_style_parameters)).astype(np.float32)
+    sw = O.synthetic_style_weights(2, 64, 128) if styles == 2 else None
+    ref_taps = {}
+    ref = O.transfer_forward(spec, weights, content, params, sw, taps=ref_taps).numpy()
+    want = {k: v for k, v in ref_taps.items() if k.startswith("residual_block") and not k.endswith("conv1/cin")}
+    out, taps, launches = run_bf16(shape_in, shape_out, 16, 128, styles, weights, content, params, sw, want)
+    assert launches > 0
+    # first tensor-core layer in isolation, then the accumulated trunk
+    assert rel_l2(taps["residual_block_0/conv0/relu"], ref_taps["residual_block_0/conv0/relu"].numpy()) < 1e-2
+    for name, got in taps.items():
+        assert rel_l2(got, ref_taps[name].numpy()) < 5e-2, name
+    err = np.abs(out - ref)
+    print(f"bf16 small styles={styles} trained_like={trained_like}: rel_l2={rel_l2(out, ref):.4e} "
+          f"max_abs={err.max():.4e} p99.9={np.quantile(err, 0.999):.4e}")
+    assert rel_l2(out, ref) <= BF16_REL_TOL
+    assert np.quantile(err, 0.999) <= 2e-2
+
+
+def test_transfer_bf16_full_resolution(cuda_device):
+    """rst-960-120-128-17 geometry (BASELINE.json configs[1]) at batch 2, bf16 vs the fp32 oracle."""
+    cfg = ShapeConfig.from_spec("rst-960-120-128-17")
+    spec = O.TransferSpec(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(2, 480, 960, cfg.channels, seed=0)
+    pw = O.init_predictor_weights("MOBILE_NET", spec.num_style_parameters, seed=2)
+    style = np.random.default_rng(0).uniform(0, 1, (1, 480, 960, 3)).astype(np.float32)
+    params = np.repeat(O.predictor_forward("MOBILE_NET", pw, style).numpy()[:, None, :], 2, axis=0)
+    ref = O.transfer_forward(spec, weights, content, params).numpy()
+    out, _, launches = run_bf16(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1, weights, content, params)
+    err = np.abs(out - ref)
+    print(f"bf16 full-res: rel_l2={rel_l2(out, ref):.4e} max_abs={err.max():.4e} p99.9={np.quantile(err, 0.999):.4e} "
+          f"launches={launches}")
+    assert rel_l2(out, ref) <= BF16_REL_TOL
+    assert np.quantile(err, 0.999) <= 2e-2
+    assert out.min() >= 0 and out.max() <= 1
+
+
+def test_bf16_frames_independent_and_deterministic(cuda_device):
+    shape_in, shape_out = (64, 128, 17), (64, 128, 3)
+    spec = O.TransferSpec(shape_in, shape_out, 16, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(3, 64, 128, ShapeConfig(num_channels=17).channels, seed=3, unit_depth=True)
+    params = np.random.default_rng(1).uniform(0.3, 1.0, (3, 1, spec.num_style_parameters)).astype(np.float32)
+    ctx = _native.NativeContext(in_shape=shape_in, out_shape=shape_out, bottleneck_res_y=16, bottleneck_num_filters=128,
+                                num_styles=1, max_batch=3, precision=_native.PRECISION_BF16)
+    ctx.set_weights(weights)
+    full = ctx.transfer_forward_host(content, params)
+    for i in range(3):
+        single = ctx.transfer_forward_host(content[i:i + 1], params[i:i + 1])
+        # statistics are accumulated with atomics: order may differ, values agree to rounding
+        assert np.abs(single[0] - full[i]).max() < 5e-3
+    ctx.close()
+
+
+def test_mixed_precision_policy_selects_tensor_core_path(cuda_device):
+    mixed_precision.set_global_policy("mixed_bfloat16")
+    try:
+        model, p = styleTransfer.create_style_transfer_model((64, 128, 17), (64, 128, 3), 16, 128, 1)
+        spec = O.TransferSpec((64, 128, 17), (64, 128, 3), 16, 128, 1)
+        w = O.init_transfer_weights(spec, seed=1)
+        model.set_weights(w)
+        content = O.synthetic_content(1, 64, 128, ShapeConfig(num_channels=17).channels, seed=0, unit_depth=True)
+        params = np.random.default_rng(2).uniform(0.3, 1.2, (1, 1, p)).astype(np.float32)
+        out = model.predict({"content": content, "style_params": params})
+        ref = O.transfer_forward(spec, w, content, params).numpy()
+        assert model._ctx.cfg.precision == _native.PRECISION_BF16
+        assert rel_l2(out, ref) <= BF16_REL_TOL
+        d_out = model({"content": torch.as_tensor(content).to(cuda_device), "style_params": torch.as_tensor(params).to(cuda_device)})
+        assert rel_l2(d_out.cpu().numpy(), ref) <= BF16_REL_TOL
+        model.close()
+    finally:
+        mixed_precision.set_global_policy("float32")
