@@ -223,6 +223,7 @@ static void free_ctx(rst_ctx* c) {
     if (c->w_pyramid) cudaFree(c->w_pyramid);
     for (float* p : {c->st_content, c->st_params, c->st_weights, c->st_out, c->st_style}) if (p) cudaFree(p);
     for (auto& kv : c->taps) if (kv.second.dev) cudaFree(kv.second.dev);
+    for (auto e : c->event_pool) cudaEventDestroy(e);
     c->bf16.reset();
     c->train.reset();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -560,8 +561,8 @@ static int collect_profile(rst_ctx* c) {
         ProfileGroup& g = c->profile[std::get<0>(t)];
         g.total_ms += ms;
         g.launches += 1;
-        cudaEventDestroy(std::get<1>(t));
-        cudaEventDestroy(std::get<2>(t));
+        c->event_pool.push_back(std::get<1>(t));
+        c->event_pool.push_back(std::get<2>(t));
     }
     c->pending_events.clear();
     return RST_OK;

@@ -93,6 +93,13 @@ struct rst_ctx {
     bool profiling = false;
     std::map<std::string, rst::ProfileGroup> profile;
     std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> pending_events;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t take_event() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
 
     const rst::Weight* find_weight(const std::string& n) const {
         auto it = weight_index.find(n);
@@ -112,8 +119,8 @@ struct LaunchScope {
     LaunchScope(rst_ctx* c, cudaStream_t st, const char* g, int n = 1) : ctx(c), s(st), group(g) {
         ctx->launches += n;
         if (ctx->profiling) {
-            cudaEventCreate(&e0);
-            cudaEventCreate(&e1);
+            e0 = ctx->take_event();
+            e1 = ctx->take_event();
             cudaEventRecord(e0, s);
         }
     }
