@@ -1,0 +1,646 @@
+// tcgen05 / TMA halo-GEMM kernel (design notes in halo_gemm.cuh) and its bf16 elementwise companions.
+#include <mutex>
+
+#include "halo_gemm.cuh"
+
+namespace rst {
+
+using namespace umma;
+
+__device__ __forceinline__ float actf(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+// Every lane holds v[0..31] (32 columns of its row); afterwards lane j holds the sum over the 32 lanes of
+// column j.  31 shuffles instead of 160.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float send = upper ? v[i] : v[i + off];
+            float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+constexpr int kTailBytes = 6400;    // barriers (256) + per-column bias/scale/shift (3*N*4) + per-warp stats (4*2*N*4)
+constexpr int kMaxKsteps = 128;
+
+// MODE bits: what the epilogue does besides "+ bias" (compile-time so that the epilogue stays small: an epilogue
+// that does not fit the instruction cache is fetch-bound, see profiles/r01_01_icache.md)
+constexpr int MODE_RELU = 1;      // ReLU after the bias
+constexpr int MODE_POST = 2;      // then per-column affine (inference BatchNorm) and a second ReLU
+constexpr int MODE_F32 = 4;       // store fp32 instead of bf16
+
+template <int N, int ROWB, int EPI, int MODE>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const HaloGemmParams p) {
+    constexpr int BBLK = N * 128;                      // bytes of one B block (4 K-steps)
+    constexpr uint64_t SWZ = ROWB == 128 ? SWIZZLE_128B : SWIZZLE_64B;
+    constexpr int ROW_ELEMS = ROWB / 2;
+    constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+    constexpr int CW = N >= 32 ? 32 : 16;              // columns per epilogue chunk
+    constexpr int NCH = N / CW;
+    static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA_M=128 needs 16 <= N <= 256, N % 16 == 0");
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int halo_bytes = p.halo_h * p.halo_w * ROWB;
+    const int a_stage_bytes = (halo_bytes + 1023) & ~1023;
+    const int blocks_per_tile = p.n_groups * p.ksteps / 4;
+    const int nbslots = p.b_resident ? blocks_per_tile : p.n_bstages;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + p.n_astages * a_stage_bytes;
+    uint8_t* tail = sB + nbslots * BBLK;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + 8;
+    uint64_t* acc_full = b_empty + 8;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(tail + 256);
+    float* scale_s = bias_s + N;
+    float* shift_s = scale_s + N;
+    float* stat_s = shift_s + N;                       // [4 warps][2][N]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+    const int total_tiles = p.B * tiles_per_img;
+    const int tpc = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int tile_begin = blockIdx.x * tpc;
+    const int tile_end = min(total_tiles, tile_begin + tpc);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        bias_s[i] = p.bias ? p.bias[i] : 0.f;
+        scale_s[i] = p.post_scale ? p.post_scale[i] : 1.f;
+        shift_s[i] = p.post_shift ? p.post_shift[i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) stat_s[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= A producer: one halo patch per (tile, channel group) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = tile_begin; t < tile_end; ++t) {
+                const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+                const int h0 = (r / p.tiles_w) * 8, w0 = (r % p.tiles_w) * 16;
+                for (int g = 0; g < p.n_groups; ++g) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&a_full[stage], halo_bytes);
+                    tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 + p.ox, n);
+                    if (++stage == (uint32_t)p.n_astages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= B producer ===========================================================
+        if (lane == 0 && tile_begin < tile_end) {
+            if (p.b_resident) {
+                mbar_expect_tx(&b_full[0], blocks_per_tile * BBLK);
+                for (int kb = 0; kb < blocks_per_tile; ++kb) tma_load_2d(sB + kb * BBLK, &tmB, &b_full[0], 0, kb * N);
+            } else {
+                uint32_t stage = 0, phase = 0;
+                for (int t = tile_begin; t < tile_end; ++t) {
+                    for (int kb = 0; kb < blocks_per_tile; ++kb) {
+                        mbar_wait(&b_empty[stage], phase ^ 1);
+                        mbar_expect_tx(&b_full[stage], BBLK);
+                        tma_load_2d(sB + stage * BBLK, &tmB, &b_full[stage], 0, kb * N);
+                        if (++stage == (uint32_t)p.n_bstages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= MMA issuer (single thread) ===========================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, N);
+            // descriptors differ only in their 14-bit start-address field: build the constant part once
+            const uint64_t da_const = make_smem_desc(0, 16, p.halo_h * ROWB, SWZ);
+            const uint64_t db_const = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
+            if (p.b_resident && tile_begin < tile_end) mbar_wait(&b_full[0], 0);
+            for (int t = tile_begin; t < tile_end; ++t) {
+                mbar_wait(&acc_empty[cs], cph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + cs * N;
+                for (int g = 0; g < p.n_groups; ++g) {
+                    mbar_wait(&a_full[as], aph);
+                    tc_fence_after();
+                    const uint32_t a_base16 = smem_u32(sA + as * a_stage_bytes) >> 4;
+#pragma unroll 1
+                    for (int kb = 0; kb < p.ksteps / 4; ++kb) {
+                        uint32_t b_base16;
+                        if (p.b_resident) {
+                            b_base16 = smem_u32(sB + (g * (p.ksteps / 4) + kb) * BBLK) >> 4;
+                        } else {
+                            mbar_wait(&b_full[bs], bph);
+                            tc_fence_after();
+                            b_base16 = smem_u32(sB + bs * BBLK) >> 4;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = da_const | (uint64_t)(a_base16 + p.a_off16[kb * 4 + k]);
+                            const uint64_t db = db_const | (uint64_t)(b_base16 + k * 2);
+                            mma_f16_ss(tmem_d, da, db, idesc, (uint32_t)((g | kb | k) != 0));
+                        }
+                        if (!p.b_resident) {
+                            mma_commit(&b_empty[bs]);
+                            if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                    mma_commit(&a_empty[as]);
+                    if (++as == (uint32_t)p.n_astages) { as = 0; aph ^= 1; }
+                }
+                mma_commit(&acc_full[cs]);
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue ==============================================================
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int w_l = row >> 3, h_l = row & 7;
+        float* my_sum = stat_s + q * 2 * N;      // per-warp column accumulators (lane j owns column c*CW+j)
+        float* my_sq = my_sum + N;
+        const bool do_stats = p.stats != nullptr;
+        int cur_n = -1;
+        auto flush = [&]() {
+            if (do_stats && cur_n >= 0) {
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const int col = c * CW + lane;
+                    int ch = col;
+                    bool on = lane < CW;
+                    if (EPI == EPI_CONVT2) ch = col % p.stats_c;
+                    if (EPI == EPI_QUAD3) { ch = col % 3; on = on && col < 12; }
+                    if (lane < CW) {
+                        if (on) {
+                            double* dst = p.stats + ((size_t)cur_n * p.stats_c + ch) * 2;
+                            atomicAdd(dst, (double)my_sum[col]);
+                            atomicAdd(dst + 1, (double)my_sq[col]);
+                        }
+                        my_sum[col] = 0.f; my_sq[col] = 0.f;
+                    }
+                }
+            }
+        };
+        uint32_t cs = 0, cph = 0;
+        for (int t = tile_begin; t < tile_end; ++t) {
+            const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+            const int gh = (r / p.tiles_w) * 8 + h_l, gw = (r % p.tiles_w) * 16 + w_l;
+            const bool valid = gh < p.H && gw < p.WRU;
+            if (n != cur_n) { flush(); cur_n = n; }
+            mbar_wait(&acc_full[cs], cph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * N;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                float v[32];
+                if (CW == 32) tmem_ld_32x32(taddr + c * 32, v);
+                else {
+                    tmem_ld_32x16(taddr + c * 16, v);
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                }
+                tmem_ld_wait();
+                const float* bs_ = bias_s + c * CW;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    float x = v[j] + bs_[j];
+                    if (MODE & MODE_RELU) x = fmaxf(x, 0.f);
+                    if (MODE & MODE_POST) x = fmaxf(fmaf(x, scale_s[c * CW + j], shift_s[c * CW + j]), 0.f);
+                    v[j] = x;
+                }
+                if (MODE & MODE_F32) {
+                    if (valid) {
+                        float4* o4;
+                        if (EPI == EPI_QUAD3)
+                            o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (((size_t)n * p.out_H + gh) * p.out_W + 4 * gw) * 3);
+                        else
+                            o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW);
+                        constexpr int NV = EPI == EPI_QUAD3 ? 3 : CW / 4;
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) v[j] = 0.f;
+                    }
+                } else {
+                    // bf16 stores; statistics are taken on the values as stored
+                    uint32_t packed[CW / 2];
+#pragma unroll
+                    for (int j = 0; j < CW; j += 2) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                        packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                        v[j] = valid ? __low2float(h2) : 0.f;
+                        v[j + 1] = valid ? __high2float(h2) : 0.f;
+                    }
+                    if (valid) {
+                        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
+                        if (EPI == EPI_NHWC) {
+                            uint4* o4 = reinterpret_cast<uint4*>(yb + (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW);
+#pragma unroll
+                            for (int j = 0; j < CW / 8; ++j)
+                                o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        } else if (EPI == EPI_CONVT2) {
+                            // columns = phase*CQ + ch with CQ = N/4; a 32-column chunk holds 32/CQ phases
+                            constexpr int CQ = N / 4 >= 8 ? N / 4 : 8;
+                            constexpr int PER_CHUNK = CW / CQ > 0 ? CW / CQ : 1;
+#pragma unroll
+                            for (int sph = 0; sph < PER_CHUNK; ++sph) {
+                                const int phase = c * PER_CHUNK + sph;
+                                const int oy = 2 * gh + (phase >> 1), ox = 2 * gw + (phase & 1);
+                                uint4* o4 = reinterpret_cast<uint4*>(yb + (((size_t)n * p.out_H + oy) * p.out_W + ox) * CQ);
+#pragma unroll
+                                for (int j = 0; j < CQ / 8; ++j)
+                                    o4[j] = make_uint4(packed[sph * (CQ / 2) + 4 * j], packed[sph * (CQ / 2) + 4 * j + 1],
+                                                       packed[sph * (CQ / 2) + 4 * j + 2], packed[sph * (CQ / 2) + 4 * j + 3]);
+                            }
+                        }
+                    }
+                }
+                if (do_stats) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = warp_transpose_reduce(v, lane);
+                    const float s2 = warp_transpose_reduce(sq, lane);
+                    if (lane < CW) {
+                        my_sum[c * CW + lane] += s1;
+                        my_sq[c * CW + lane] += s2;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[cs]);
+            if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
+        flush();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmemBudget = 227 * 1024;
+
+bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err) {
+    if (p->ksteps % 4 != 0 || p->ksteps > kMaxKsteps || p->ksteps <= 0) {
+        if (err) *err = "halo_gemm: ksteps must be a positive multiple of 4, at most 128";
+        return false;
+    }
+    const int a_stage = (p->halo_h * p->halo_w * l->row_bytes + 1023) & ~1023;
+    const int bblk = l->N * 128;
+    const int blocks = p->n_groups * p->ksteps / 4;
+    const int fixed = 1024 + kTailBytes;
+    p->b_resident = (blocks * bblk + 2 * a_stage + fixed <= kSmemBudget) ? 1 : 0;
+    int b_bytes;
+    if (p->b_resident) {
+        b_bytes = blocks * bblk;
+    } else {
+        p->n_bstages = 6;
+        while (p->n_bstages > 2 && p->n_bstages * bblk + 2 * a_stage + fixed > kSmemBudget) --p->n_bstages;
+        b_bytes = p->n_bstages * bblk;
+    }
+    p->n_astages = 4;
+    while (p->n_astages > 1 && p->n_astages * a_stage + b_bytes + fixed > kSmemBudget) --p->n_astages;
+    if (!p->b_resident && p->n_astages > 3) p->n_astages = 3;
+    l->smem_bytes = (size_t)p->n_astages * a_stage + b_bytes + fixed;
+    if (l->smem_bytes > (size_t)kSmemBudget) {
+        if (err) *err = "halo_gemm: tile does not fit in shared memory";
+        return false;
+    }
+    return true;
+}
+
+template <int N, int ROWB, int EPI, int MODE>
+static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloGemmParams& p,
+                            int num_sms, cudaStream_t s) {
+    static size_t configured = 0;
+    if (configured < l.smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(halo_gemm_kernel<N, ROWB, EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)l.smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = l.smem_bytes;
+    }
+    const int total = p.B * p.tiles_h * p.tiles_w;
+    if (total == 0) return cudaSuccess;
+    const int grid = total < num_sms ? total : num_sms;
+    halo_gemm_kernel<N, ROWB, EPI, MODE><<<grid, kHaloThreads, l.smem_bytes, s>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             const HaloGemmParams& p, int num_sms, cudaStream_t s) {
+    const int mode = l.mode;
+#define RST_HALO_CASE(NN, RB, EP, MD) \
+    if (l.N == NN && l.row_bytes == RB && l.epi == EP && mode == (MD)) return launch_t<NN, RB, EP, (MD)>(l, tmA, tmB, p, num_sms, s);
+    RST_HALO_CASE(128, 128, EPI_NHWC, MODE_RELU)                          // bottleneck 3x3 convs (64-channel groups)
+    RST_HALO_CASE(128, 64, EPI_NHWC, MODE_RELU)                           // residual_block_0/conv0 (32 input channels)
+    RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU)
+    RST_HALO_CASE(64, 64, EPI_NHWC, MODE_RELU)
+    RST_HALO_CASE(32, 64, EPI_NHWC, MODE_RELU | MODE_POST | MODE_F32)     // 9x9 stem (16 real + 16 windowed channels)
+    RST_HALO_CASE(32, 128, EPI_NHWC, MODE_RELU | MODE_POST | MODE_F32)    // stem with 18 / 3 channels (64-element rows)
+    RST_HALO_CASE(128, 128, EPI_CONVT2, 0)                                // expand_0: 4 phases x 32 channels
+    RST_HALO_CASE(64, 64, EPI_CONVT2, 0)                                  // expand_1: 4 phases x 16 channels
+    RST_HALO_CASE(16, 128, EPI_QUAD3, MODE_F32)                           // expand_last: 4 pixels x 3 channels
+#undef RST_HALO_CASE
+    return cudaErrorInvalidValue;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+bool umma_init(std::string* err) {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    });
+    if (!g_encode && err) *err = "cuTensorMapEncodeTiled is not available from this driver";
+    return g_encode != nullptr;
+}
+
+// Dims ordered (C, H, WRU, B) so that a box enumerates rows (h) fastest among row units.
+bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, int C, int row_elems, int halo_h,
+                     int halo_w, std::string* err) {
+    if (!umma_init(err)) return false;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)WRU, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)WRU * C * 2, (cuuint64_t)C * 2, (cuuint64_t)H * WRU * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)halo_h, (cuuint32_t)halo_w, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUtensorMapSwizzle sw = row_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    if (row_elems != 64 && row_elems != 32) {
+        if (err) *err = "encode_halo_map: row must be 32 or 64 bf16 elements";
+        return false;
+    }
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled(activation) failed with code " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err) {
+    if (!umma_init(err)) return false;
+    cuuint64_t gdim[2] = {64, (cuuint64_t)nblocks * N};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)N};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out) {
+    const int nblocks = total_ksteps / 4;
+    out->assign((size_t)nblocks * N * 64, __float2bfloat16(0.f));
+    for (int ks = 0; ks < total_ksteps; ++ks)
+        for (int n = 0; n < N; ++n)
+            for (int e = 0; e < 16; ++e) {
+                float w = f(ks, n, e);
+                if (w != 0.f) (*out)[((size_t)(ks / 4) * N + n) * 64 + (ks % 4) * 16 + e] = __float2bfloat16(w);
+            }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 elementwise companions
+// ------------------------------------------------------------------------------------------------
+__global__ void f32_to_bf16_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long total, int c_in,
+                                       int c_out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % c_out);
+    long long pix = i / c_out;
+    y[i] = __float2bfloat16(c < c_in ? x[pix * c_in + c] : 0.f);
+}
+cudaError_t launch_f32_to_bf16_pad(const float* x, __nv_bfloat16* y, long long pixels, int c_in, int c_out, cudaStream_t s) {
+    long long total = pixels * c_out;
+    if (total == 0) return cudaSuccess;
+    f32_to_bf16_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, total, c_in, c_out);
+    return cudaGetLastError();
+}
+
+__global__ void bf16_to_f32_slice_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long total, int c_in,
+                                         int c_out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % c_out);
+    long long pix = i / c_out;
+    y[i] = __bfloat162float(x[pix * c_in + c]);
+}
+cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long pixels, int c_in, int c_out, cudaStream_t s) {
+    long long total = pixels * c_out;
+    if (total == 0) return cudaSuccess;
+    bf16_to_f32_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, total, c_in, c_out);
+    return cudaGetLastError();
+}
+
+// One thread per (pixel, 8-element slot group of the packed row).
+__global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C,
+                                       int n_real, int row_elems, long long total_slots) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_slots) return;
+    const int slots = row_elems / 8;
+    const int slot = (int)(i % slots);
+    const long long pix = i / slots;
+    const int px = (int)(pix % W);
+    const float* xp = x + pix * C;
+    float v[8];
+    const int e0 = slot * 8;
+    const int real_elems = n_real > 0 ? 16 : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int e = e0 + j;
+        float val = 0.f;
+        if (e < real_elems) {
+            if (e < n_real) val = xp[e];
+        } else {
+            const int g = (e - real_elems) / 16, t = (e - real_elems) % 16;   // virtual group g, horizontal tap t
+            const int ch = n_real + g;
+            if (ch < C && t < 9) {
+                const int sx = px + t - 4;
+                if (sx >= 0 && sx < W) val = xp[(long long)(t - 4) * C + ch];
+            }
+        }
+        v[j] = val;
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                         *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    reinterpret_cast<uint4*>(y)[i] = o;
+}
+cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
+                                   cudaStream_t s) {
+    long long total = (long long)B * H * W * (row_elems / 8);
+    if (total == 0) return cudaSuccess;
+    pack_stem_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, total);
+    return cudaGetLastError();
+}
+
+// Instance-norm apply, VEC channels per thread-iteration (8 for bf16 input, 4 or fewer for fp32 input).
+template <bool XF32, bool YF32>
+__global__ void __launch_bounds__(256) cin_apply_v_kernel(const CinApplyV p, int pix_per_block) {
+    extern __shared__ float smf[];
+    const int C = p.C;
+    float* s_inv = smf;
+    float* s_nmi = smf + C;
+    float* s_scale = smf + 2 * C;                    // [S][C]
+    float* s_bias = s_scale + p.num_styles * C;      // [S][C]
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sum = p.stats[((long long)n * C + c) * 2 + 0];
+        double sq = p.stats[((long long)n * C + c) * 2 + 1];
+        double mean = sum / (double)p.P;
+        double var = sq / (double)p.P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float inv = rsqrtf((float)var + p.eps);
+        s_inv[c] = inv;
+        s_nmi[c] = -(float)mean * inv;
+        for (int st = 0; st < p.num_styles; ++st) {
+            const float* ps = p.params + n * p.param_bstride + st * p.param_sstride;
+            s_scale[st * C + c] = ps[p.scale_off + c];
+            s_bias[st * C + c] = ps[p.bias_off + c];
+        }
+    }
+    __syncthreads();
+    const bool blend = p.num_styles == 2 && p.weights != nullptr;
+    if (XF32) {
+        // fp32 input (3-channel head): scalar path, one element per thread-iteration
+        const long long base = (long long)n * p.P * C;
+        const long long e0 = (long long)blockIdx.x * pix_per_block * C;
+        const long long e1 = min((long long)p.P * C, e0 + (long long)pix_per_block * C);
+        for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int c = (int)(e % C);
+            float scale = s_scale[c], bias = s_bias[c];
+            if (blend) {
+                const float2 w = *reinterpret_cast<const float2*>(p.weights + ((long long)n * p.P + e / C) * 2);
+                scale = s_scale[c] * w.x + s_scale[C + c] * w.y;
+                bias = s_bias[c] * w.x + s_bias[C + c] * w.y;
+            }
+            float xh = reinterpret_cast<const float*>(p.x)[base + e] * s_inv[c] + s_nmi[c];
+            float o = actf(bias + xh * scale, p.act);
+            if (YF32) reinterpret_cast<float*>(p.y)[base + e] = o;
+            else reinterpret_cast<__nv_bfloat16*>(p.y)[base + e] = __float2bfloat16(o);
+        }
+        return;
+    }
+    const int vec_per_pix = C >> 3;
+    const long long base = (long long)n * p.P * vec_per_pix;
+    const long long v0 = (long long)blockIdx.x * pix_per_block * vec_per_pix;
+    const long long v1 = min((long long)p.P * vec_per_pix, v0 + (long long)pix_per_block * vec_per_pix);
+    const uint4* x4 = reinterpret_cast<const uint4*>(p.x) + base;
+    const uint4* r4 = p.residual ? reinterpret_cast<const uint4*>(p.residual) + base : nullptr;
+    for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        const int c0 = (int)(v % vec_per_pix) * 8;
+        uint4 xin = x4[v];
+        uint4 rin = r4 ? r4[v] : make_uint4(0, 0, 0, 0);
+        float w0 = 1.f, w1 = 0.f;
+        if (blend) {
+            const long long pix = v / vec_per_pix;
+            const float2 w = *reinterpret_cast<const float2*>(p.weights + ((long long)n * p.P + pix) * 2);
+            w0 = w.x; w1 = w.y;
+        }
+        const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xin);
+        const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rin);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 xv = __bfloat1622float2(xb[j]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 2 * j + h;
+                float scale, bias;
+                if (blend) {
+                    scale = s_scale[c] * w0 + s_scale[C + c] * w1;
+                    bias = s_bias[c] * w0 + s_bias[C + c] * w1;
+                } else {
+                    scale = s_scale[c];
+                    bias = s_bias[c];
+                }
+                float xh = (h ? xv.y : xv.x) * s_inv[c] + s_nmi[c];
+                o[2 * j + h] = actf(bias + xh * scale, p.act);
+            }
+            if (r4) {
+                float2 rv = __bfloat1622float2(rb[j]);
+                o[2 * j] += rv.x; o[2 * j + 1] += rv.y;
+            }
+        }
+        if (YF32) {
+            float4* y4 = reinterpret_cast<float4*>(p.y) + (base + v) * 2;
+            y4[0] = make_float4(o[0], o[1], o[2], o[3]);
+            y4[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+            reinterpret_cast<uint4*>(p.y)[base + v] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                                 *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+    }
+}
+
+cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
+    if (p.B == 0 || p.P == 0) return cudaSuccess;
+    if (!p.x_f32 && p.C % 8 != 0) return cudaErrorInvalidValue;
+    if (p.x_f32 && p.residual) return cudaErrorInvalidValue;
+    int pix_per_block = max(1, 32768 / p.C);
+    dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
+    size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
+    if (p.x_f32 && p.y_f32) cin_apply_v_kernel<true, true><<<grid, 256, smem, s>>>(p, pix_per_block);
+    else if (p.x_f32) cin_apply_v_kernel<true, false><<<grid, 256, smem, s>>>(p, pix_per_block);
+    else if (p.y_f32) cin_apply_v_kernel<false, true><<<grid, 256, smem, s>>>(p, pix_per_block);
+    else cin_apply_v_kernel<false, false><<<grid, 256, smem, s>>>(p, pix_per_block);
+    return cudaGetLastError();
+}
+
+}  // namespace rst

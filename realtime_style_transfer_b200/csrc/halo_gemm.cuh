@@ -1,0 +1,102 @@
+// tcgen05 "halo GEMM": the one tensor-core kernel behind every convolution of the transfer network.
+//
+// A CTA tile is 128 GEMM rows = an 8-row x 16-"row unit" patch of the output grid (row index r = wru*8 + h).
+// A row unit (RU) is whatever one shared-memory row of the A operand holds: one pixel with 64 channels
+// (128 B, SWIZZLE_128B), one pixel with 32 channels (64 B, SWIZZLE_64B), or four adjacent pixels with 16
+// channels (128 B) for the 3-channel output head.
+//
+// The input patch including its halo is TMA-loaded ONCE per (tile, channel group) with out-of-bounds rows
+// zero-filled (= 'same' padding).  Every K-step (one tcgen05.mma, K = 16) reads its A operand through a
+// shared-memory descriptor whose start address is the halo base plus a per-K-step byte offset taken from a
+// small table: filter taps are shifted views of the same bytes, never copies.  (Verified on B200 with
+// tests/cuda/umma_probe.cu: the swizzle XOR is a function of the absolute shared-memory address, so starts
+// that are not 1024-byte aligned are legal with base_offset = 0.)
+//
+// B (weights) is pre-packed on the host as blocks of 4 K-steps: [block][N rows][4 x 16 bf16] (128 B rows,
+// SWIZZLE_128B, K-major).  Small layers keep all blocks resident in shared memory for the CTA's lifetime;
+// the 128->128 bottleneck convs stream them through a ring.
+//
+// Warp roles (224 threads): 0 = A TMA producer, 1 = B TMA producer, 2 = MMA issuer (one elected lane),
+// 3..6 = epilogue (TMEM -> registers -> global), two TMEM accumulator stages.
+#pragma once
+
+#include <functional>
+
+#include "rst_internal.cuh"
+#include "umma.cuh"
+
+namespace rst {
+
+enum HaloEpi : int {
+    EPI_NHWC = 0,     // out[n, gh, gw, col]                       (conv)
+    EPI_CONVT2 = 1,   // col = phase*Cq + c -> out[n, 2gh+a, 2gw+b, c] (stride-2 transposed conv as 4 phases)
+    EPI_QUAD3 = 2,    // col = j*3 + c (j<4) -> out[n, gh, 4gw+j, c]   (3-channel head, 4 pixels per row unit)
+};
+
+struct HaloGemmParams {
+    // output grid in rows / row units, tiling
+    int B = 0, H = 0, WRU = 0, tiles_h = 0, tiles_w = 0;
+    // A halo
+    int oy = 0, ox = 0;              // halo origin relative to the tile origin (rows, RUs)
+    int halo_h = 10, halo_w = 18;    // box extent (rows, RUs)
+    int n_groups = 1;                // halo loads per tile; group g loads channel coordinate g * row_elems
+    int ksteps = 0;                  // K-steps per group, multiple of 4
+    uint32_t a_off16[128] = {};      // [ksteps] A start offsets into the halo in 16-byte units (kernel-param / constant bank)
+    int b_resident = 0;
+    int n_astages = 3, n_bstages = 6;
+    // epilogue
+    void* y = nullptr; int y_f32 = 0;
+    int out_H = 0, out_W = 0, out_C = 0;
+    const float* bias = nullptr;         // [N] (already expanded to GEMM columns)
+    const float* post_scale = nullptr;   // [N] optional per-column affine after act1 (inference BatchNorm)
+    const float* post_shift = nullptr;
+    double* stats = nullptr;             // (B, stats_c, 2) [sum, sumsq] or null
+    int stats_c = 0;
+};
+
+constexpr int kHaloThreads = 224;
+constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4;
+
+struct HaloGemmLaunch {
+    int N = 128;            // GEMM N (output columns): 16, 32, 64 or 128
+    int row_bytes = 128;    // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    int epi = EPI_NHWC;
+    int mode = 0;           // HALO_MODE_* bits (compile-time epilogue variant)
+    size_t smem_bytes = 0;  // filled by halo_gemm_plan
+};
+
+// Chooses stage counts for the shared-memory budget and fills p.n_astages / p.n_bstages / l.smem_bytes.
+bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err);
+cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             const HaloGemmParams& p, int num_sms, cudaStream_t s);
+
+// ---- host helpers -------------------------------------------------------------------------------
+// Activation tensor (B, H, WRU, row_elems*n_groups) bf16 viewed for the halo box (row_elems, halo_h, halo_w, 1).
+bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, int C, int row_elems, int halo_h,
+                     int halo_w, std::string* err);
+// Packed weights: nblocks*N rows of 64 bf16; box = (64, N).
+bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err);
+// Packs B: f(kstep, n, e) -> weight of K-step `kstep`, output column n, K element e (0..15).
+void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out);
+
+// ---- bf16 elementwise companions ------------------------------------------------------------------
+cudaError_t launch_f32_to_bf16_pad(const float* x, __nv_bfloat16* y, long long pixels, int c_in, int c_out, cudaStream_t s);
+cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long pixels, int c_in, int c_out, cudaStream_t s);
+
+// Stem input packing: fp32 NHWC (C channels) -> bf16 rows of `row_elems`: [n_real real channels, zero padded to
+// 16 when n_real > 0][one 16-slot group per remaining channel c: x[y, x-4 .. x+4, c] then 7 zeros].
+cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
+                                   cudaStream_t s);
+
+// instance-norm apply: y = act(bias + (x-mean)*inv*scale) [+ residual]; x bf16 or fp32, y bf16 or fp32, C % vec == 0
+struct CinApplyV {
+    const void* x = nullptr; void* y = nullptr; const __nv_bfloat16* residual = nullptr;
+    int x_f32 = 0, y_f32 = 0;
+    const double* stats = nullptr; const float* params = nullptr;
+    long long param_bstride = 0, param_sstride = 0; int scale_off = 0, bias_off = 0;
+    const float* weights = nullptr;    // (B,P,2) or null
+    int B = 0, P = 0, C = 0, num_styles = 1, act = ACT_NONE; float eps = 1e-5f;
+};
+cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s);
+
+}  // namespace rst

@@ -1,212 +1,512 @@
-// RST_PRECISION_BF16 forward of the transfer network: residual bottleneck on tcgen05 tensor cores
-// (conv_umma.cu), instance-norm statistics fused into the conv epilogues, normalisation + style affine +
-// ReLU / skip-add as one bf16 pass per layer.  Encoder / decoder layers still run the fp32 kernels.
-#include "conv_umma.cuh"
+// RST_PRECISION_BF16 forward of the transfer network on tcgen05 tensor cores.
+//
+//   content fp32 --pack--> [16 real | 9-tap window of channel 16] bf16 rows
+//     -> stem 9x9 (halo GEMM, bias+ReLU+BatchNorm+ReLU epilogue)
+//     -> contract_0 / contract_1 (3x3 stride 2)                      [fp32 CUDA-core kernels for now]
+//     -> 10 bottleneck convs (halo GEMM; bias+ReLU+instance-norm statistics fused in the epilogue)
+//        each followed by ONE bf16 pass: normalise + style affine (+ReLU | + skip add)
+//     -> expand_0 / expand_1 (stride-2 transposed conv as a 2x2-tap GEMM over 4 output phases, stats fused)
+//     -> expand_last 9x9 (4 pixels per GEMM row, 12 of 16 columns used) -> normalise + sigmoid -> fp32 image
+#include "halo_gemm.cuh"
 #include "rst_ctx.h"
 
 namespace rst {
 
-struct TrunkLayer {
-    __nv_bfloat16* w_packed = nullptr;   // [half][tap][COUT][64] bf16, K-major
-    CUtensorMap tmB;
-    int nhalf = 1;
+// ------------------------------------------------------------------------------------------------
+// One convolution layer mapped onto the halo GEMM: packed weights, K-step table, tensor maps.
+// ------------------------------------------------------------------------------------------------
+struct HaloConv {
+    HaloGemmLaunch launch;
+    HaloGemmParams p;
+    CUtensorMap tmA, tmB;
+    __nv_bfloat16* w_packed = nullptr;
+    float* col_bias = nullptr;     // [N] bias expanded to GEMM columns
+    float* col_scale = nullptr;    // [N] optional post affine
+    float* col_shift = nullptr;
+    std::vector<uint32_t> a_off;
+    int total_ksteps = 0;          // n_groups * ksteps
+    int in_C = 0;                  // channels (bf16 elements per row unit) of the bound input tensor
+
+    ~HaloConv() {
+        for (void* q : {(void*)w_packed, (void*)col_bias, (void*)col_scale, (void*)col_shift})
+            if (q) cudaFree(q);
+    }
+
+    cudaError_t upload(const std::vector<__nv_bfloat16>& packed, const std::vector<float>& bias,
+                       const std::vector<float>* scale, const std::vector<float>* shift) {
+        cudaError_t e = cudaSuccess;
+        auto up = [&](void** dst, const void* src, size_t bytes) {
+            if (e != cudaSuccess) return;
+            if (!*dst) e = cudaMalloc(dst, bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        };
+        up((void**)&w_packed, packed.data(), packed.size() * 2);
+        up((void**)&col_bias, bias.data(), bias.size() * 4);
+        if (scale) up((void**)&col_scale, scale->data(), scale->size() * 4);
+        if (shift) up((void**)&col_shift, shift->data(), shift->size() * 4);
+        for (size_t i = 0; i < a_off.size() && i < 128; ++i) p.a_off16[i] = a_off[i] >> 4;
+        p.bias = col_bias;
+        p.post_scale = scale ? col_scale : nullptr;
+        p.post_shift = shift ? col_shift : nullptr;
+        return e;
+    }
+
+    // Bind the input tensor (B, H, WRU, in_C) and finish the launch plan.
+    bool bind_input(const void* x, int B, int H, int WRU, std::string* err) {
+        p.B = B; p.H = H; p.WRU = WRU;
+        p.tiles_h = ceil_div(H, 8); p.tiles_w = ceil_div(WRU, 16);
+        if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
+        if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
+        return halo_gemm_plan(&launch, &p, err);
+    }
+
+    cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s) {
+        HaloGemmParams q = p;
+        q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
+        return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
+    }
 };
 
+static void pad_ksteps(HaloConv* c) {
+    while (c->a_off.size() % 4) c->a_off.push_back(0);
+}
+
+// 3x3 stride-1 'same' conv, Keras kernel (3,3,ci,co).  ci <= 32 uses 64-byte rows, otherwise 64-channel groups.
+static void setup_conv3x3(HaloConv* c, int ci, int co, const float* k, const float* bias, int act,
+                          std::vector<__nv_bfloat16>* packed, std::vector<float>* col_bias) {
+    const int row_elems = ci <= 32 ? 32 : 64, rowb = row_elems * 2;
+    c->launch.N = co; c->launch.row_bytes = rowb; c->launch.epi = EPI_NHWC;
+    c->in_C = (ci + row_elems - 1) / row_elems * row_elems;
+    c->p.n_groups = c->in_C / row_elems;
+    c->p.oy = -1; c->p.ox = -1; c->p.halo_h = 10; c->p.halo_w = 18;
+    const int kper = row_elems / 16;
+    c->a_off.clear();
+    for (int tap = 0; tap < 9; ++tap)
+        for (int kk = 0; kk < kper; ++kk) c->a_off.push_back(((tap % 3) * 10 + tap / 3) * rowb + kk * 32);
+    const int real_ksteps = (int)c->a_off.size();
+    pad_ksteps(c);
+    c->p.ksteps = (int)c->a_off.size();
+    c->total_ksteps = c->p.n_groups * c->p.ksteps;
+    c->launch.mode = HALO_MODE_RELU; (void)act;
+    c->p.out_C = co; c->p.stats_c = co;
+    const int ksteps = c->p.ksteps;
+    pack_b_blocks(c->total_ksteps, co, [&](int ks, int n, int e) -> float {
+        const int g = ks / ksteps, l = ks % ksteps;
+        if (l >= real_ksteps) return 0.f;
+        const int tap = l / kper, cin = g * row_elems + (l % kper) * 16 + e;
+        return cin < ci ? k[((size_t)tap * ci + cin) * co + n] : 0.f;
+    }, packed);
+    col_bias->assign(bias, bias + co);
+}
+
+struct StemLayout { int n_real, n_virtual, row_elems; };
+static bool stem_layout(int C, StemLayout* L) {
+    if (C >= 16) { L->n_real = 16; L->n_virtual = C - 16; }
+    else if (C <= 4) { L->n_real = 0; L->n_virtual = C; }
+    else { L->n_real = C; L->n_virtual = 0; }
+    const int elems = (L->n_real ? 16 : 0) + 16 * L->n_virtual;
+    if (elems > 64) return false;
+    L->row_elems = elems <= 32 ? 32 : 64;
+    return true;
+}
+
+// 9x9 stride-1 'same' conv over packed rows [16 real | 16 per virtual channel], Keras kernel (9,9,C,co).
+static bool setup_stem(HaloConv* c, int C, int co, const float* k, const float* bias, const float* bn_scale,
+                       const float* bn_shift, std::vector<__nv_bfloat16>* packed, std::vector<float>* col_bias,
+                       std::vector<float>* col_scale, std::vector<float>* col_shift) {
+    StemLayout L;
+    if (!stem_layout(C, &L)) return false;
+    const int rowb = L.row_elems * 2;
+    c->launch.N = co; c->launch.row_bytes = rowb; c->launch.epi = EPI_NHWC;
+    c->in_C = L.row_elems; c->p.n_groups = 1;
+    c->p.oy = -4; c->p.ox = -4; c->p.halo_h = 16; c->p.halo_w = 24;
+    c->a_off.clear();
+    const int real_ksteps = L.n_real ? 81 : 0;
+    for (int t = 0; t < real_ksteps; ++t) c->a_off.push_back(((t % 9) * 16 + t / 9) * rowb);
+    const int virt_byte0 = L.n_real ? 32 : 0;
+    for (int v = 0; v < L.n_virtual; ++v)
+        for (int ky = 0; ky < 9; ++ky) c->a_off.push_back((4 * 16 + ky) * rowb + virt_byte0 + v * 32);
+    const int used = (int)c->a_off.size();
+    pad_ksteps(c);
+    c->p.ksteps = (int)c->a_off.size();
+    c->total_ksteps = c->p.ksteps;
+    c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST | HALO_MODE_F32;
+    c->p.out_C = co; c->p.stats_c = co;
+    pack_b_blocks(c->total_ksteps, co, [&](int ks, int n, int e) -> float {
+        if (ks >= used) return 0.f;
+        if (ks < real_ksteps) {
+            return e < L.n_real ? k[((size_t)ks * C + e) * co + n] : 0.f;      // ks == ky*9 + kx
+        }
+        const int v = (ks - real_ksteps) / 9, ky = (ks - real_ksteps) % 9, ch = L.n_real + v;
+        return e < 9 ? k[((size_t)(ky * 9 + e) * C + ch) * co + n] : 0.f;      // e == kx
+    }, packed);
+    col_bias->assign(bias, bias + co);
+    col_scale->assign(bn_scale, bn_scale + co);
+    col_shift->assign(bn_shift, bn_shift + co);
+    return true;
+}
+
+// Conv2DTranspose 3x3 stride 2 'same' (Keras kernel (3,3,co,ci)): out[2i+a, 2j+b] over the 2x2 input window
+// rows {i-1, i} x cols {j-1, j}; phase a uses ky = {d==1: a, d==0: a==0 ? 2 : none}.
+static void setup_convt2(HaloConv* c, int ci, int co, const float* k, const float* bias,
+                         std::vector<__nv_bfloat16>* packed, std::vector<float>* col_bias) {
+    const int row_elems = ci <= 32 ? 32 : 64, rowb = row_elems * 2;
+    c->launch.N = 4 * co; c->launch.row_bytes = rowb; c->launch.epi = EPI_CONVT2;
+    c->in_C = (ci + row_elems - 1) / row_elems * row_elems;
+    c->p.n_groups = c->in_C / row_elems;
+    c->p.oy = -1; c->p.ox = -1; c->p.halo_h = 9; c->p.halo_w = 17;
+    const int kper = row_elems / 16;
+    c->a_off.clear();
+    for (int tap = 0; tap < 4; ++tap)       // tap = dy*2 + dx
+        for (int kk = 0; kk < kper; ++kk) c->a_off.push_back(((tap % 2) * 9 + tap / 2) * rowb + kk * 32);
+    pad_ksteps(c);
+    c->p.ksteps = (int)c->a_off.size();
+    c->total_ksteps = c->p.n_groups * c->p.ksteps;
+    c->launch.mode = 0;
+    c->p.out_C = co; c->p.stats_c = co;
+    const int ksteps = c->p.ksteps;
+    auto tap_of = [](int phase_bit, int d) -> int { return d == 1 ? phase_bit : (phase_bit == 0 ? 2 : -1); };
+    pack_b_blocks(c->total_ksteps, 4 * co, [&](int ks, int n, int e) -> float {
+        const int g = ks / ksteps, l = ks % ksteps;
+        if (l >= 4 * kper) return 0.f;
+        const int tap = l / kper, dy = tap / 2, dx = tap % 2;
+        const int cin = g * row_elems + (l % kper) * 16 + e;
+        const int phase = n / co, o = n % co;
+        const int ky = tap_of(phase >> 1, dy), kx = tap_of(phase & 1, dx);
+        if (ky < 0 || kx < 0 || cin >= ci) return 0.f;
+        return k[((size_t)(ky * 3 + kx) * co + o) * ci + cin];
+    }, packed);
+    col_bias->resize(4 * co);
+    for (int n = 0; n < 4 * co; ++n) (*col_bias)[n] = bias[n % co];
+}
+
+// Conv2DTranspose 9x9 stride 1 'same', 16 -> 3 channels (Keras kernel (9,9,3,16)); a GEMM row is 4 adjacent
+// pixels (one 128-byte row unit), columns j*3+c for pixel j of the quad; window pixel kx' covers 4r-4+kx'.
+static void setup_head(HaloConv* c, const float* k, const float* bias, std::vector<__nv_bfloat16>* packed,
+                       std::vector<float>* col_bias) {
+    c->launch.N = 16; c->launch.row_bytes = 128; c->launch.epi = EPI_QUAD3;
+    c->in_C = 64; c->p.n_groups = 1;
+    c->p.oy = -4; c->p.ox = -1; c->p.halo_h = 16; c->p.halo_w = 18;
+    c->a_off.clear();
+    for (int dy = 0; dy < 9; ++dy)
+        for (int kx = 0; kx < 12; ++kx) c->a_off.push_back(((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32);
+    c->p.ksteps = (int)c->a_off.size();      // 108
+    c->total_ksteps = c->p.ksteps;
+    c->launch.mode = HALO_MODE_F32;
+    c->p.out_C = 3; c->p.stats_c = 3;
+    pack_b_blocks(c->total_ksteps, 16, [&](int ks, int n, int e) -> float {
+        if (n >= 12) return 0.f;
+        const int dy = ks / 12, kxp = ks % 12, j = n / 3, o = n % 3;
+        const int ky = 8 - dy, kx = j + 8 - kxp;
+        if (kx < 0 || kx > 8) return 0.f;
+        return k[((size_t)(ky * 9 + kx) * 3 + o) * 16 + e];
+    }, packed);
+    col_bias->assign(16, 0.f);
+    for (int n = 0; n < 12; ++n) (*col_bias)[n] = bias[n % 3];
+}
+
+// ------------------------------------------------------------------------------------------------
 struct Bf16State {
     int num_sms = 148;
-    int cin_pad = 64;                        // channels of the (zero-padded) bottleneck input
-    __nv_bfloat16 *b_in = nullptr, *bx = nullptr, *by = nullptr, *bz = nullptr;
-    CUtensorMap tm_in, tm_x, tm_z;
-    double* stats = nullptr;                 // [10][max_batch][F][2]
-    size_t stats_bytes = 0;
-    TrunkLayer layers[10];
+    bool tc_decoder = false;            // expand layers on tensor cores (standard 2-expand geometry)
+    StemLayout stem_layout{};
+    HaloConv stem, trunk[10], e0, e1, head;
+    __nv_bfloat16 *s_in = nullptr;      // packed stem input
+    __nv_bfloat16 *b_in = nullptr, *bx = nullptr, *by = nullptr, *bz = nullptr;   // bottleneck tensors
+    __nv_bfloat16 *ye0 = nullptr, *ze0 = nullptr, *ye1 = nullptr, *ze1 = nullptr;  // decoder tensors
+    float* ylast = nullptr;
+    double* stats = nullptr;            // [13][max_batch][F][2]
+    size_t stats_bytes = 0, stats_stride = 0;
     ~Bf16State() {
-        for (void* p : {(void*)b_in, (void*)bx, (void*)by, (void*)bz, (void*)stats}) if (p) cudaFree(p);
-        for (auto& l : layers) if (l.w_packed) cudaFree(l.w_packed);
+        for (void* q : {(void*)s_in, (void*)b_in, (void*)bx, (void*)by, (void*)bz, (void*)ye0, (void*)ze0, (void*)ye1,
+                        (void*)ze1, (void*)ylast, (void*)stats})
+            if (q) cudaFree(q);
     }
 };
 struct TrainState {};
 
 int bf16_create(rst_ctx* c) {
-    const int F = c->cfg.bottleneck_num_filters;
+    const rst_config& g = c->cfg;
+    const int F = g.bottleneck_num_filters;
     if (F != 64 && F != 128)
         return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: bottleneck_num_filters must be 64 or 128 (use the fp32 path otherwise)");
     std::string err;
     if (!umma_init(&err)) return fail(c, RST_ERR_CUDA, err);
     auto st = std::make_shared<Bf16State>();
+    if (!stem_layout(g.in_c, &st->stem_layout))
+        return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: more than 19 input channels are not supported by the stem packing");
     cudaDeviceProp prop;
     RST_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
     st->num_sms = prop.multiProcessorCount;
-    const int B = c->cfg.max_batch, H = c->bott_h, W = c->bott_w;
-    const int res_in = c->residual[0].ci;
-    st->cin_pad = (res_in + 63) / 64 * 64;
-    const int fpad = F;
-    const size_t px = (size_t)B * H * W;
-    RST_CUDA(c, cudaMalloc(&st->b_in, px * st->cin_pad * 2));
-    RST_CUDA(c, cudaMalloc(&st->bx, px * fpad * 2));
-    RST_CUDA(c, cudaMalloc(&st->by, px * F * 2));
-    RST_CUDA(c, cudaMalloc(&st->bz, px * fpad * 2));
-    RST_CUDA(c, cudaMemset(st->bx, 0, px * fpad * 2));
-    RST_CUDA(c, cudaMemset(st->bz, 0, px * fpad * 2));
-    st->stats_bytes = (size_t)10 * B * F * 2 * sizeof(double);
+    const size_t B = g.max_batch;
+    const size_t pin = B * g.in_h * g.in_w, pb = B * c->bott_h * c->bott_w;
+    RST_CUDA(c, cudaMalloc(&st->s_in, pin * st->stem_layout.row_elems * 2));
+    RST_CUDA(c, cudaMalloc(&st->b_in, pb * 32 * 2));
+    RST_CUDA(c, cudaMalloc(&st->bx, pb * F * 2));
+    RST_CUDA(c, cudaMalloc(&st->by, pb * F * 2));
+    RST_CUDA(c, cudaMalloc(&st->bz, pb * F * 2));
+    st->tc_decoder = c->n_expand == 2 && F == 128 && g.out_w % 64 == 0;
+    if (st->tc_decoder) {
+        const size_t p1 = pb * 4, p2 = pb * 16;
+        RST_CUDA(c, cudaMalloc(&st->ye0, p1 * 32 * 2));
+        RST_CUDA(c, cudaMalloc(&st->ze0, p1 * 32 * 2));
+        RST_CUDA(c, cudaMalloc(&st->ye1, p2 * 16 * 2));
+        RST_CUDA(c, cudaMalloc(&st->ze1, p2 * 16 * 2));
+        RST_CUDA(c, cudaMalloc(&st->ylast, p2 * 3 * 4));
+    }
+    st->stats_stride = B * F * 2;
+    st->stats_bytes = 13 * st->stats_stride * sizeof(double);
     RST_CUDA(c, cudaMalloc(&st->stats, st->stats_bytes));
-    if (!umma_encode_activation_map(&st->tm_in, st->b_in, B, H, W, st->cin_pad, &err)) return fail(c, RST_ERR_CUDA, err);
-    if (!umma_encode_activation_map(&st->tm_x, st->bx, B, H, W, fpad, &err)) return fail(c, RST_ERR_CUDA, err);
-    if (!umma_encode_activation_map(&st->tm_z, st->bz, B, H, W, fpad, &err)) return fail(c, RST_ERR_CUDA, err);
     c->bf16 = st;
     return RST_OK;
 }
 
-// Keras Conv2D kernel (3,3,ci,co) fp32 -> [half][tap][co][64] bf16 (zero padded input channels)
-static void pack_conv3x3(const std::vector<float>& k, int ci, int co, int nhalf, std::vector<__nv_bfloat16>* out) {
-    out->assign((size_t)nhalf * 9 * co * 64, __float2bfloat16(0.f));
-    for (int tap = 0; tap < 9; ++tap)
-        for (int i = 0; i < ci; ++i)
-            for (int o = 0; o < co; ++o) {
-                int half = i / 64, il = i % 64;
-                (*out)[(((size_t)half * 9 + tap) * co + o) * 64 + il] = __float2bfloat16(k[((size_t)tap * ci + i) * co + o]);
-            }
-}
-
 int bf16_commit(rst_ctx* c) {
     Bf16State* st = c->bf16.get();
-    const int F = c->cfg.bottleneck_num_filters;
+    const rst_config& g = c->cfg;
+    const int F = g.bottleneck_num_filters, B = g.max_batch;
     std::string err;
+    std::vector<__nv_bfloat16> packed;
+    std::vector<float> cb, cs, csh;
+    // ---- stem ----
+    {
+        const LayerDesc& L = c->contract[0];
+        const Weight* k = c->find_weight(L.name + "/conv/kernel");
+        const Weight* b = c->find_weight(L.name + "/conv/bias");
+        std::vector<float> scale(L.co), shift(L.co);
+        RST_CUDA(c, cudaMemcpy(scale.data(), c->folded[L.name + "/bn/scale"], L.co * 4, cudaMemcpyDeviceToHost));
+        RST_CUDA(c, cudaMemcpy(shift.data(), c->folded[L.name + "/bn/shift"], L.co * 4, cudaMemcpyDeviceToHost));
+        if (!setup_stem(&st->stem, L.ci, L.co, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb, &cs, &csh))
+            return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: stem channel layout");
+        RST_CUDA(c, st->stem.upload(packed, cb, &cs, &csh));
+        st->stem.p.out_H = L.ho; st->stem.p.out_W = L.wo;
+        if (!st->stem.bind_input(st->s_in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+    }
+    // ---- bottleneck ----
     for (int i = 0; i < 10; ++i) {
         const LayerDesc& L = c->residual[i];
         const Weight* k = c->find_weight(L.name + "/kernel");
-        TrunkLayer& tl = st->layers[i];
-        tl.nhalf = (L.ci + 63) / 64;
-        std::vector<__nv_bfloat16> packed;
-        pack_conv3x3(k->host, L.ci, F, tl.nhalf, &packed);
-        if (!tl.w_packed) RST_CUDA(c, cudaMalloc(&tl.w_packed, packed.size() * 2));
-        RST_CUDA(c, cudaMemcpy(tl.w_packed, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
-        if (!umma_encode_weight_map(&tl.tmB, tl.w_packed, tl.nhalf * 9 * F, F, &err)) return fail(c, RST_ERR_CUDA, err);
+        const Weight* b = c->find_weight(L.name + "/bias");
+        HaloConv& hc = st->trunk[i];
+        setup_conv3x3(&hc, L.ci, F, k->host.data(), b->host.data(), ACT_RELU, &packed, &cb);
+        RST_CUDA(c, hc.upload(packed, cb, nullptr, nullptr));
+        hc.p.out_H = L.ho; hc.p.out_W = L.wo;
+        const void* in = i == 0 ? (const void*)st->b_in : (i % 2 == 0 ? (const void*)st->bx : (const void*)st->bz);
+        if (i == 0 && L.ci > 32) return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: bottleneck input wider than 32 channels");
+        if (!hc.bind_input(in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+    }
+    // ---- decoder ----
+    if (st->tc_decoder) {
+        const LayerDesc& L0 = c->expand[0];
+        const LayerDesc& L1 = c->expand[1];
+        const LayerDesc& L2 = c->expand[2];
+        setup_convt2(&st->e0, L0.ci, L0.co, c->find_weight(L0.name + "/conv/kernel")->host.data(),
+                     c->find_weight(L0.name + "/conv/bias")->host.data(), &packed, &cb);
+        RST_CUDA(c, st->e0.upload(packed, cb, nullptr, nullptr));
+        st->e0.p.out_H = L0.ho; st->e0.p.out_W = L0.wo;
+        if (!st->e0.bind_input(st->bx, B, L0.hi, L0.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        setup_convt2(&st->e1, L1.ci, L1.co, c->find_weight(L1.name + "/conv/kernel")->host.data(),
+                     c->find_weight(L1.name + "/conv/bias")->host.data(), &packed, &cb);
+        RST_CUDA(c, st->e1.upload(packed, cb, nullptr, nullptr));
+        st->e1.p.out_H = L1.ho; st->e1.p.out_W = L1.wo;
+        if (!st->e1.bind_input(st->ze0, B, L1.hi, L1.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        setup_head(&st->head, c->find_weight(L2.name + "/conv/kernel")->host.data(),
+                   c->find_weight(L2.name + "/conv/bias")->host.data(), &packed, &cb);
+        RST_CUDA(c, st->head.upload(packed, cb, nullptr, nullptr));
+        st->head.p.out_H = L2.ho; st->head.p.out_W = L2.wo;
+        if (!st->head.bind_input(st->ze1, B, L2.hi, L2.wi / 4, &err)) return fail(c, RST_ERR_CUDA, err);
     }
     return RST_OK;
 }
 
-static int trunk_conv(rst_ctx* c, int layer, const CUtensorMap& tmA, int batch, cudaStream_t s) {
-    Bf16State* st = c->bf16.get();
-    const int F = c->cfg.bottleneck_num_filters;
-    ConvUmmaParams p;
-    p.y = st->by;
-    p.bias = c->wdev(c->residual[layer].name + "/bias");
-    p.stats = st->stats + (size_t)layer * c->cfg.max_batch * F * 2;
-    p.B = batch; p.H = c->bott_h; p.W = c->bott_w;
-    p.nhalf = st->layers[layer].nhalf;
-    p.tiles_h = ceil_div(p.H, kUmmaTH);
-    p.tiles_w = ceil_div(p.W, kUmmaTW);
-    p.relu = 1;
-    LaunchScope ls(c, s, "conv3x3_umma");
-    RST_CUDA(c, launch_conv3x3_umma(F, tmA, st->layers[layer].tmB, p, st->num_sms, s));
-    return RST_OK;
-}
-
-static int trunk_norm(rst_ctx* c, int layer, __nv_bfloat16* dst, const __nv_bfloat16* residual, int batch,
-                      const float* d_style_params, int param_off, int act, cudaStream_t s) {
-    Bf16State* st = c->bf16.get();
-    const int F = c->cfg.bottleneck_num_filters;
-    CinApplyBf16 a;
-    a.x = st->by; a.y = dst; a.residual = residual;
-    a.stats = st->stats + (size_t)layer * c->cfg.max_batch * F * 2;
+static int norm_pass(rst_ctx* c, const void* x, bool x_f32, void* y, bool y_f32, const __nv_bfloat16* residual,
+                     const double* stats, int batch, int P, int C, int width, const float* d_style_params, int param_off,
+                     int act, cudaStream_t s) {
+    CinApplyV a;
+    a.x = x; a.x_f32 = x_f32; a.y = y; a.y_f32 = y_f32; a.residual = residual; a.stats = stats;
     a.params = d_style_params;
     a.param_bstride = (long long)c->cfg.num_styles * c->num_style_params;
     a.param_sstride = c->num_style_params;
-    a.scale_off = param_off; a.bias_off = param_off + F;
-    a.weights = c->cfg.num_styles == 2 ? mip_for_width(c, c->bott_w) : nullptr;
-    a.B = batch; a.P = c->bott_h * c->bott_w; a.C = F; a.num_styles = c->cfg.num_styles; a.act = act; a.eps = 1e-5f;
-    if (c->cfg.num_styles == 2 && !a.weights) return fail(c, RST_ERR_STATE, "no style-weight mip for the bottleneck");
+    a.scale_off = param_off; a.bias_off = param_off + C;
+    a.weights = c->cfg.num_styles == 2 ? mip_for_width(c, width) : nullptr;
+    a.B = batch; a.P = P; a.C = C; a.num_styles = c->cfg.num_styles; a.act = act;
+    if (c->cfg.num_styles == 2 && !a.weights) return fail(c, RST_ERR_STATE, "no style-weight mip for this layer width");
     LaunchScope ls(c, s, "cin_apply_bf16");
-    RST_CUDA(c, launch_cin_apply_bf16(a, s));
+    RST_CUDA(c, launch_cin_apply_v(a, s));
     return RST_OK;
 }
 
 int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_style_params, const float* d_style_weights,
                           float* d_out, int batch, cudaStream_t s) {
     Bf16State* st = c->bf16.get();
-    const int F = c->cfg.bottleneck_num_filters;
-    const long long px = (long long)batch * c->bott_h * c->bott_w;
+    const rst_config& g = c->cfg;
+    const int F = g.bottleneck_num_filters;
+    const int PB = c->bott_h * c->bott_w;
+    const long long px = (long long)batch * PB;
     int rc = build_mips(c, d_style_weights, batch, s);
     if (rc) return rc;
-    float* enc = nullptr;
-    int free_idx = 0;
-    rc = fp32_contract_stage(c, d_content, batch, s, &enc, &free_idx);
-    if (rc) return rc;
+    RST_CUDA(c, cudaMemsetAsync(st->stats, 0, st->stats_bytes, s));
+
+    // ---- encoder ----
+    {
+        LaunchScope ls(c, s, "pack_input");
+        RST_CUDA(c, launch_pack_stem_input(d_content, st->s_in, batch, g.in_h, g.in_w, g.in_c, st->stem_layout.n_real,
+                                           st->stem_layout.row_elems, s));
+    }
+    float* stem_out = c->act[0];
+    {
+        LaunchScope ls(c, s, "stem_umma");
+        RST_CUDA(c, st->stem.run(stem_out, true, nullptr, batch, st->num_sms, s));
+    }
+    record_tap(c, c->contract[0].name, stem_out, (int64_t)batch * g.in_h * g.in_w * 32, false, s);
+    const float* cur = stem_out;
+    int which = 1;
+    for (size_t i = 1; i < c->contract.size(); ++i) {           // 3x3 stride-2 convs (fp32 kernels for now)
+        const LayerDesc& L = c->contract[i];
+        float* y = c->act[which];
+        ConvF32 p;
+        p.x = cur; p.y = y; p.w = c->wdev(L.name + "/conv/kernel"); p.bias = c->wdev(L.name + "/conv/bias");
+        p.B = batch; p.Hi = L.hi; p.Wi = L.wi; p.Ci = L.ci; p.Ho = L.ho; p.Wo = L.wo; p.Co = L.co;
+        p.kh = L.k; p.kw = L.k; p.stride = L.stride; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
+        p.w_tap = (long long)L.ci * L.co; p.w_ci = L.co; p.w_co = 1;
+        p.act1 = ACT_RELU; p.post_scale = c->folded[L.name + "/bn/scale"]; p.post_shift = c->folded[L.name + "/bn/shift"];
+        p.act2 = ACT_RELU;
+        { LaunchScope ls(c, s, "conv_fp32"); RST_CUDA(c, launch_conv_f32(p, s)); }
+        record_tap(c, L.name, y, (int64_t)batch * L.ho * L.wo * L.co, false, s);
+        cur = y;
+        which = which == 1 ? 2 : 1;
+    }
     {
         LaunchScope ls(c, s, "convert");
-        RST_CUDA(c, launch_f32_to_bf16_pad(enc, st->b_in, px, c->residual[0].ci, st->cin_pad, s));
+        RST_CUDA(c, launch_f32_to_bf16_pad(cur, st->b_in, px, c->residual[0].ci, 32, s));
     }
-    RST_CUDA(c, cudaMemsetAsync(st->stats, 0, st->stats_bytes, s));
+
+    // ---- residual bottleneck (styleTransfer.py:144-185) ----
     int cursor = 0;
-    for (int b = 0; b < 5; ++b) {                                     // residual_block, styleTransfer.py:144-185
+    for (int b = 0; b < 5; ++b) {
         const std::string name = "residual_block_" + std::to_string(b);
-        rc = trunk_conv(c, 2 * b, b == 0 ? st->tm_in : st->tm_x, batch, s);
-        if (rc) return rc;
+        double* st0 = st->stats + (size_t)(2 * b) * st->stats_stride;
+        double* st1 = st->stats + (size_t)(2 * b + 1) * st->stats_stride;
+        { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b].run(st->by, false, st0, batch, st->num_sms, s)); }
         record_tap(c, name + "/conv0/relu", st->by, px * F, true, s);
-        rc = trunk_norm(c, 2 * b, st->bz, nullptr, batch, d_style_params, cursor, ACT_RELU, s);
+        rc = norm_pass(c, st->by, false, st->bz, false, nullptr, st0, batch, PB, F, c->bott_w, d_style_params, cursor, ACT_RELU, s);
         if (rc) return rc;
         record_tap(c, name + "/conv0/cin", st->bz, px * F, true, s);
-        rc = trunk_conv(c, 2 * b + 1, st->tm_z, batch, s);
-        if (rc) return rc;
+        { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(st->by, false, st1, batch, st->num_sms, s)); }
         record_tap(c, name + "/conv1/relu", st->by, px * F, true, s);
-        rc = trunk_norm(c, 2 * b + 1, st->bx, b == 0 ? nullptr : st->bx, batch, d_style_params, cursor + 2 * F, ACT_NONE, s);
+        rc = norm_pass(c, st->by, false, st->bx, false, b == 0 ? nullptr : st->bx, st1, batch, PB, F, c->bott_w, d_style_params,
+                       cursor + 2 * F, ACT_NONE, s);
         if (rc) return rc;
         record_tap(c, name, st->bx, px * F, true, s);
         cursor += 4 * F;
     }
-    float* x = c->act[free_idx];
-    float* t1 = c->act[2];
-    {
-        LaunchScope ls(c, s, "convert");
-        RST_CUDA(c, launch_bf16_to_f32_slice(st->bx, x, px, F, F, s));
+
+    // ---- decoder (styleTransfer.py:95-141, :260-276) ----
+    if (!st->tc_decoder) {
+        float* x = c->act[0];
+        float* t1 = c->act[1];
+        {
+            LaunchScope ls(c, s, "convert");
+            RST_CUDA(c, launch_bf16_to_f32_slice(st->bx, x, px, F, F, s));
+        }
+        return fp32_expand_stage(c, x, t1, d_style_params, cursor, d_out, batch, s);
     }
-    return fp32_expand_stage(c, x, t1, d_style_params, cursor, d_out, batch, s);
+    const LayerDesc& L0 = c->expand[0];
+    const LayerDesc& L1 = c->expand[1];
+    const LayerDesc& L2 = c->expand[2];
+    double* se0 = st->stats + (size_t)10 * st->stats_stride;
+    double* se1 = st->stats + (size_t)11 * st->stats_stride;
+    double* se2 = st->stats + (size_t)12 * st->stats_stride;
+    { LaunchScope ls(c, s, "convt_umma"); RST_CUDA(c, st->e0.run(st->ye0, false, se0, batch, st->num_sms, s)); }
+    record_tap(c, L0.name + "/conv", st->ye0, (int64_t)batch * L0.ho * L0.wo * L0.co, true, s);
+    rc = norm_pass(c, st->ye0, false, st->ze0, false, nullptr, se0, batch, L0.ho * L0.wo, L0.co, L0.wo, d_style_params, cursor,
+                   ACT_RELU, s);
+    if (rc) return rc;
+    record_tap(c, L0.name, st->ze0, (int64_t)batch * L0.ho * L0.wo * L0.co, true, s);
+    cursor += 2 * L0.co;
+    { LaunchScope ls(c, s, "convt_umma"); RST_CUDA(c, st->e1.run(st->ye1, false, se1, batch, st->num_sms, s)); }
+    record_tap(c, L1.name + "/conv", st->ye1, (int64_t)batch * L1.ho * L1.wo * L1.co, true, s);
+    rc = norm_pass(c, st->ye1, false, st->ze1, false, nullptr, se1, batch, L1.ho * L1.wo, L1.co, L1.wo, d_style_params, cursor,
+                   ACT_RELU, s);
+    if (rc) return rc;
+    record_tap(c, L1.name, st->ze1, (int64_t)batch * L1.ho * L1.wo * L1.co, true, s);
+    cursor += 2 * L1.co;
+    { LaunchScope ls(c, s, "head_umma"); RST_CUDA(c, st->head.run(st->ylast, true, se2, batch, st->num_sms, s)); }
+    record_tap(c, L2.name + "/conv", st->ylast, (int64_t)batch * L2.ho * L2.wo * 3, false, s);
+    rc = norm_pass(c, st->ylast, true, d_out, true, nullptr, se2, batch, L2.ho * L2.wo, 3, L2.wo, d_style_params, cursor,
+                   ACT_SIGMOID, s);
+    if (rc) return rc;
+    record_tap(c, L2.name, d_out, (int64_t)batch * L2.ho * L2.wo * 3, false, s);
+    return RST_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// stand-alone operator (tests): 3x3 stride-1 'same' conv through the tensor-core kernel, fp32 tensors at the
-// boundary (converted to bf16 on the device).  Not a hot path: allocates and frees its scratch.
+// stand-alone operator (tests): one convolution through the tensor-core kernel with fp32 tensors at the boundary.
+// Not a hot path: allocates and frees its scratch.  Supported: 3x3 s1 conv (co 64/128), 9x9 s1 conv (co 32,
+// ci <= 19), Conv2DTranspose 3x3 s2 (co 16/32) and Conv2DTranspose 9x9 s1 16 -> 3.
 // ------------------------------------------------------------------------------------------------
 int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch, int h, int w, int ci,
                    int co, int kh, int kw, int stride, int transposed, int act, cudaStream_t s, std::string* err) {
-    if (kh != 3 || kw != 3 || stride != 1 || transposed || (co != 32 && co != 64 && co != 128) ||
-        (act != ACT_NONE && act != ACT_RELU)) {
-        *err = "rst_op_conv2d(bf16): only 3x3 stride-1 convs with 32/64/128 filters run on the tensor-core kernel";
+    enum { K3, STEM, CONVT2, HEAD, NONE } kind = NONE;
+    if (!transposed && kh == 3 && kw == 3 && stride == 1 && (co == 64 || co == 128)) kind = K3;
+    else if (!transposed && kh == 9 && kw == 9 && stride == 1 && co == 32 && ci <= 19) kind = STEM;
+    else if (transposed && kh == 3 && kw == 3 && stride == 2 && (co == 16 || co == 32) && (ci <= 32 || ci % 64 == 0)) kind = CONVT2;
+    else if (transposed && kh == 9 && kw == 9 && stride == 1 && co == 3 && ci == 16 && w % 4 == 0) kind = HEAD;
+    const bool conv_like = kind == K3 || kind == STEM;
+    if (kind == NONE || act != (conv_like ? ACT_RELU : ACT_NONE)) {
+        *err = "rst_op_conv2d(bf16): shape/activation not mapped onto the tensor-core kernel (convs: ReLU, transposed convs: none)";
         return RST_ERR_UNSUPPORTED;
     }
     if (!umma_init(err)) return RST_ERR_CUDA;
-    const int nhalf = (ci + 63) / 64, cpad = nhalf * 64;
-    const long long px = (long long)batch * h * w;
-    std::vector<float> hk((size_t)9 * ci * co);
-    cudaError_t e = cudaMemcpy(hk.data(), d_kernel, hk.size() * 4, cudaMemcpyDeviceToHost);
+    const size_t kelems = (size_t)kh * kw * ci * co;
+    std::vector<float> hk(kelems), hb(co, 0.f);
+    cudaError_t e = cudaMemcpy(hk.data(), d_kernel, kelems * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && d_bias) e = cudaMemcpy(hb.data(), d_bias, co * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return RST_ERR_CUDA; }
+    HaloConv hc;
     std::vector<__nv_bfloat16> packed;
-    pack_conv3x3(hk, ci, co, nhalf, &packed);
-    __nv_bfloat16 *xb = nullptr, *yb = nullptr, *wb = nullptr;
-    if (e == cudaSuccess) e = cudaMalloc(&xb, px * cpad * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&yb, px * co * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&wb, packed.size() * 2);
-    if (e == cudaSuccess) e = cudaMemcpy(wb, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice);
-    CUtensorMap tmA, tmB;
+    std::vector<float> cb, cs, csh;
+    StemLayout SL{};
+    int oh = h, ow = w, wru = w;
+    bool y_f32 = false;
+    if (kind == K3) {
+        setup_conv3x3(&hc, ci, co, hk.data(), hb.data(), act, &packed, &cb);
+    } else if (kind == STEM) {
+        std::vector<float> one(co, 1.f), zero(co, 0.f);
+        stem_layout(ci, &SL);
+        setup_stem(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
+        y_f32 = true;
+    } else if (kind == CONVT2) {
+        setup_convt2(&hc, ci, co, hk.data(), hb.data(), &packed, &cb);
+        oh = 2 * h; ow = 2 * w;
+    } else {
+        setup_head(&hc, hk.data(), hb.data(), &packed, &cb);
+        wru = w / 4; y_f32 = true;
+    }
+    e = kind == STEM ? hc.upload(packed, cb, &cs, &csh) : hc.upload(packed, cb, nullptr, nullptr);
+    const long long pin = (long long)batch * h * w, pout = (long long)batch * oh * ow;
+    __nv_bfloat16 *xb = nullptr, *yb = nullptr;
+    const int in_c_dev = kind == HEAD ? 16 : hc.in_C;
+    if (e == cudaSuccess) e = cudaMalloc(&xb, pin * in_c_dev * 2);
+    if (e == cudaSuccess && !y_f32) e = cudaMalloc(&yb, pout * co * 2);
     int rc = RST_OK;
     if (e == cudaSuccess) {
-        if (!umma_encode_activation_map(&tmA, xb, batch, h, w, cpad, err) ||
-            !umma_encode_weight_map(&tmB, wb, nhalf * 9 * co, co, err))
-            rc = RST_ERR_CUDA;
+        if (kind == STEM) e = launch_pack_stem_input(d_x, xb, batch, h, w, ci, SL.n_real, SL.row_elems, s);
+        else e = launch_f32_to_bf16_pad(d_x, xb, pin, ci, in_c_dev, s);
+    }
+    if (e == cudaSuccess) {
+        hc.p.out_H = oh; hc.p.out_W = ow;
+        if (!hc.bind_input(xb, batch, h, wru, err)) rc = RST_ERR_CUDA;
     }
     if (e == cudaSuccess && rc == RST_OK) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = launch_f32_to_bf16_pad(d_x, xb, px, ci, cpad, s);
-        ConvUmmaParams p;
-        p.y = yb; p.bias = d_bias; p.stats = nullptr; p.B = batch; p.H = h; p.W = w; p.nhalf = nhalf;
-        p.tiles_h = ceil_div(h, kUmmaTH); p.tiles_w = ceil_div(w, kUmmaTW); p.relu = act == ACT_RELU;
-        if (e == cudaSuccess) e = launch_conv3x3_umma(co, tmA, tmB, p, sms, s);
-        if (e == cudaSuccess) e = launch_bf16_to_f32_slice(yb, d_y, px, co, co, s);
+        e = hc.run(y_f32 ? (void*)d_y : (void*)yb, y_f32, nullptr, batch, sms, s);
+        if (e == cudaSuccess && !y_f32) e = launch_bf16_to_f32_slice(yb, d_y, pout, co, co, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    for (void* p : {(void*)xb, (void*)yb, (void*)wb}) if (p) cudaFree(p);
+    for (void* q : {(void*)xb, (void*)yb}) if (q) cudaFree(q);
     if (e != cudaSuccess) { *err = std::string("rst_op_conv2d(bf16): ") + cudaGetErrorString(e); return RST_ERR_CUDA; }
     return rc;
 }
