@@ -49,7 +49,7 @@ constexpr int MODE_RELU = 1;      // ReLU after the bias
 constexpr int MODE_POST = 2;      // then per-column affine (inference BatchNorm) and a second ReLU
 constexpr int MODE_F32 = 4;       // store fp32 instead of bf16
 
-template <int N, int ROWB, int EPI, int MODE>
+template <int N, int ROWB, int EPI, int MODE, int SCH, bool BRES>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const HaloGemmParams p) {
@@ -59,6 +59,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
     constexpr int CW = N >= 32 ? 32 : 16;              // columns per epilogue chunk
     constexpr int NCH = N / CW;
+    constexpr int KS = sched_ksteps(SCH, ROWB);         // K-steps per channel group
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA_M=128 needs 16 <= N <= 256, N % 16 == 0");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two");
 
@@ -67,7 +68,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int halo_bytes = p.halo_h * p.halo_w * ROWB;
     const int a_stage_bytes = (halo_bytes + 1023) & ~1023;
     const int blocks_per_tile = p.n_groups * p.ksteps / 4;
-    const int nbslots = p.b_resident ? blocks_per_tile : p.n_bstages;
+    const int nbslots = BRES ? blocks_per_tile : p.n_bstages;
     uint8_t* sA = smem;
     uint8_t* sB = sA + p.n_astages * a_stage_bytes;
     uint8_t* tail = sB + nbslots * BBLK;
@@ -127,7 +128,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ================= B producer ===========================================================
         if (lane == 0 && tile_begin < tile_end) {
-            if (p.b_resident) {
+            if (BRES) {
                 mbar_expect_tx(&b_full[0], blocks_per_tile * BBLK);
                 for (int kb = 0; kb < blocks_per_tile; ++kb) tma_load_2d(sB + kb * BBLK, &tmB, &b_full[0], 0, kb * N);
             } else {
@@ -143,47 +144,49 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 2) {
-        // ================= MMA issuer (single thread) ===========================================
-        if (lane == 0) {
+        // ================= MMA issuer ===========================================================
+        // The whole warp runs the (fully unrolled, compile-time scheduled) loop so that descriptor arithmetic stays in
+        // the uniform datapath; only the tcgen05.mma / tcgen05.commit instructions themselves are issued by lane 0.
+        {
             const uint32_t idesc = make_idesc_bf16(128, N);
-            // descriptors differ only in their 14-bit start-address field: build the constant part once
-            const uint64_t da_const = make_smem_desc(0, 16, p.halo_h * ROWB, SWZ);
+            const uint64_t da_const = make_smem_desc(0, 16, sched_halo_h(SCH) * ROWB, SWZ);
             const uint64_t db_const = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
+            const bool leader = elect_one();
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
-            if (p.b_resident && tile_begin < tile_end) mbar_wait(&b_full[0], 0);
+            if (BRES && tile_begin < tile_end) mbar_wait(&b_full[0], 0);
+            // warp-uniform by construction; the shuffles let ptxas prove it and keep descriptors in uniform registers
+            const uint32_t sB16 = __shfl_sync(0xffffffffu, smem_u32(sB) >> 4, 0);
+            const uint32_t sA16 = __shfl_sync(0xffffffffu, smem_u32(sA) >> 4, 0);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t a_stage16 = (uint32_t)a_stage_bytes >> 4;
             for (int t = tile_begin; t < tile_end; ++t) {
                 mbar_wait(&acc_empty[cs], cph ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + cs * N;
+                const uint32_t tmem_d = tmem_u + cs * N;
                 for (int g = 0; g < p.n_groups; ++g) {
                     mbar_wait(&a_full[as], aph);
                     tc_fence_after();
-                    const uint32_t a_base16 = smem_u32(sA + as * a_stage_bytes) >> 4;
-#pragma unroll 1
-                    for (int kb = 0; kb < p.ksteps / 4; ++kb) {
-                        uint32_t b_base16;
-                        if (p.b_resident) {
-                            b_base16 = smem_u32(sB + (g * (p.ksteps / 4) + kb) * BBLK) >> 4;
-                        } else {
+                    const uint32_t a_base16 = sA16 + as * a_stage16;
+                    uint32_t b_base16 = sB16 + g * (KS / 4) * (BBLK / 16);
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        if (!BRES && (ks & 3) == 0) {
                             mbar_wait(&b_full[bs], bph);
                             tc_fence_after();
-                            b_base16 = smem_u32(sB + bs * BBLK) >> 4;
+                            b_base16 = sB16 + bs * (BBLK / 16);
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = da_const | (uint64_t)(a_base16 + p.a_off16[kb * 4 + k]);
-                            const uint64_t db = db_const | (uint64_t)(b_base16 + k * 2);
-                            mma_f16_ss(tmem_d, da, db, idesc, (uint32_t)((g | kb | k) != 0));
-                        }
-                        if (!p.b_resident) {
-                            mma_commit(&b_empty[bs]);
+                        const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH, ROWB, ks) >> 4));
+                        const uint64_t db = db_const | (uint64_t)(b_base16 + (BRES ? (ks / 4) * (BBLK / 16) : 0) + (ks & 3) * 2);
+                        if (leader) mma_f16_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
+                        if (!BRES && (ks & 3) == 3) {
+                            if (leader) mma_commit(&b_empty[bs]);
                             if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
                         }
                     }
-                    mma_commit(&a_empty[as]);
+                    if (leader) mma_commit(&a_empty[as]);
                     if (++as == (uint32_t)p.n_astages) { as = 0; aph ^= 1; }
                 }
-                mma_commit(&acc_full[cs]);
+                if (leader) mma_commit(&acc_full[cs]);
                 if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         }
@@ -320,66 +323,69 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmemBudget = 227 * 1024;
 
+static bool sched_resident(const HaloGemmLaunch& l) { return !(l.sched == SCH_C3 && l.row_bytes == 128 && l.N == 128); }
+
 bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err) {
-    if (p->ksteps % 4 != 0 || p->ksteps > kMaxKsteps || p->ksteps <= 0) {
-        if (err) *err = "halo_gemm: ksteps must be a positive multiple of 4, at most 128";
-        return false;
-    }
+    p->ksteps = sched_ksteps(l->sched, l->row_bytes);
+    p->halo_h = sched_halo_h(l->sched); p->halo_w = sched_halo_w(l->sched);
+    p->oy = sched_oy(l->sched); p->ox = sched_ox(l->sched);
     const int a_stage = (p->halo_h * p->halo_w * l->row_bytes + 1023) & ~1023;
     const int bblk = l->N * 128;
     const int blocks = p->n_groups * p->ksteps / 4;
     const int fixed = 1024 + kTailBytes;
-    p->b_resident = (blocks * bblk + 2 * a_stage + fixed <= kSmemBudget) ? 1 : 0;
+    p->b_resident = sched_resident(*l) ? 1 : 0;
     int b_bytes;
     if (p->b_resident) {
         b_bytes = blocks * bblk;
     } else {
         p->n_bstages = 6;
-        while (p->n_bstages > 2 && p->n_bstages * bblk + 2 * a_stage + fixed > kSmemBudget) --p->n_bstages;
         b_bytes = p->n_bstages * bblk;
     }
     p->n_astages = 4;
     while (p->n_astages > 1 && p->n_astages * a_stage + b_bytes + fixed > kSmemBudget) --p->n_astages;
     if (!p->b_resident && p->n_astages > 3) p->n_astages = 3;
     l->smem_bytes = (size_t)p->n_astages * a_stage + b_bytes + fixed;
-    if (l->smem_bytes > (size_t)kSmemBudget) {
+    if (l->smem_bytes > (size_t)kSmemBudget || (p->b_resident && p->n_astages < 2)) {
         if (err) *err = "halo_gemm: tile does not fit in shared memory";
         return false;
     }
     return true;
 }
 
-template <int N, int ROWB, int EPI, int MODE>
+template <int N, int ROWB, int EPI, int MODE, int SCH, bool BRES>
 static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloGemmParams& p,
                             int num_sms, cudaStream_t s) {
     static size_t configured = 0;
     if (configured < l.smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(halo_gemm_kernel<N, ROWB, EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)l.smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
         if (e != cudaSuccess) return e;
         configured = l.smem_bytes;
     }
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    halo_gemm_kernel<N, ROWB, EPI, MODE><<<grid, kHaloThreads, l.smem_bytes, s>>>(tmA, tmB, p);
+    halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES><<<grid, kHaloThreads, l.smem_bytes, s>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              const HaloGemmParams& p, int num_sms, cudaStream_t s) {
-    const int mode = l.mode;
-#define RST_HALO_CASE(NN, RB, EP, MD) \
-    if (l.N == NN && l.row_bytes == RB && l.epi == EP && mode == (MD)) return launch_t<NN, RB, EP, (MD)>(l, tmA, tmB, p, num_sms, s);
-    RST_HALO_CASE(128, 128, EPI_NHWC, MODE_RELU)                          // bottleneck 3x3 convs (64-channel groups)
-    RST_HALO_CASE(128, 64, EPI_NHWC, MODE_RELU)                           // residual_block_0/conv0 (32 input channels)
-    RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU)
-    RST_HALO_CASE(64, 64, EPI_NHWC, MODE_RELU)
-    RST_HALO_CASE(32, 64, EPI_NHWC, MODE_RELU | MODE_POST | MODE_F32)     // 9x9 stem (16 real + 16 windowed channels)
-    RST_HALO_CASE(32, 128, EPI_NHWC, MODE_RELU | MODE_POST | MODE_F32)    // stem with 18 / 3 channels (64-element rows)
-    RST_HALO_CASE(128, 128, EPI_CONVT2, 0)                                // expand_0: 4 phases x 32 channels
-    RST_HALO_CASE(64, 64, EPI_CONVT2, 0)                                  // expand_1: 4 phases x 16 channels
-    RST_HALO_CASE(16, 128, EPI_QUAD3, MODE_F32)                           // expand_last: 4 pixels x 3 channels
+    constexpr int STEM_MODE = MODE_RELU | MODE_POST | MODE_F32;
+#define RST_HALO_CASE(NN, RB, EP, MD, SC, RES) \
+    if (l.N == NN && l.row_bytes == RB && l.epi == EP && l.mode == (MD) && l.sched == (SC)) \
+        return launch_t<NN, RB, EP, (MD), (SC), RES>(l, tmA, tmB, p, num_sms, s);
+    RST_HALO_CASE(128, 128, EPI_NHWC, MODE_RELU, SCH_C3, false)             // bottleneck 3x3 convs, weights streamed
+    RST_HALO_CASE(128, 64, EPI_NHWC, MODE_RELU, SCH_C3, true)               // residual_block_0/conv0 (32 input channels)
+    RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU, SCH_C3, true)
+    RST_HALO_CASE(64, 64, EPI_NHWC, MODE_RELU, SCH_C3, true)
+    RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 1, true)      // 9x9 stem, 17 channels: 16 real + 1 windowed
+    RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 0, true)      // 5..16 channels
+    RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 2, true)     // 18 channels
+    RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_STEM + 0 + 3, true)     // RGB: three windowed channels
+    RST_HALO_CASE(128, 128, EPI_CONVT2, 0, SCH_T2, true)                    // expand_0: 4 phases x 32 channels
+    RST_HALO_CASE(64, 64, EPI_CONVT2, 0, SCH_T2, true)                      // expand_1: 4 phases x 16 channels
+    RST_HALO_CASE(16, 128, EPI_QUAD3, MODE_F32, SCH_HEAD, true)             // expand_last: 4 pixels x 3 channels
 #undef RST_HALO_CASE
     return cudaErrorInvalidValue;
 }

@@ -33,6 +33,32 @@ enum HaloEpi : int {
     EPI_QUAD3 = 2,    // col = j*3 + c (j<4) -> out[n, gh, 4gw+j, c]   (3-channel head, 4 pixels per row unit)
 };
 
+// ---- K-step schedules: compile-time A-operand offsets so that the MMA issue loop is fully unrolled ----------------
+// SCH_C3: 3x3 taps x (row_bytes/32) channel slices, halo 10x18.     SCH_T2: 2x2 taps (stride-2 transposed conv), halo 9x17.
+// SCH_HEAD: 9 rows x 12 window pixels over 4-pixel row units, halo 16x18.
+// SCH_STEM + 4*REAL + NV: 9x9 taps over the 16 real channels (REAL) plus 9 row taps per windowed channel group (NV).
+enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_STEM = 10 };
+__host__ __device__ constexpr int sched_real_ksteps(int sch, int rowb) {
+    return sch == SCH_C3 ? 9 * (rowb / 32) : sch == SCH_T2 ? 4 * (rowb / 32) : sch == SCH_HEAD ? 108
+           : 81 * ((sch - SCH_STEM) / 4) + 9 * ((sch - SCH_STEM) % 4);
+}
+__host__ __device__ constexpr int sched_ksteps(int sch, int rowb) { return (sched_real_ksteps(sch, rowb) + 3) / 4 * 4; }
+__host__ __device__ constexpr int sched_halo_h(int sch) { return sch == SCH_C3 ? 10 : sch == SCH_T2 ? 9 : 16; }
+__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 ? 17 : sch == SCH_HEAD ? 18 : 24; }
+__host__ __device__ constexpr int sched_oy(int sch) { return sch == SCH_C3 || sch == SCH_T2 ? -1 : -4; }
+__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD ? -1 : -4; }
+// byte offset of K-step ks into the halo patch
+__host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
+    if (ks >= sched_real_ksteps(sch, rowb)) return 0;
+    if (sch == SCH_C3) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 3) * 10 + tap / 3) * rowb + (ks % kper) * 32; }
+    if (sch == SCH_T2) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 2) * 9 + tap / 2) * rowb + (ks % kper) * 32; }
+    if (sch == SCH_HEAD) { const int dy = ks / 12, kx = ks % 12; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
+    const int real = (sch - SCH_STEM) / 4;
+    if (ks < 81 * real) return ((ks % 9) * 16 + ks / 9) * rowb;
+    const int v = (ks - 81 * real) / 9, ky = (ks - 81 * real) % 9;
+    return (4 * 16 + ky) * rowb + 32 * real + v * 32;
+}
+
 struct HaloGemmParams {
     // output grid in rows / row units, tiling
     int B = 0, H = 0, WRU = 0, tiles_h = 0, tiles_w = 0;
@@ -41,7 +67,6 @@ struct HaloGemmParams {
     int halo_h = 10, halo_w = 18;    // box extent (rows, RUs)
     int n_groups = 1;                // halo loads per tile; group g loads channel coordinate g * row_elems
     int ksteps = 0;                  // K-steps per group, multiple of 4
-    uint32_t a_off16[128] = {};      // [ksteps] A start offsets into the halo in 16-byte units (kernel-param / constant bank)
     int b_resident = 0;
     int n_astages = 3, n_bstages = 6;
     // epilogue
@@ -62,6 +87,7 @@ struct HaloGemmLaunch {
     int row_bytes = 128;    // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
     int epi = EPI_NHWC;
     int mode = 0;           // HALO_MODE_* bits (compile-time epilogue variant)
+    int sched = SCH_C3;     // HaloSched (compile-time K-step schedule)
     size_t smem_bytes = 0;  // filled by halo_gemm_plan
 };
 

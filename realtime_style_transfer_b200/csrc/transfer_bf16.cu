@@ -23,7 +23,6 @@ struct HaloConv {
     float* col_bias = nullptr;     // [N] bias expanded to GEMM columns
     float* col_scale = nullptr;    // [N] optional post affine
     float* col_shift = nullptr;
-    std::vector<uint32_t> a_off;
     int total_ksteps = 0;          // n_groups * ksteps
     int in_C = 0;                  // channels (bf16 elements per row unit) of the bound input tensor
 
@@ -44,7 +43,6 @@ struct HaloConv {
         up((void**)&col_bias, bias.data(), bias.size() * 4);
         if (scale) up((void**)&col_scale, scale->data(), scale->size() * 4);
         if (shift) up((void**)&col_shift, shift->data(), shift->size() * 4);
-        for (size_t i = 0; i < a_off.size() && i < 128; ++i) p.a_off16[i] = a_off[i] >> 4;
         p.bias = col_bias;
         p.post_scale = scale ? col_scale : nullptr;
         p.post_shift = shift ? col_shift : nullptr;
@@ -67,8 +65,12 @@ struct HaloConv {
     }
 };
 
-static void pad_ksteps(HaloConv* c) {
-    while (c->a_off.size() % 4) c->a_off.push_back(0);
+static void use_sched(HaloConv* c, int sch) {
+    c->launch.sched = sch;
+    c->p.ksteps = sched_ksteps(sch, c->launch.row_bytes);
+    c->p.halo_h = sched_halo_h(sch); c->p.halo_w = sched_halo_w(sch);
+    c->p.oy = sched_oy(sch); c->p.ox = sched_ox(sch);
+    c->total_ksteps = c->p.n_groups * c->p.ksteps;
 }
 
 // 3x3 stride-1 'same' conv, Keras kernel (3,3,ci,co).  ci <= 32 uses 64-byte rows, otherwise 64-channel groups.
@@ -78,15 +80,9 @@ static void setup_conv3x3(HaloConv* c, int ci, int co, const float* k, const flo
     c->launch.N = co; c->launch.row_bytes = rowb; c->launch.epi = EPI_NHWC;
     c->in_C = (ci + row_elems - 1) / row_elems * row_elems;
     c->p.n_groups = c->in_C / row_elems;
-    c->p.oy = -1; c->p.ox = -1; c->p.halo_h = 10; c->p.halo_w = 18;
     const int kper = row_elems / 16;
-    c->a_off.clear();
-    for (int tap = 0; tap < 9; ++tap)
-        for (int kk = 0; kk < kper; ++kk) c->a_off.push_back(((tap % 3) * 10 + tap / 3) * rowb + kk * 32);
-    const int real_ksteps = (int)c->a_off.size();
-    pad_ksteps(c);
-    c->p.ksteps = (int)c->a_off.size();
-    c->total_ksteps = c->p.n_groups * c->p.ksteps;
+    use_sched(c, SCH_C3);
+    const int real_ksteps = 9 * kper;
     c->launch.mode = HALO_MODE_RELU; (void)act;
     c->p.out_C = co; c->p.stats_c = co;
     const int ksteps = c->p.ksteps;
@@ -102,12 +98,14 @@ static void setup_conv3x3(HaloConv* c, int ci, int co, const float* k, const flo
 struct StemLayout { int n_real, n_virtual, row_elems; };
 static bool stem_layout(int C, StemLayout* L) {
     if (C >= 16) { L->n_real = 16; L->n_virtual = C - 16; }
-    else if (C <= 4) { L->n_real = 0; L->n_virtual = C; }
+    else if (C <= 3) { L->n_real = 0; L->n_virtual = C; }
     else { L->n_real = C; L->n_virtual = 0; }
     const int elems = (L->n_real ? 16 : 0) + 16 * L->n_virtual;
     if (elems > 64) return false;
     L->row_elems = elems <= 32 ? 32 : 64;
-    return true;
+    // schedules instantiated in halo_gemm.cu: (real, windowed) = (16,0) (16,1) (16,2) (0,3)
+    const int key = (L->n_real ? 4 : 0) + L->n_virtual;
+    return key == 4 || key == 5 || key == 6 || key == 3;
 }
 
 // 9x9 stride-1 'same' conv over packed rows [16 real | 16 per virtual channel], Keras kernel (9,9,C,co).
@@ -119,17 +117,9 @@ static bool setup_stem(HaloConv* c, int C, int co, const float* k, const float* 
     const int rowb = L.row_elems * 2;
     c->launch.N = co; c->launch.row_bytes = rowb; c->launch.epi = EPI_NHWC;
     c->in_C = L.row_elems; c->p.n_groups = 1;
-    c->p.oy = -4; c->p.ox = -4; c->p.halo_h = 16; c->p.halo_w = 24;
-    c->a_off.clear();
     const int real_ksteps = L.n_real ? 81 : 0;
-    for (int t = 0; t < real_ksteps; ++t) c->a_off.push_back(((t % 9) * 16 + t / 9) * rowb);
-    const int virt_byte0 = L.n_real ? 32 : 0;
-    for (int v = 0; v < L.n_virtual; ++v)
-        for (int ky = 0; ky < 9; ++ky) c->a_off.push_back((4 * 16 + ky) * rowb + virt_byte0 + v * 32);
-    const int used = (int)c->a_off.size();
-    pad_ksteps(c);
-    c->p.ksteps = (int)c->a_off.size();
-    c->total_ksteps = c->p.ksteps;
+    use_sched(c, SCH_STEM + 4 * (L.n_real ? 1 : 0) + L.n_virtual);
+    const int used = real_ksteps + 9 * L.n_virtual;
     c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST | HALO_MODE_F32;
     c->p.out_C = co; c->p.stats_c = co;
     pack_b_blocks(c->total_ksteps, co, [&](int ks, int n, int e) -> float {
@@ -154,14 +144,8 @@ static void setup_convt2(HaloConv* c, int ci, int co, const float* k, const floa
     c->launch.N = 4 * co; c->launch.row_bytes = rowb; c->launch.epi = EPI_CONVT2;
     c->in_C = (ci + row_elems - 1) / row_elems * row_elems;
     c->p.n_groups = c->in_C / row_elems;
-    c->p.oy = -1; c->p.ox = -1; c->p.halo_h = 9; c->p.halo_w = 17;
     const int kper = row_elems / 16;
-    c->a_off.clear();
-    for (int tap = 0; tap < 4; ++tap)       // tap = dy*2 + dx
-        for (int kk = 0; kk < kper; ++kk) c->a_off.push_back(((tap % 2) * 9 + tap / 2) * rowb + kk * 32);
-    pad_ksteps(c);
-    c->p.ksteps = (int)c->a_off.size();
-    c->total_ksteps = c->p.n_groups * c->p.ksteps;
+    use_sched(c, SCH_T2);
     c->launch.mode = 0;
     c->p.out_C = co; c->p.stats_c = co;
     const int ksteps = c->p.ksteps;
@@ -186,12 +170,7 @@ static void setup_head(HaloConv* c, const float* k, const float* bias, std::vect
                        std::vector<float>* col_bias) {
     c->launch.N = 16; c->launch.row_bytes = 128; c->launch.epi = EPI_QUAD3;
     c->in_C = 64; c->p.n_groups = 1;
-    c->p.oy = -4; c->p.ox = -1; c->p.halo_h = 16; c->p.halo_w = 18;
-    c->a_off.clear();
-    for (int dy = 0; dy < 9; ++dy)
-        for (int kx = 0; kx < 12; ++kx) c->a_off.push_back(((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32);
-    c->p.ksteps = (int)c->a_off.size();      // 108
-    c->total_ksteps = c->p.ksteps;
+    use_sched(c, SCH_HEAD);
     c->launch.mode = HALO_MODE_F32;
     c->p.out_C = 3; c->p.stats_c = 3;
     pack_b_blocks(c->total_ksteps, 16, [&](int ks, int n, int e) -> float {
