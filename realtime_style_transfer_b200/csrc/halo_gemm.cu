@@ -120,7 +120,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int g = 0; g < p.n_groups; ++g) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     mbar_expect_tx(&a_full[stage], halo_bytes);
-                    tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 + p.ox, n);
+                    if (SCH == SCH_S2D) tma_load_5d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], 0, h0, 0, w0, n);
+                    else tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 + p.ox, n);
                     if (++stage == (uint32_t)p.n_astages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -371,7 +372,7 @@ static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, con
 
 cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              const HaloGemmParams& p, int num_sms, cudaStream_t s) {
-    constexpr int STEM_MODE = MODE_RELU | MODE_POST | MODE_F32;
+    constexpr int STEM_MODE = MODE_RELU | MODE_POST;
 #define RST_HALO_CASE(NN, RB, EP, MD, SC, RES) \
     if (l.N == NN && l.row_bytes == RB && l.epi == EP && l.mode == (MD) && l.sched == (SC)) \
         return launch_t<NN, RB, EP, (MD), (SC), RES>(l, tmA, tmB, p, num_sms, s);
@@ -383,6 +384,9 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
     RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 0, true)      // 5..16 channels
     RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 2, true)     // 18 channels
     RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_STEM + 0 + 3, true)     // RGB: three windowed channels
+    RST_HALO_CASE(16, 128, EPI_NHWC, STEM_MODE, SCH_S2D, true)              // contract_0: 3x3 stride 2, 32 -> 16
+    RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_S2D, true)               // contract_1: 16 -> 32
+    RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_S2D, true)              // deeper contract blocks: 32 -> 32
     RST_HALO_CASE(128, 128, EPI_CONVT2, 0, SCH_T2, true)                    // expand_0: 4 phases x 32 channels
     RST_HALO_CASE(64, 64, EPI_CONVT2, 0, SCH_T2, true)                      // expand_1: 4 phases x 16 channels
     RST_HALO_CASE(16, 128, EPI_QUAD3, MODE_F32, SCH_HEAD, true)             // expand_last: 4 pixels x 3 channels
@@ -426,6 +430,26 @@ bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, 
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (err) *err = "cuTensorMapEncodeTiled(activation) failed with code " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+bool encode_s2d_map(CUtensorMap* out, const void* base, int B, int H, int W, int C, std::string* err) {
+    if (!umma_init(err)) return false;
+    if ((H & 1) || (W & 1) || (2 * C != 64 && 2 * C != 32)) {
+        if (err) *err = "encode_s2d_map: needs even H, W and 16 or 32 channels";
+        return false;
+    }
+    cuuint64_t gdim[5] = {(cuuint64_t)2 * C, (cuuint64_t)H / 2, 2, (cuuint64_t)W / 2, (cuuint64_t)B};
+    cuuint64_t gstr[4] = {(cuuint64_t)2 * W * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)2 * C, 9, 2, 17, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUtensorMapSwizzle sw = 2 * C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled(space-to-depth) failed with code " + std::to_string((int)r);
         return false;
     }
     return true;

@@ -37,22 +37,31 @@ enum HaloEpi : int {
 // SCH_C3: 3x3 taps x (row_bytes/32) channel slices, halo 10x18.     SCH_T2: 2x2 taps (stride-2 transposed conv), halo 9x17.
 // SCH_HEAD: 9 rows x 12 window pixels over 4-pixel row units, halo 16x18.
 // SCH_STEM + 4*REAL + NV: 9x9 taps over the 16 real channels (REAL) plus 9 row taps per windowed channel group (NV).
-enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_STEM = 10 };
+// SCH_S2D: 3x3 stride-2 conv over the space-to-depth view (h2, row parity, w2, [col parity x channels]) of the input:
+//          row taps ky -> (h2 + ky/2, parity ky%2); column taps kx -> (w2 + kx/2, parity kx%2) = channel slice of the row.
+enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM = 10 };
 __host__ __device__ constexpr int sched_real_ksteps(int sch, int rowb) {
     return sch == SCH_C3 ? 9 * (rowb / 32) : sch == SCH_T2 ? 4 * (rowb / 32) : sch == SCH_HEAD ? 108
+           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64)
            : 81 * ((sch - SCH_STEM) / 4) + 9 * ((sch - SCH_STEM) % 4);
 }
 __host__ __device__ constexpr int sched_ksteps(int sch, int rowb) { return (sched_real_ksteps(sch, rowb) + 3) / 4 * 4; }
-__host__ __device__ constexpr int sched_halo_h(int sch) { return sch == SCH_C3 ? 10 : sch == SCH_T2 ? 9 : 16; }
-__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 ? 17 : sch == SCH_HEAD ? 18 : 24; }
-__host__ __device__ constexpr int sched_oy(int sch) { return sch == SCH_C3 || sch == SCH_T2 ? -1 : -4; }
-__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD ? -1 : -4; }
+__host__ __device__ constexpr int sched_halo_h(int sch) { return sch == SCH_C3 ? 10 : sch == SCH_T2 ? 9 : sch == SCH_S2D ? 18 : 16; }
+__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : 24; }
+__host__ __device__ constexpr int sched_oy(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : -4; }
+__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD ? -1 : -4; }
 // byte offset of K-step ks into the halo patch
 __host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
     if (ks >= sched_real_ksteps(sch, rowb)) return 0;
     if (sch == SCH_C3) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 3) * 10 + tap / 3) * rowb + (ks % kper) * 32; }
     if (sch == SCH_T2) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 2) * 9 + tap / 2) * rowb + (ks % kper) * 32; }
     if (sch == SCH_HEAD) { const int dy = ks / 12, kx = ks % 12; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
+    if (sch == SCH_S2D) {
+        // per row tap: kper slices at w2+0 (column taps 0,1) then kper/2 slices at w2+1 (column tap 2)
+        const int kper = rowb / 32, per_ky = kper + kper / 2, ky = ks / per_ky, l = ks % per_ky;
+        const int w2off = l >= kper ? 1 : 0, k = l >= kper ? l - kper : l;
+        return ((w2off * 2 + ky % 2) * 9 + ky / 2) * rowb + k * 32;
+    }
     const int real = (sch - SCH_STEM) / 4;
     if (ks < 81 * real) return ((ks % 9) * 16 + ks / 9) * rowb;
     const int v = (ks - 81 * real) / 9, ky = (ks - 81 * real) % 9;
@@ -101,6 +110,8 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
 bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, int C, int row_elems, int halo_h,
                      int halo_w, std::string* err);
 // Packed weights: nblocks*N rows of 64 bf16; box = (64, N).
+// Space-to-depth view of an NHWC tensor (B, H, W, C), H and W even: dims (2C, H/2, 2, W/2, B), box (2C, 9, 2, 17, 1).
+bool encode_s2d_map(CUtensorMap* out, const void* base, int B, int H, int W, int C, std::string* err);
 bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err);
 // Packs B: f(kstep, n, e) -> weight of K-step `kstep`, output column n, K element e (0..15).
 void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out);

@@ -50,10 +50,13 @@ struct HaloConv {
     }
 
     // Bind the input tensor (B, H, WRU, in_C) and finish the launch plan.
+    // For SCH_S2D the bound tensor is the un-strided input (B, 2H, 2W, in_C/2); H, WRU are the OUTPUT grid.
     bool bind_input(const void* x, int B, int H, int WRU, std::string* err) {
         p.B = B; p.H = H; p.WRU = WRU;
         p.tiles_h = ceil_div(H, 8); p.tiles_w = ceil_div(WRU, 16);
-        if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
+        if (launch.sched == SCH_S2D) {
+            if (!encode_s2d_map(&tmA, x, B, 2 * H, 2 * WRU, in_C / 2, err)) return false;
+        } else if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
         if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
         return halo_gemm_plan(&launch, &p, err);
     }
@@ -120,7 +123,7 @@ static bool setup_stem(HaloConv* c, int C, int co, const float* k, const float* 
     const int real_ksteps = L.n_real ? 81 : 0;
     use_sched(c, SCH_STEM + 4 * (L.n_real ? 1 : 0) + L.n_virtual);
     const int used = real_ksteps + 9 * L.n_virtual;
-    c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST | HALO_MODE_F32;
+    c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST;
     c->p.out_C = co; c->p.stats_c = co;
     pack_b_blocks(c->total_ksteps, co, [&](int ks, int n, int e) -> float {
         if (ks >= used) return 0.f;
@@ -129,6 +132,34 @@ static bool setup_stem(HaloConv* c, int C, int co, const float* k, const float* 
         }
         const int v = (ks - real_ksteps) / 9, ky = (ks - real_ksteps) % 9, ch = L.n_real + v;
         return e < 9 ? k[((size_t)(ky * 9 + e) * C + ch) * co + n] : 0.f;      // e == kx
+    }, packed);
+    col_bias->assign(bias, bias + co);
+    col_scale->assign(bn_scale, bn_scale + co);
+    col_shift->assign(bn_shift, bn_shift + co);
+    return true;
+}
+
+// 3x3 stride-2 'same' conv on even-sized inputs (TF pads 0 before / 1 after), Keras kernel (3,3,ci,co), followed by
+// ReLU -> BatchNorm -> ReLU (contract blocks).  Runs over the space-to-depth view: a row holds [col parity 0 | col parity 1].
+static bool setup_conv_s2(HaloConv* c, int ci, int co, const float* k, const float* bias, const float* bn_scale,
+                          const float* bn_shift, std::vector<__nv_bfloat16>* packed, std::vector<float>* col_bias,
+                          std::vector<float>* col_scale, std::vector<float>* col_shift) {
+    if ((ci != 16 && ci != 32) || (co != 16 && co != 32)) return false;
+    const int row_elems = 2 * ci, rowb = row_elems * 2;
+    c->launch.N = co; c->launch.row_bytes = rowb; c->launch.epi = EPI_NHWC;
+    c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST;
+    c->in_C = row_elems; c->p.n_groups = 1;
+    use_sched(c, SCH_S2D);
+    const int kper = rowb / 32, per_ky = kper + kper / 2, real = 3 * per_ky;
+    c->p.out_C = co; c->p.stats_c = co;
+    pack_b_blocks(c->total_ksteps, co, [&](int ks, int n, int e) -> float {
+        if (ks >= real) return 0.f;
+        const int ky = ks / per_ky, l = ks % per_ky;
+        const int w2off = l >= kper ? 1 : 0, kk = l >= kper ? l - kper : l;
+        const int cc = kk * 16 + e, pw = cc / ci, cin = cc % ci;
+        const int kx = 2 * w2off + pw;
+        if (kx > 2) return 0.f;
+        return k[((size_t)(ky * 3 + kx) * ci + cin) * co + n];
     }, packed);
     col_bias->assign(bias, bias + co);
     col_scale->assign(bn_scale, bn_scale + co);
@@ -189,15 +220,17 @@ struct Bf16State {
     int num_sms = 148;
     bool tc_decoder = false;            // expand layers on tensor cores (standard 2-expand geometry)
     StemLayout stem_layout{};
-    HaloConv stem, trunk[10], e0, e1, head;
+    HaloConv stem, contract[4], trunk[10], e0, e1, head;
     __nv_bfloat16 *s_in = nullptr;      // packed stem input
-    __nv_bfloat16 *b_in = nullptr, *bx = nullptr, *by = nullptr, *bz = nullptr;   // bottleneck tensors
+    __nv_bfloat16* enc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // encoder activations (enc[0] = stem output)
+    __nv_bfloat16 *bx = nullptr, *by = nullptr, *bz = nullptr;   // bottleneck tensors
     __nv_bfloat16 *ye0 = nullptr, *ze0 = nullptr, *ye1 = nullptr, *ze1 = nullptr;  // decoder tensors
     float* ylast = nullptr;
     double* stats = nullptr;            // [13][max_batch][F][2]
     size_t stats_bytes = 0, stats_stride = 0;
     ~Bf16State() {
-        for (void* q : {(void*)s_in, (void*)b_in, (void*)bx, (void*)by, (void*)bz, (void*)ye0, (void*)ze0, (void*)ye1,
+        for (auto q : enc) if (q) cudaFree(q);
+        for (void* q : {(void*)s_in, (void*)bx, (void*)by, (void*)bz, (void*)ye0, (void*)ze0, (void*)ye1,
                         (void*)ze1, (void*)ylast, (void*)stats})
             if (q) cudaFree(q);
     }
@@ -220,7 +253,12 @@ int bf16_create(rst_ctx* c) {
     const size_t B = g.max_batch;
     const size_t pin = B * g.in_h * g.in_w, pb = B * c->bott_h * c->bott_w;
     RST_CUDA(c, cudaMalloc(&st->s_in, pin * st->stem_layout.row_elems * 2));
-    RST_CUDA(c, cudaMalloc(&st->b_in, pb * 32 * 2));
+    for (size_t i = 0; i < c->contract.size(); ++i) {
+        const LayerDesc& L = c->contract[i];
+        if ((L.ho % 2 || L.wo % 2) && i + 1 < c->contract.size())
+            return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: odd-sized encoder activations");
+        RST_CUDA(c, cudaMalloc(&st->enc[i], B * L.ho * L.wo * L.co * 2));
+    }
     RST_CUDA(c, cudaMalloc(&st->bx, pb * F * 2));
     RST_CUDA(c, cudaMalloc(&st->by, pb * F * 2));
     RST_CUDA(c, cudaMalloc(&st->bz, pb * F * 2));
@@ -261,6 +299,20 @@ int bf16_commit(rst_ctx* c) {
         st->stem.p.out_H = L.ho; st->stem.p.out_W = L.wo;
         if (!st->stem.bind_input(st->s_in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
     }
+    // ---- strided encoder convs ----
+    for (size_t i = 1; i < c->contract.size(); ++i) {
+        const LayerDesc& L = c->contract[i];
+        std::vector<float> scale(L.co), shift(L.co);
+        RST_CUDA(c, cudaMemcpy(scale.data(), c->folded[L.name + "/bn/scale"], L.co * 4, cudaMemcpyDeviceToHost));
+        RST_CUDA(c, cudaMemcpy(shift.data(), c->folded[L.name + "/bn/shift"], L.co * 4, cudaMemcpyDeviceToHost));
+        HaloConv& hc = st->contract[i - 1];
+        if (!setup_conv_s2(&hc, L.ci, L.co, c->find_weight(L.name + "/conv/kernel")->host.data(),
+                           c->find_weight(L.name + "/conv/bias")->host.data(), scale.data(), shift.data(), &packed, &cb, &cs, &csh))
+            return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: strided conv channel counts");
+        RST_CUDA(c, hc.upload(packed, cb, &cs, &csh));
+        hc.p.out_H = L.ho; hc.p.out_W = L.wo;
+        if (!hc.bind_input(st->enc[i - 1], B, L.ho, L.wo, &err)) return fail(c, RST_ERR_CUDA, err);
+    }
     // ---- bottleneck ----
     for (int i = 0; i < 10; ++i) {
         const LayerDesc& L = c->residual[i];
@@ -270,7 +322,7 @@ int bf16_commit(rst_ctx* c) {
         setup_conv3x3(&hc, L.ci, F, k->host.data(), b->host.data(), ACT_RELU, &packed, &cb);
         RST_CUDA(c, hc.upload(packed, cb, nullptr, nullptr));
         hc.p.out_H = L.ho; hc.p.out_W = L.wo;
-        const void* in = i == 0 ? (const void*)st->b_in : (i % 2 == 0 ? (const void*)st->bx : (const void*)st->bz);
+        const void* in = i == 0 ? (const void*)st->enc[c->contract.size() - 1] : (i % 2 == 0 ? (const void*)st->bx : (const void*)st->bz);
         if (i == 0 && L.ci > 32) return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: bottleneck input wider than 32 channels");
         if (!hc.bind_input(in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
     }
@@ -332,32 +384,15 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
         RST_CUDA(c, launch_pack_stem_input(d_content, st->s_in, batch, g.in_h, g.in_w, g.in_c, st->stem_layout.n_real,
                                            st->stem_layout.row_elems, s));
     }
-    float* stem_out = c->act[0];
     {
         LaunchScope ls(c, s, "stem_umma");
-        RST_CUDA(c, st->stem.run(stem_out, true, nullptr, batch, st->num_sms, s));
+        RST_CUDA(c, st->stem.run(st->enc[0], false, nullptr, batch, st->num_sms, s));
     }
-    record_tap(c, c->contract[0].name, stem_out, (int64_t)batch * g.in_h * g.in_w * 32, false, s);
-    const float* cur = stem_out;
-    int which = 1;
-    for (size_t i = 1; i < c->contract.size(); ++i) {           // 3x3 stride-2 convs (fp32 kernels for now)
+    record_tap(c, c->contract[0].name, st->enc[0], (int64_t)batch * g.in_h * g.in_w * c->contract[0].co, true, s);
+    for (size_t i = 1; i < c->contract.size(); ++i) {           // 3x3 stride-2 convs over the space-to-depth view
         const LayerDesc& L = c->contract[i];
-        float* y = c->act[which];
-        ConvF32 p;
-        p.x = cur; p.y = y; p.w = c->wdev(L.name + "/conv/kernel"); p.bias = c->wdev(L.name + "/conv/bias");
-        p.B = batch; p.Hi = L.hi; p.Wi = L.wi; p.Ci = L.ci; p.Ho = L.ho; p.Wo = L.wo; p.Co = L.co;
-        p.kh = L.k; p.kw = L.k; p.stride = L.stride; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
-        p.w_tap = (long long)L.ci * L.co; p.w_ci = L.co; p.w_co = 1;
-        p.act1 = ACT_RELU; p.post_scale = c->folded[L.name + "/bn/scale"]; p.post_shift = c->folded[L.name + "/bn/shift"];
-        p.act2 = ACT_RELU;
-        { LaunchScope ls(c, s, "conv_fp32"); RST_CUDA(c, launch_conv_f32(p, s)); }
-        record_tap(c, L.name, y, (int64_t)batch * L.ho * L.wo * L.co, false, s);
-        cur = y;
-        which = which == 1 ? 2 : 1;
-    }
-    {
-        LaunchScope ls(c, s, "convert");
-        RST_CUDA(c, launch_f32_to_bf16_pad(cur, st->b_in, px, c->residual[0].ci, 32, s));
+        { LaunchScope ls(c, s, "conv_s2_umma"); RST_CUDA(c, st->contract[i - 1].run(st->enc[i], false, nullptr, batch, st->num_sms, s)); }
+        record_tap(c, L.name, st->enc[i], (int64_t)batch * L.ho * L.wo * L.co, true, s);
     }
 
     // ---- residual bottleneck (styleTransfer.py:144-185) ----
@@ -426,12 +461,14 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
 // ------------------------------------------------------------------------------------------------
 int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch, int h, int w, int ci,
                    int co, int kh, int kw, int stride, int transposed, int act, cudaStream_t s, std::string* err) {
-    enum { K3, STEM, CONVT2, HEAD, NONE } kind = NONE;
+    enum { K3, STEM, CONVT2, HEAD, S2, NONE } kind = NONE;
     if (!transposed && kh == 3 && kw == 3 && stride == 1 && (co == 64 || co == 128)) kind = K3;
     else if (!transposed && kh == 9 && kw == 9 && stride == 1 && co == 32 && ci <= 19) kind = STEM;
+    else if (!transposed && kh == 3 && kw == 3 && stride == 2 && (ci == 16 || ci == 32) && (co == 16 || co == 32) && h % 2 == 0 &&
+             w % 2 == 0) kind = S2;
     else if (transposed && kh == 3 && kw == 3 && stride == 2 && (co == 16 || co == 32) && (ci <= 32 || ci % 64 == 0)) kind = CONVT2;
     else if (transposed && kh == 9 && kw == 9 && stride == 1 && co == 3 && ci == 16 && w % 4 == 0) kind = HEAD;
-    const bool conv_like = kind == K3 || kind == STEM;
+    const bool conv_like = kind == K3 || kind == STEM || kind == S2;
     if (kind == NONE || act != (conv_like ? ACT_RELU : ACT_NONE)) {
         *err = "rst_op_conv2d(bf16): shape/activation not mapped onto the tensor-core kernel (convs: ReLU, transposed convs: none)";
         return RST_ERR_UNSUPPORTED;
@@ -454,7 +491,10 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
         std::vector<float> one(co, 1.f), zero(co, 0.f);
         stem_layout(ci, &SL);
         setup_stem(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
-        y_f32 = true;
+    } else if (kind == S2) {
+        std::vector<float> one(co, 1.f), zero(co, 0.f);
+        setup_conv_s2(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
+        oh = h / 2; ow = w / 2; wru = w / 2;
     } else if (kind == CONVT2) {
         setup_convt2(&hc, ci, co, hk.data(), hb.data(), &packed, &cb);
         oh = 2 * h; ow = 2 * w;
@@ -462,10 +502,10 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
         setup_head(&hc, hk.data(), hb.data(), &packed, &cb);
         wru = w / 4; y_f32 = true;
     }
-    e = kind == STEM ? hc.upload(packed, cb, &cs, &csh) : hc.upload(packed, cb, nullptr, nullptr);
+    e = (kind == STEM || kind == S2) ? hc.upload(packed, cb, &cs, &csh) : hc.upload(packed, cb, nullptr, nullptr);
     const long long pin = (long long)batch * h * w, pout = (long long)batch * oh * ow;
     __nv_bfloat16 *xb = nullptr, *yb = nullptr;
-    const int in_c_dev = kind == HEAD ? 16 : hc.in_C;
+    const int in_c_dev = kind == HEAD ? 16 : kind == S2 ? ci : hc.in_C;
     if (e == cudaSuccess) e = cudaMalloc(&xb, pin * in_c_dev * 2);
     if (e == cudaSuccess && !y_f32) e = cudaMalloc(&yb, pout * co * 2);
     int rc = RST_OK;
@@ -475,7 +515,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
     }
     if (e == cudaSuccess) {
         hc.p.out_H = oh; hc.p.out_W = ow;
-        if (!hc.bind_input(xb, batch, h, wru, err)) rc = RST_ERR_CUDA;
+        if (!hc.bind_input(xb, batch, kind == S2 ? oh : h, wru, err)) rc = RST_ERR_CUDA;
     }
     if (e == cudaSuccess && rc == RST_OK) {
         int dev = 0, sms = 148;

@@ -38,6 +38,9 @@ def bf16_round(a):
     (2, 24, 40, 17, 32, 9, 1, False),        # 9x9 stem: 16 real channels + 1 windowed channel per pixel
     (1, 21, 37, 18, 32, 9, 1, False),        # 18-channel variant (two windowed channels, 128-byte rows)
     (1, 16, 32, 3, 32, 9, 1, False),         # RGB stem: three windowed channels
+    (2, 24, 40, 32, 16, 3, 2, False),        # contract_0: stride-2 conv over the space-to-depth view
+    (1, 16, 36, 16, 32, 3, 2, False),        # contract_1
+    (1, 18, 34, 32, 32, 3, 2, False),        # deeper contract block, ragged tile edges
     (2, 12, 20, 128, 32, 3, 2, True),        # expand_0: stride-2 transposed conv as 4 phases
     (1, 13, 19, 32, 16, 3, 2, True),         # expand_1
     (2, 24, 64, 16, 3, 9, 1, True),          # expand_last: 4 pixels per GEMM row, 3 channels
