@@ -659,10 +659,144 @@ __global__ void __launch_bounds__(256) cin_apply_v_kernel(const CinApplyV p, int
     }
 }
 
+// ---- fast paths ------------------------------------------------------------------------------------
+// bf16 -> bf16, C in {16,32,64,128}: every thread owns a fixed group of 8 channels (blockDim % (C/8) == 0), keeps the
+// fused coefficients y = x*a + b in registers and streams 4 independent 16-byte vectors per iteration.
+template <bool BLEND, bool RES>
+__global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, int pix_per_block) {
+    const int C = p.C, n = blockIdx.y;
+    const int vec_per_pix = C >> 3;
+    const int c0 = (threadIdx.x % vec_per_pix) * 8;
+    float a0[8], b0[8], a1[8], b1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const double sum = p.stats[((long long)n * C + c) * 2 + 0], sq = p.stats[((long long)n * C + c) * 2 + 1];
+        const double mean = sum / (double)p.P;
+        double var = sq / (double)p.P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float inv = rsqrtf((float)var + p.eps), nmi = -(float)mean * inv;
+        const float* ps = p.params + n * p.param_bstride;
+        a0[j] = inv * ps[p.scale_off + c];
+        b0[j] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
+        if (BLEND) {
+            const float* p1 = ps + p.param_sstride;
+            a1[j] = inv * p1[p.scale_off + c];
+            b1[j] = p1[p.bias_off + c] + nmi * p1[p.scale_off + c];
+        }
+    }
+    const long long base = (long long)n * p.P * vec_per_pix;
+    const long long v0 = (long long)blockIdx.x * pix_per_block * vec_per_pix;
+    const long long v1 = min((long long)p.P * vec_per_pix, v0 + (long long)pix_per_block * vec_per_pix);
+    const uint4* x4 = reinterpret_cast<const uint4*>(p.x) + base;
+    const uint4* r4 = RES ? reinterpret_cast<const uint4*>(p.residual) + base : nullptr;
+    uint4* y4 = reinterpret_cast<uint4*>(p.y) + base;
+    const float2* w2 = BLEND ? reinterpret_cast<const float2*>(p.weights) + (long long)n * p.P : nullptr;
+    const int act = p.act;
+    auto one = [&](uint4 xin, uint4 rin, float2 w) -> uint4 {
+        const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xin);
+        const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rin);
+        uint4 outv;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 xv = __bfloat1622float2(xb[j]);
+            float aa0 = a0[2 * j], bb0 = b0[2 * j], aa1 = a0[2 * j + 1], bb1 = b0[2 * j + 1];
+            if (BLEND) {
+                aa0 = aa0 * w.x + a1[2 * j] * w.y;         bb0 = bb0 * w.x + b1[2 * j] * w.y;
+                aa1 = aa1 * w.x + a1[2 * j + 1] * w.y;     bb1 = bb1 * w.x + b1[2 * j + 1] * w.y;
+            }
+            float o0 = fmaf(xv.x, aa0, bb0), o1 = fmaf(xv.y, aa1, bb1);
+            if (act == ACT_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+            if (RES) { const float2 rv = __bfloat1622float2(rb[j]); o0 += rv.x; o1 += rv.y; }
+            ob[j] = __floats2bfloat162_rn(o0, o1);
+        }
+        return outv;
+    };
+    const long long stride = blockDim.x;
+    long long v = v0 + threadIdx.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (; v + 3 * stride < v1; v += 4 * stride) {
+        uint4 xi[4], ri[4];
+        float2 wi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            xi[u] = x4[v + u * stride];
+            ri[u] = RES ? r4[v + u * stride] : z;
+            wi[u] = BLEND ? w2[(v + u * stride) / vec_per_pix] : make_float2(1.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) y4[v + u * stride] = one(xi[u], ri[u], wi[u]);
+    }
+    for (; v < v1; v += stride)
+        y4[v] = one(x4[v], RES ? r4[v] : z, BLEND ? w2[v / vec_per_pix] : make_float2(1.f, 0.f));
+}
+
+// fp32 -> fp32 with 3 channels (the image head): 4 consecutive floats per thread, sigmoid.
+template <bool BLEND>
+__global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
+    __shared__ float sa[2][3], sb[2][3];
+    const int n = blockIdx.y;
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        const double sum = p.stats[((long long)n * 3 + c) * 2 + 0], sq = p.stats[((long long)n * 3 + c) * 2 + 1];
+        const double mean = sum / (double)p.P;
+        double var = sq / (double)p.P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float inv = rsqrtf((float)var + p.eps), nmi = -(float)mean * inv;
+        for (int st = 0; st < p.num_styles; ++st) {
+            const float* ps = p.params + n * p.param_bstride + st * p.param_sstride;
+            sa[st][c] = inv * ps[p.scale_off + c];
+            sb[st][c] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
+        }
+    }
+    __syncthreads();
+    const long long total4 = (long long)p.P * 3 / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(p.x) + (long long)n * total4;
+    float4* y4 = reinterpret_cast<float4*>(p.y) + (long long)n * total4;
+    const float2* w2 = BLEND ? reinterpret_cast<const float2*>(p.weights) + (long long)n * p.P : nullptr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = x4[i];
+        float in[4] = {xv.x, xv.y, xv.z, xv.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long e = i * 4 + j;
+            const int c = (int)(e % 3);
+            float a = sa[0][c], b = sb[0][c];
+            if (BLEND) {
+                const float2 w = w2[e / 3];
+                a = a * w.x + sa[1][c] * w.y;
+                b = b * w.x + sb[1][c] * w.y;
+            }
+            const float t = fmaf(in[j], a, b);
+            o[j] = p.act == ACT_SIGMOID ? 1.f / (1.f + __expf(-t)) : (p.act == ACT_RELU ? fmaxf(t, 0.f) : t);
+        }
+        y4[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
     if (p.B == 0 || p.P == 0) return cudaSuccess;
     if (!p.x_f32 && p.C % 8 != 0) return cudaErrorInvalidValue;
     if (p.x_f32 && p.residual) return cudaErrorInvalidValue;
+    const bool blend = p.num_styles == 2 && p.weights != nullptr;
+    if (!p.x_f32 && !p.y_f32 && p.act != ACT_SIGMOID && (p.C == 16 || p.C == 32 || p.C == 64 || p.C == 128)) {
+        const int pix_per_block = max(256, 65536 / p.C);          // >= 8 vectors per thread
+        dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
+        if (blend && p.residual) cin_apply_fast_kernel<true, true><<<grid, 256, 0, s>>>(p, pix_per_block);
+        else if (blend) cin_apply_fast_kernel<true, false><<<grid, 256, 0, s>>>(p, pix_per_block);
+        else if (p.residual) cin_apply_fast_kernel<false, true><<<grid, 256, 0, s>>>(p, pix_per_block);
+        else cin_apply_fast_kernel<false, false><<<grid, 256, 0, s>>>(p, pix_per_block);
+        return cudaGetLastError();
+    }
+    if (p.x_f32 && p.y_f32 && p.C == 3 && ((long long)p.P * 3) % 4 == 0) {
+        const long long total4 = (long long)p.P * 3 / 4;
+        const long long want = (total4 + 255) / 256;
+        dim3 grid((unsigned)(want < 148 * 8 ? want : 148 * 8), (unsigned)p.B);
+        if (blend) cin_apply_c3_kernel<true><<<grid, 256, 0, s>>>(p);
+        else cin_apply_c3_kernel<false><<<grid, 256, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     int pix_per_block = max(1, 32768 / p.C);
     dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
     size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
