@@ -92,6 +92,13 @@ int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const float* d_st
 /* Same with HOST buffers: H2D copies, forward, D2H copy and a stream synchronise inside. */
 int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
                               const float* h_style_weights, float* h_out, int batch);
+/* The frame loop of predict_video_using_checkpoint.py:90-98 (`for frame in dataset.prefetch(5): transfer.predict(...)`):
+ * asynchronous submit of one batch with HOST buffers (pinned for real overlap).  The H2D copy of batch i+1 and the D2H
+ * copy of batch i-1 overlap the forward of batch i (two staging slots).  h_out is valid after rst_transfer_wait(ticket);
+ * at most two tickets are in flight (a third submit blocks until the oldest has drained). */
+int rst_transfer_submit_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
+                             const float* h_style_weights, float* h_out, int batch, int64_t* ticket);
+int rst_transfer_wait(rst_ctx* ctx, int64_t ticket);
 /* style_predictor(style_image) (models/stylePrediction.py:25-75): d_style (B,style_h,style_w,3) in [0,1]
  * -> d_params (B,P). */
 int rst_predict_style(rst_ctx* ctx, const float* d_style, float* d_params, int batch, void* stream);

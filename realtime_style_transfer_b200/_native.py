@@ -54,6 +54,8 @@ SIGNATURES = {
     "rst_commit_weights": (C.c_int, [_vp]),
     "rst_transfer_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rst_transfer_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "rst_transfer_submit_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _i64p]),
+    "rst_transfer_wait": (C.c_int, [_vp, C.c_int64]),
     "rst_predict_style": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "rst_predict_style_host": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "rst_inference_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
@@ -190,6 +192,18 @@ class NativeContext:
         self._check(self.lib.rst_transfer_forward(self.handle, _vp(d_content), _vp(d_style_params),
                                                   _vp(d_style_weights) if d_style_weights else None, _vp(d_out),
                                                   batch, _vp(stream) if stream else None))
+
+    def transfer_submit_host(self, content: np.ndarray, style_params: np.ndarray, style_weights, out: np.ndarray) -> int:
+        """Asynchronous submit; the caller keeps the (ideally pinned) float32 arrays alive until transfer_wait(ticket)."""
+        for a in (content, style_params, out):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        ticket = C.c_int64()
+        self._check(self.lib.rst_transfer_submit_host(self.handle, _ptr(content), _ptr(style_params), _ptr(style_weights),
+                                                      _ptr(out), content.shape[0], C.byref(ticket)))
+        return int(ticket.value)
+
+    def transfer_wait(self, ticket: int):
+        self._check(self.lib.rst_transfer_wait(self.handle, ticket))
 
     def predict_style_host(self, style) -> np.ndarray:
         style = _host_f32(style)

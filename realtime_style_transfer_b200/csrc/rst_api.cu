@@ -226,6 +226,14 @@ static void free_ctx(rst_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     c->bf16.reset();
     c->train.reset();
+    if (c->pipe.ready) {
+        for (int i = 0; i < 2; ++i) {
+            for (float* q : {c->pipe.content[i], c->pipe.params[i], c->pipe.weights[i], c->pipe.out[i]}) if (q) cudaFree(q);
+            for (cudaEvent_t e : {c->pipe.in_done[i], c->pipe.comp_done[i], c->pipe.out_done[i]}) if (e) cudaEventDestroy(e);
+        }
+        if (c->pipe.s_in) cudaStreamDestroy(c->pipe.s_in);
+        if (c->pipe.s_out) cudaStreamDestroy(c->pipe.s_out);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -610,6 +618,80 @@ extern "C" int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, c
     RST_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->st_out, (size_t)batch * g.out_h * g.out_w * 3 * sizeof(float),
                                   cudaMemcpyDeviceToHost, s));
     RST_CUDA(ctx, cudaStreamSynchronize(s));
+    if (ctx->profiling) collect_profile(ctx);
+    return RST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Asynchronous, double-buffered host pipeline: the frame loop of predict_video_using_checkpoint.py:90-98
+// (`for frame in dataset.prefetch(5): transfer.predict(...)`) with the H2D copy of batch i+1 and the D2H copy of
+// batch i-1 overlapping the forward of batch i.  Host buffers should be pinned for the copies to be asynchronous.
+// ------------------------------------------------------------------------------------------------
+static int pipe_init(rst_ctx* c) {
+    if (c->pipe.ready) return RST_OK;
+    const rst_config& g = c->cfg;
+    const size_t B = g.max_batch;
+    for (int i = 0; i < 2; ++i) {
+        RST_CUDA(c, cudaMalloc(&c->pipe.content[i], B * g.in_h * g.in_w * g.in_c * sizeof(float)));
+        RST_CUDA(c, cudaMalloc(&c->pipe.params[i], B * g.num_styles * c->num_style_params * sizeof(float)));
+        RST_CUDA(c, cudaMalloc(&c->pipe.out[i], B * g.out_h * g.out_w * 3 * sizeof(float)));
+        if (g.num_styles > 1)
+            RST_CUDA(c, cudaMalloc(&c->pipe.weights[i], B * g.out_h * g.out_w * (g.num_styles - 1) * sizeof(float)));
+        RST_CUDA(c, cudaEventCreateWithFlags(&c->pipe.in_done[i], cudaEventDisableTiming));
+        RST_CUDA(c, cudaEventCreateWithFlags(&c->pipe.comp_done[i], cudaEventDisableTiming));
+        RST_CUDA(c, cudaEventCreateWithFlags(&c->pipe.out_done[i], cudaEventDisableTiming));
+    }
+    RST_CUDA(c, cudaStreamCreateWithFlags(&c->pipe.s_in, cudaStreamNonBlocking));
+    RST_CUDA(c, cudaStreamCreateWithFlags(&c->pipe.s_out, cudaStreamNonBlocking));
+    c->pipe.ready = true;
+    return RST_OK;
+}
+
+extern "C" int rst_transfer_submit_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
+                                        const float* h_style_weights, float* h_out, int batch, int64_t* ticket) {
+    if (!ctx) return RST_ERR_INVALID;
+    if (ctx->cfg.in_h == 0) return fail(ctx, RST_ERR_STATE, "rst_transfer_submit_host: predictor-only context");
+    if (!ctx->committed) return fail(ctx, RST_ERR_STATE, "rst_transfer_submit_host: weights not committed");
+    if (!h_content || !h_style_params || !h_out || !ticket) return fail(ctx, RST_ERR_INVALID, "rst_transfer_submit_host: null argument");
+    if (batch < 1 || batch > ctx->cfg.max_batch) return fail(ctx, RST_ERR_INVALID, "rst_transfer_submit_host: batch out of range");
+    cudaSetDevice(ctx->device);
+    int rc = pipe_init(ctx);
+    if (rc) return rc;
+    const rst_config& g = ctx->cfg;
+    auto& P = ctx->pipe;
+    const int slot = (int)(P.next & 1);
+    if (P.busy[slot]) RST_CUDA(ctx, cudaEventSynchronize(P.out_done[slot]));     // the slot's previous batch has fully drained
+    RST_CUDA(ctx, cudaMemcpyAsync(P.content[slot], h_content, (size_t)batch * g.in_h * g.in_w * g.in_c * sizeof(float),
+                                  cudaMemcpyHostToDevice, P.s_in));
+    RST_CUDA(ctx, cudaMemcpyAsync(P.params[slot], h_style_params,
+                                  (size_t)batch * g.num_styles * ctx->num_style_params * sizeof(float), cudaMemcpyHostToDevice, P.s_in));
+    if (g.num_styles > 1) {
+        if (!h_style_weights) return fail(ctx, RST_ERR_INVALID, "style_weights required when num_styles > 1");
+        RST_CUDA(ctx, cudaMemcpyAsync(P.weights[slot], h_style_weights,
+                                      (size_t)batch * g.out_h * g.out_w * (g.num_styles - 1) * sizeof(float),
+                                      cudaMemcpyHostToDevice, P.s_in));
+    }
+    RST_CUDA(ctx, cudaEventRecord(P.in_done[slot], P.s_in));
+    RST_CUDA(ctx, cudaStreamWaitEvent(ctx->own_stream, P.in_done[slot], 0));
+    rc = rst_transfer_forward(ctx, P.content[slot], P.params[slot], g.num_styles > 1 ? P.weights[slot] : nullptr, P.out[slot],
+                              batch, (void*)ctx->own_stream);
+    if (rc) return rc;
+    RST_CUDA(ctx, cudaEventRecord(P.comp_done[slot], ctx->own_stream));
+    RST_CUDA(ctx, cudaStreamWaitEvent(P.s_out, P.comp_done[slot], 0));
+    RST_CUDA(ctx, cudaMemcpyAsync(h_out, P.out[slot], (size_t)batch * g.out_h * g.out_w * 3 * sizeof(float),
+                                  cudaMemcpyDeviceToHost, P.s_out));
+    RST_CUDA(ctx, cudaEventRecord(P.out_done[slot], P.s_out));
+    P.busy[slot] = true;
+    *ticket = P.next++;
+    return RST_OK;
+}
+
+extern "C" int rst_transfer_wait(rst_ctx* ctx, int64_t ticket) {
+    if (!ctx || !ctx->pipe.ready) return RST_ERR_INVALID;
+    if (ticket < 0 || ticket >= ctx->pipe.next) return fail(ctx, RST_ERR_INVALID, "rst_transfer_wait: unknown ticket");
+    if (ticket + 2 < ctx->pipe.next) return RST_OK;          // slot already recycled => that batch completed long ago
+    cudaSetDevice(ctx->device);
+    RST_CUDA(ctx, cudaEventSynchronize(ctx->pipe.out_done[ticket & 1]));
     if (ctx->profiling) collect_profile(ctx);
     return RST_OK;
 }

@@ -81,6 +81,16 @@ struct rst_ctx {
     float* st_content = nullptr; float* st_params = nullptr; float* st_weights = nullptr;
     float* st_out = nullptr; float* st_style = nullptr;
     cudaStream_t own_stream = nullptr;
+    // double-buffered asynchronous host pipeline (rst_transfer_submit_host / rst_transfer_wait)
+    struct Pipe {
+        bool ready = false;
+        float *content[2] = {nullptr, nullptr}, *params[2] = {nullptr, nullptr}, *weights[2] = {nullptr, nullptr},
+              *out[2] = {nullptr, nullptr};
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+        bool busy[2] = {false, false};
+        int64_t next = 0;
+    } pipe;
 
     // ---- bf16 tensor-core path ----
     std::shared_ptr<rst::Bf16State> bf16;

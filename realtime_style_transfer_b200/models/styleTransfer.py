@@ -185,6 +185,47 @@ class StyleTransferModel(NativeModel):
         return np.concatenate(outs, axis=0) if len(outs) > 1 else outs[0]
 
 
+def _predict_frames(self, batches, pinned: bool = True):
+    """Streaming variant of the reference's video loop (predict_video_using_checkpoint.py:90-98): yields one
+    stylised numpy batch per input dict, with the host<->device copies of neighbouring batches overlapping the forward.
+    Inputs are staged through two pinned buffers unless they already are pinned torch tensors."""
+    import torch
+    slots, pending = [], []
+    ctx = None
+    for k, element in enumerate(batches):
+        content, params, weights = self._check_inputs(element)
+        content, params = as_numpy(content), as_numpy(params)
+        weights = as_numpy(weights) if weights is not None else None
+        b = content.shape[0]
+        if ctx is None:
+            ctx = self._get_ctx(b)
+            for _ in range(2):
+                mk = (lambda shape: torch.empty(shape, dtype=torch.float32).pin_memory().numpy()) if pinned else \
+                     (lambda shape: np.empty(shape, np.float32))
+                slots.append({"content": mk((ctx.cfg.max_batch,) + self.plan.input_shape),
+                              "params": mk((ctx.cfg.max_batch, self.plan.num_styles, self.num_style_parameters)),
+                              "weights": mk((ctx.cfg.max_batch,) + self.plan.output_shape[:2] + (max(self.plan.num_styles - 1, 1),)),
+                              "out": mk((ctx.cfg.max_batch,) + self.plan.output_shape)})
+        if len(pending) == 2:
+            t, sl, n = pending.pop(0)
+            ctx.transfer_wait(t)
+            yield sl["out"][:n].copy()
+        sl = slots[k % 2]
+        sl["content"][:b] = content
+        sl["params"][:b] = params
+        if weights is not None:
+            sl["weights"][:b] = weights
+        ticket = ctx.transfer_submit_host(sl["content"][:b], sl["params"][:b], sl["weights"][:b] if weights is not None else None,
+                                          sl["out"][:b])
+        pending.append((ticket, sl, b))
+    for t, sl, n in pending:
+        ctx.transfer_wait(t)
+        yield sl["out"][:n].copy()
+
+
+StyleTransferModel.predict_frames = _predict_frames
+
+
 def create_style_transfer_model(input_shape, output_shape, bottleneck_res_y, bottleneck_num_filters, num_styles,
                                 name="StyleTransferModel"):
     log.info(f"Using {num_styles} styles")

@@ -166,3 +166,25 @@ def test_mixed_precision_policy_selects_tensor_core_path(cuda_device):
         model.close()
     finally:
         mixed_precision.set_global_policy("float32")
+
+
+def test_streaming_predict_frames_matches_predict(cuda_device):
+    """The asynchronous double-buffered host pipeline (video loop) returns the same frames as predict()."""
+    mixed_precision.set_global_policy("mixed_bfloat16")
+    try:
+        model, p = styleTransfer.create_style_transfer_model((64, 128, 17), (64, 128, 3), 16, 128, 1)
+        rng = np.random.default_rng(0)
+        batches = []
+        for k in range(5):
+            batches.append({"content": O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=17).channels, seed=k,
+                                                           unit_depth=True),
+                            "style_params": rng.uniform(0.3, 1.2, (2, 1, p)).astype(np.float32)})
+        streamed = list(model.predict_frames(iter(batches)))
+        assert len(streamed) == 5
+        for el, got in zip(batches, streamed):
+            want = model.predict(el)
+            assert got.shape == want.shape == (2, 64, 128, 3)
+            assert np.abs(got - want).max() < 5e-3        # fp64 atomics in the statistics: order may differ
+        model.close()
+    finally:
+        mixed_precision.set_global_policy("float32")
