@@ -59,6 +59,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
     constexpr int CW = N >= 32 ? 32 : 16;              // columns per epilogue chunk
     constexpr int NCH = N / CW;
+    constexpr int ESPLIT = NCH >= 2 ? 2 : 1;           // epilogue warps per TMEM lane quadrant
     constexpr int KS = sched_ksteps(SCH, ROWB);         // K-steps per channel group
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA_M=128 needs 16 <= N <= 256, N % 16 == 0");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two");
@@ -94,7 +95,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * ESPLIT); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
@@ -191,9 +192,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         }
-    } else {
+    } else if (warp < 3 + 4 * ESPLIT) {
         // ================= epilogue ==============================================================
         const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int c_begin = ((warp - 3) >> 2) * (NCH / ESPLIT), c_end = c_begin + NCH / ESPLIT;   // this warp's column chunks
         const int row = q * 32 + lane;
         const int w_l = row >> 3, h_l = row & 7;
         float* my_sum = stat_s + q * 2 * N;      // per-warp column accumulators (lane j owns column c*CW+j)
@@ -203,7 +205,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         auto flush = [&]() {
             if (do_stats && cur_n >= 0) {
 #pragma unroll 1
-                for (int c = 0; c < NCH; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     const int col = c * CW + lane;
                     int ch = col;
                     bool on = lane < CW;
@@ -230,7 +232,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * N;
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 float v[32];
                 if (CW == 32) tmem_ld_32x32(taddr + c * 32, v);
                 else {
@@ -455,11 +457,11 @@ bool encode_s2d_map(CUtensorMap* out, const void* base, int B, int H, int W, int
     return true;
 }
 
-bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err) {
+bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err, int box_rows) {
     if (!umma_init(err)) return false;
     cuuint64_t gdim[2] = {64, (cuuint64_t)nblocks * N};
     cuuint64_t gstr[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)N};
+    cuuint32_t box[2] = {64, (cuuint32_t)(box_rows > 0 ? box_rows : N)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -16,8 +16,10 @@
 // SWIZZLE_128B, K-major).  Small layers keep all blocks resident in shared memory for the CTA's lifetime;
 // the 128->128 bottleneck convs stream them through a ring.
 //
-// Warp roles (224 threads): 0 = A TMA producer, 1 = B TMA producer, 2 = MMA issuer (one elected lane),
-// 3..6 = epilogue (TMEM -> registers -> global), two TMEM accumulator stages.
+// Warp roles (352 threads): 0 = A TMA producer, 1 = B TMA producer, 2 = MMA issuer (one elected lane),
+// 3..10 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quadrant split the column chunks when the
+// tile has more than one 32-column chunk -- the epilogue instruction stream was the bottleneck of the 128-column
+// kernels), two TMEM accumulator stages.
 #pragma once
 
 #include <functional>
@@ -88,7 +90,7 @@ struct HaloGemmParams {
     int stats_c = 0;
 };
 
-constexpr int kHaloThreads = 224;
+constexpr int kHaloThreads = 352;    // warps: 0 A-TMA, 1 B-TMA, 2 MMA, 3..10 epilogue (two per TMEM lane quadrant)
 constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4;
 
 struct HaloGemmLaunch {
@@ -112,7 +114,12 @@ bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, 
 // Packed weights: nblocks*N rows of 64 bf16; box = (64, N).
 // Space-to-depth view of an NHWC tensor (B, H, W, C), H and W even: dims (2C, H/2, 2, W/2, B), box (2C, 9, 2, 17, 1).
 bool encode_s2d_map(CUtensorMap* out, const void* base, int B, int H, int W, int C, std::string* err);
-bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err);
+bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err, int box_rows = 0);
+
+// 2-CTA (cta_group::2) weight-resident kernel for the 128-filter 3x3 bottleneck convs (halo_gemm2.cu); tmB_half has a 64-row box.
+size_t halo_gemm2_smem_bytes(int n_groups);
+cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
+                              cudaStream_t s);
 // Packs B: f(kstep, n, e) -> weight of K-step `kstep`, output column n, K element e (0..15).
 void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out);
 

@@ -1,0 +1,253 @@
+// 2-CTA (tcgen05 cta_group::2) variant of the halo GEMM for the 128->128 3x3 bottleneck convolutions.
+//
+// Why: with one CTA per tile the 288 KB weight matrix does not fit in shared memory and is re-streamed for every
+// 128-pixel tile; the B ring is latency bound and tensor-pipe activity stalls near 50 % (profiles/r01_02).  Here a
+// cluster of two CTAs works on two tiles at once with UMMA_M = 256: each CTA supplies its own 128-row A halo patch and
+// HALF of B (64 of the 128 output channels: 18 blocks x 8 KB = 144 KB), which therefore stays RESIDENT for the whole
+// kernel.  Per MMA each SM reads 4 KB of A + 2 KB of B from shared memory for 64 cycles of tensor work.
+//
+// Protocol (leader = even CTA of the pair):
+//   * both CTAs TMA their operands with .cta_group::2, completing transactions on the LEADER's full barriers;
+//   * the leader's elected thread issues tcgen05.mma.cta_group::2 and multicasts tcgen05.commit to the empty /
+//     accumulator-full barriers of BOTH CTAs;
+//   * both CTAs' epilogue warps drain their own TMEM half and arrive on the leader's accumulator-empty barrier.
+#include "halo_gemm.cuh"
+
+namespace rst {
+
+using namespace umma;
+
+__device__ __forceinline__ float warp_transpose_reduce2(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float send = upper ? v[i] : v[i + off];
+            float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+constexpr int kN2 = 128;                 // output channels
+constexpr int kRowB2 = 128;              // bytes per A row (64 channels)
+constexpr int kKS2 = sched_ksteps(SCH_C3, kRowB2);          // 36 K-steps per 64-channel group
+constexpr int kBHalf = (kN2 / 2) * 128;  // bytes of one B block half (4 K-steps x 64 rows)
+constexpr int kHalo2 = 10 * 18 * kRowB2;
+constexpr int kAStage2 = (kHalo2 + 1023) & ~1023;
+constexpr int kAStages2 = 3;
+constexpr int kTail2 = 6400;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloGemmParams p) {
+    constexpr int N = kN2, CW = 32, NCH = N / CW, ESPLIT = 2;
+    constexpr uint32_t TMEM_COLS = 2 * N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nblocks = p.n_groups * kKS2 / 4;               // 18 for 128 input channels
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + kAStages2 * kAStage2;
+    uint8_t* tail = sB + nblocks * kBHalf;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* acc_full = b_full + 2;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(tail + 256);
+    float* stat_s = bias_s + N;                              // [4 warps][2][N]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader_cta = rank == 0;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+    const int total_tiles = p.B * tiles_per_img;
+    const int total_pairs = (total_tiles + 1) / 2;
+    const int nclusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int ppc = (total_pairs + nclusters - 1) / nclusters;
+    const int pair_begin = cid * ppc;
+    const int pair_end = min(total_pairs, pair_begin + ppc);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        mbar_init(&b_full[0], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 4 * ESPLIT); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) stat_s[i] = 0.f;
+    __syncthreads();
+    cluster_sync();                                           // barriers of both CTAs are initialised
+    if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int t, int& n, int& h0, int& w0) {
+        if (t >= total_tiles) { n = p.B; h0 = 0; w0 = 0; return; }     // phantom tile: out of bounds everywhere -> zeros
+        n = t / tiles_per_img;
+        const int r = t - n * tiles_per_img;
+        h0 = (r / p.tiles_w) * 8; w0 = (r % p.tiles_w) * 16;
+    };
+
+    if (warp == 0) {
+        // ================= A producer (both CTAs): own halo patch, transactions land on the leader's barrier ====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int pr = pair_begin; pr < pair_end; ++pr) {
+                int n, h0, w0;
+                tile_coords(2 * pr + (int)rank, n, h0, w0);
+                for (int g = 0; g < p.n_groups; ++g) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    if (leader_cta) mbar_expect_tx(&a_full[stage], 2 * kHalo2);
+                    tma_load_4d_2sm(sA + stage * kAStage2, &tmA, &a_full[stage], g * 64, h0 - 1, w0 - 1, n);
+                    if (++stage == kAStages2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= B producer (both CTAs): this CTA's 64 output channels of every block, once ==========
+        if (lane == 0 && pair_begin < pair_end) {
+            if (leader_cta) mbar_expect_tx(&b_full[0], 2 * nblocks * kBHalf);
+            for (int kb = 0; kb < nblocks; ++kb)
+                tma_load_2d_2sm(sB + kb * kBHalf, &tmB, &b_full[0], 0, kb * N + (int)rank * (N / 2));
+        }
+    } else if (warp == 2) {
+        // ================= MMA issuer: leader CTA only ==========================================================
+        if (leader_cta) {
+            const uint32_t idesc = make_idesc_bf16(256, N);
+            const uint64_t da_const = make_smem_desc(0, 16, 10 * kRowB2, SWIZZLE_128B);
+            const uint64_t db_const = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
+            const bool issuer = elect_one();
+            uint32_t as = 0, aph = 0, cs = 0, cph = 0;
+            if (pair_begin < pair_end) mbar_wait(&b_full[0], 0);
+            const uint32_t sB16 = __shfl_sync(0xffffffffu, smem_u32(sB) >> 4, 0);
+            const uint32_t sA16 = __shfl_sync(0xffffffffu, smem_u32(sA) >> 4, 0);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            for (int pr = pair_begin; pr < pair_end; ++pr) {
+                mbar_wait(&acc_empty[cs], cph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_u + cs * N;
+                for (int g = 0; g < p.n_groups; ++g) {
+                    mbar_wait(&a_full[as], aph);
+                    tc_fence_after();
+                    const uint32_t a_base16 = sA16 + as * (kAStage2 >> 4);
+                    const uint32_t b_base16 = sB16 + g * (kKS2 / 4) * (kBHalf >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < kKS2; ++ks) {
+                        const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH_C3, kRowB2, ks) >> 4));
+                        const uint64_t db = db_const | (uint64_t)(b_base16 + (ks / 4) * (kBHalf >> 4) + (ks & 3) * 2);
+                        if (issuer) mma_f16_ss_2sm(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
+                    }
+                    if (issuer) mma_commit_2sm(&a_empty[as], 3);
+                    if (++as == kAStages2) { as = 0; aph ^= 1; }
+                }
+                if (issuer) mma_commit_2sm(&acc_full[cs], 3);
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (both CTAs): own 128 rows; two warps per lane quadrant split the columns ======
+        const int q = warp & 3;
+        const int c_begin = ((warp - 3) >> 2) * (NCH / ESPLIT), c_end = c_begin + NCH / ESPLIT;
+        const int row = q * 32 + lane;
+        const int w_l = row >> 3, h_l = row & 7;
+        float* my_sum = stat_s + q * 2 * N;
+        float* my_sq = my_sum + N;
+        const bool do_stats = p.stats != nullptr;
+        int cur_n = -1;
+        auto flush = [&]() {
+            if (do_stats && cur_n >= 0 && cur_n < p.B) {
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; ++c) {
+                    const int col = c * CW + lane;
+                    double* dst = p.stats + ((size_t)cur_n * p.stats_c + col) * 2;
+                    atomicAdd(dst, (double)my_sum[col]);
+                    atomicAdd(dst + 1, (double)my_sq[col]);
+                    my_sum[col] = 0.f; my_sq[col] = 0.f;
+                }
+            }
+        };
+        uint32_t cs = 0, cph = 0;
+        for (int pr = pair_begin; pr < pair_end; ++pr) {
+            int n, h0, w0;
+            tile_coords(2 * pr + (int)rank, n, h0, w0);
+            const int gh = h0 + h_l, gw = w0 + w_l;
+            const bool valid = n < p.B && gh < p.H && gw < p.WRU;
+            if (n != cur_n) { flush(); cur_n = n; }
+            mbar_wait(&acc_full[cs], cph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * N;
+#pragma unroll 1
+            for (int c = c_begin; c < c_end; ++c) {
+                float v[32];
+                tmem_ld_32x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                const float* bs_ = bias_s + c * CW;
+                uint32_t packed[CW / 2];
+#pragma unroll
+                for (int j = 0; j < CW; j += 2) {
+                    const float x0 = fmaxf(v[j] + bs_[j], 0.f), x1 = fmaxf(v[j + 1] + bs_[j + 1], 0.f);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                    v[j] = valid ? __low2float(h2) : 0.f;
+                    v[j + 1] = valid ? __high2float(h2) : 0.f;
+                }
+                if (valid) {
+                    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) +
+                                                         (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW);
+#pragma unroll
+                    for (int j = 0; j < CW / 8; ++j)
+                        o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+                if (do_stats) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = warp_transpose_reduce2(v, lane);
+                    const float s2 = warp_transpose_reduce2(sq, lane);
+                    my_sum[c * CW + lane] += s1;
+                    my_sq[c * CW + lane] += s2;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&acc_empty[cs]);
+            if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
+        flush();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                                           // both CTAs are done with TMEM and with remote barriers
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+size_t halo_gemm2_smem_bytes(int n_groups) {
+    return (size_t)kAStages2 * kAStage2 + (size_t)(n_groups * kKS2 / 4) * kBHalf + kTail2 + 1024;
+}
+
+// Weights for the 2-CTA kernel use the same packed blocks; the tensor map's box is 64 rows (one CTA's half of N).
+cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
+                              cudaStream_t s) {
+    static size_t configured = 0;
+    const size_t smem = halo_gemm2_smem_bytes(p.n_groups);
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(halo_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int total = p.B * p.tiles_h * p.tiles_w;
+    if (total == 0) return cudaSuccess;
+    const int pairs = (total + 1) / 2;
+    int clusters = num_sms / 2;
+    if (pairs < clusters) clusters = pairs;
+    halo_gemm2_kernel<<<2 * clusters, kHaloThreads, smem, s>>>(tmA, tmB_half, p);
+    return cudaGetLastError();
+}
+
+}  // namespace rst

@@ -7,6 +7,8 @@
 //        each followed by ONE bf16 pass: normalise + style affine (+ReLU | + skip add)
 //     -> expand_0 / expand_1 (stride-2 transposed conv as a 2x2-tap GEMM over 4 output phases, stats fused)
 //     -> expand_last 9x9 (4 pixels per GEMM row, 12 of 16 columns used) -> normalise + sigmoid -> fp32 image
+#include <cstdlib>
+
 #include "halo_gemm.cuh"
 #include "rst_ctx.h"
 
@@ -18,7 +20,8 @@ namespace rst {
 struct HaloConv {
     HaloGemmLaunch launch;
     HaloGemmParams p;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmB_half;
+    bool two_cta = false;          // 128->128 3x3 convs: cta_group::2 kernel with resident weights
     __nv_bfloat16* w_packed = nullptr;
     float* col_bias = nullptr;     // [N] bias expanded to GEMM columns
     float* col_scale = nullptr;    // [N] optional post affine
@@ -58,12 +61,18 @@ struct HaloConv {
             if (!encode_s2d_map(&tmA, x, B, 2 * H, 2 * WRU, in_C / 2, err)) return false;
         } else if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
         if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
+        const char* env = getenv("RST_TRUNK_2CTA");
+        two_cta = launch.sched == SCH_C3 && launch.N == 128 && launch.row_bytes == 128 && launch.epi == EPI_NHWC &&
+                  launch.mode == HALO_MODE_RELU && !(env && env[0] == '0') &&
+                  halo_gemm2_smem_bytes(p.n_groups) <= 227 * 1024;
+        if (two_cta && !encode_weight_map(&tmB_half, w_packed, total_ksteps / 4, launch.N, err, launch.N / 2)) return false;
         return halo_gemm_plan(&launch, &p, err);
     }
 
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
+        if (two_cta && !y_f32) return launch_halo_gemm2(tmA, tmB_half, q, num_sms, s);
         return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
     }
 };
