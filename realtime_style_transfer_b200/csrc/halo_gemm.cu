@@ -49,8 +49,12 @@ constexpr int MODE_RELU = 1;      // ReLU after the bias
 constexpr int MODE_POST = 2;      // then per-column affine (inference BatchNorm) and a second ReLU
 constexpr int MODE_F32 = 4;       // store fp32 instead of bf16
 
+// epilogue warps per TMEM lane quadrant: one per 32-column chunk (the epilogue is issue-latency bound, more warps hide it)
+__host__ __device__ constexpr int halo_esplit(int n) { return n >= 128 ? 4 : n >= 64 ? 2 : 1; }
+__host__ __device__ constexpr int halo_threads(int n) { return 96 + 128 * halo_esplit(n); }
+
 template <int N, int ROWB, int EPI, int MODE, int SCH, bool BRES>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(halo_threads(N), 1)
 halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const HaloGemmParams p) {
     constexpr int BBLK = N * 128;                      // bytes of one B block (4 K-steps)
@@ -59,7 +63,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
     constexpr int CW = N >= 32 ? 32 : 16;              // columns per epilogue chunk
     constexpr int NCH = N / CW;
-    constexpr int ESPLIT = NCH >= 2 ? 2 : 1;           // epilogue warps per TMEM lane quadrant
+    constexpr int ESPLIT = halo_esplit(N);             // epilogue warps per TMEM lane quadrant
     constexpr int KS = sched_ksteps(SCH, ROWB);         // K-steps per channel group
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA_M=128 needs 16 <= N <= 256, N % 16 == 0");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two");
@@ -231,16 +235,9 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&acc_full[cs], cph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * N;
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                float v[32];
-                if (CW == 32) tmem_ld_32x32(taddr + c * 32, v);
-                else {
-                    tmem_ld_32x16(taddr + c * 16, v);
-#pragma unroll
-                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
-                }
-                tmem_ld_wait();
+            // A warp owns one or two column chunks: all its TMEM loads are issued up front, the accumulator stage is handed
+            // back to the MMA warp as soon as the values are in registers, then the math / stores / statistics run.
+            auto process = [&](float (&v)[32], int c) {
                 const float* bs_ = bias_s + c * CW;
 #pragma unroll
                 for (int j = 0; j < CW; ++j) {
@@ -308,10 +305,23 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         my_sq[c * CW + lane] += s2;
                     }
                 }
+            };
+            constexpr int CPW = NCH / ESPLIT;        // chunks per warp: 1 or 2
+            static_assert(CPW == 1 || CPW == 2, "epilogue warp handles one or two chunks");
+            float va[32], vb[32];
+            if (CW == 32) tmem_ld_32x32(taddr + c_begin * 32, va);
+            else {
+                tmem_ld_32x16(taddr + c_begin * 16, va);
+#pragma unroll
+                for (int j = 16; j < 32; ++j) va[j] = 0.f;
             }
+            if (CPW == 2) tmem_ld_32x32(taddr + (c_begin + 1) * 32, vb);
+            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[cs]);
+            process(va, c_begin);
+            if (CPW == 2) process(vb, c_begin + 1);
             if (++cs == 2) { cs = 0; cph ^= 1; }
         }
         flush();
@@ -368,7 +378,7 @@ static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, con
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES><<<grid, kHaloThreads, l.smem_bytes, s>>>(tmA, tmB, p);
+    halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES><<<grid, halo_threads(N), l.smem_bytes, s>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 

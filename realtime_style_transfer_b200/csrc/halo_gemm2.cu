@@ -39,10 +39,13 @@ constexpr int kHalo2 = 10 * 18 * kRowB2;
 constexpr int kAStage2 = (kHalo2 + 1023) & ~1023;
 constexpr int kAStages2 = 3;
 constexpr int kTail2 = 6400;
+constexpr int kPrefetchPairs = 3;         // L2 prefetch distance of the A producer, in tile pairs
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+constexpr int kThreads2 = 96 + 128 * 4;  // 3 control warps + 16 epilogue warps (one per lane quadrant and 32-column chunk)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloGemmParams p) {
-    constexpr int N = kN2, CW = 32, NCH = N / CW, ESPLIT = 2;
+    constexpr int N = kN2, CW = 32, NCH = N / CW, ESPLIT = 4;
     constexpr uint32_t TMEM_COLS = 2 * N;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,6 +103,10 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t stage = 0, phase = 0;
             for (int pr = pair_begin; pr < pair_end; ++pr) {
                 int n, h0, w0;
+                if (pr + kPrefetchPairs < pair_end) {            // pull a later tile's halo into L2 while this one is consumed
+                    tile_coords(2 * (pr + kPrefetchPairs) + (int)rank, n, h0, w0);
+                    for (int g = 0; g < p.n_groups; ++g) tma_prefetch_4d(&tmA, g * 64, h0 - 1, w0 - 1, n);
+                }
                 tile_coords(2 * pr + (int)rank, n, h0, w0);
                 for (int g = 0; g < p.n_groups; ++g) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
@@ -182,11 +189,9 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&acc_full[cs], cph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * N;
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                float v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                tmem_ld_wait();
+            // Each warp owns one 32-column chunk of one lane quadrant: the accumulator stage is handed back to the MMA warp
+            // as soon as the values are in registers, then the math / stores / statistics run.
+            auto process = [&](float (&v)[32], int c) {
                 const float* bs_ = bias_s + c * CW;
                 uint32_t packed[CW / 2];
 #pragma unroll
@@ -213,10 +218,14 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     my_sum[c * CW + lane] += s1;
                     my_sq[c * CW + lane] += s2;
                 }
-            }
+            };
+            float va[32];
+            tmem_ld_32x32(taddr + c_begin * 32, va);
+            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&acc_empty[cs]);
+            process(va, c_begin);
             if (++cs == 2) { cs = 0; cph ^= 1; }
         }
         flush();
@@ -246,7 +255,7 @@ cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_hal
     const int pairs = (total + 1) / 2;
     int clusters = num_sms / 2;
     if (pairs < clusters) clusters = pairs;
-    halo_gemm2_kernel<<<2 * clusters, kHaloThreads, smem, s>>>(tmA, tmB_half, p);
+    halo_gemm2_kernel<<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
     return cudaGetLastError();
 }
 

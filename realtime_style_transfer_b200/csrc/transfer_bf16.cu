@@ -72,6 +72,7 @@ struct HaloConv {
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
+        if (getenv("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiment only (wrong results)
         if (two_cta && !y_f32) return launch_halo_gemm2(tmA, tmB_half, q, num_sms, s);
         return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
     }

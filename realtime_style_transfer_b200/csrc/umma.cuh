@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // ---- tcgen05 ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp, ncols pow2 >= 32
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -139,7 +146,7 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m,
 }
 // arrive on the leader CTA's copy of a barrier (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {   // same warp in BOTH CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
