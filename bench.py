@@ -317,6 +317,7 @@ def main():
             "roofline": roof,
             "whole_net": whole,
             "kernel_shares": shares,
+            "sum_kernel_ms_per_step": total_group_ms / args.steps,
             "dominant_group": dominant[0],
             "checksum": checksum,
         }
