@@ -76,7 +76,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nbslots = BRES ? blocks_per_tile : p.n_bstages;
     uint8_t* sA = smem;
     uint8_t* sB = sA + p.n_astages * a_stage_bytes;
-    uint8_t* tail = sB + nbslots * BBLK;
+    uint8_t* tail = sB + (sched_b_units(SCH) ? kStem2Boxes * 8192 : nbslots * BBLK);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 4;
     uint64_t* b_full = a_empty + 4;
@@ -134,7 +134,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ================= B producer ===========================================================
         if (lane == 0 && tile_begin < tile_end) {
-            if (BRES) {
+            if (sched_b_units(SCH)) {
+                mbar_expect_tx(&b_full[0], kStem2Boxes * 8192);
+                for (int kb = 0; kb < kStem2Boxes; ++kb) tma_load_2d(sB + kb * 8192, &tmB, &b_full[0], 0, kb * 256);
+            } else if (BRES) {
                 mbar_expect_tx(&b_full[0], blocks_per_tile * BBLK);
                 for (int kb = 0; kb < blocks_per_tile; ++kb) tma_load_2d(sB + kb * BBLK, &tmB, &b_full[0], 0, kb * N);
             } else {
@@ -156,7 +159,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         {
             const uint32_t idesc = make_idesc_bf16(128, N);
             const uint64_t da_const = make_smem_desc(0, 16, sched_halo_h(SCH) * ROWB, SWZ);
-            const uint64_t db_const = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
+            const uint64_t db_const = sched_b_units(SCH) ? make_smem_desc(0, 16, 256, SWIZZLE_32B) : make_smem_desc(0, 16, 1024, SWIZZLE_128B);
             const bool leader = elect_one();
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
             if (BRES && tile_begin < tile_end) mbar_wait(&b_full[0], 0);
@@ -182,7 +185,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             b_base16 = sB16 + bs * (BBLK / 16);
                         }
                         const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH, ROWB, ks) >> 4));
-                        const uint64_t db = db_const | (uint64_t)(b_base16 + (BRES ? (ks / 4) * (BBLK / 16) : 0) + (ks & 3) * 2);
+                        const uint64_t db = db_const | (uint64_t)(sched_b_units(SCH) ? sB16 + sched_b_unit(SCH, ks) * 64
+                                                                                    : b_base16 + (BRES ? (ks / 4) * (BBLK / 16) : 0) + (ks & 3) * 2);
                         if (leader) mma_f16_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
                         if (!BRES && (ks & 3) == 3) {
                             if (leader) mma_commit(&b_empty[bs]);
@@ -348,7 +352,9 @@ bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err) {
     const int fixed = 1024 + kTailBytes;
     p->b_resident = sched_resident(*l) ? 1 : 0;
     int b_bytes;
-    if (p->b_resident) {
+    if (sched_b_units(l->sched)) {
+        b_bytes = kStem2Boxes * 8192;
+    } else if (p->b_resident) {
         b_bytes = blocks * bblk;
     } else {
         p->n_bstages = 6;
@@ -392,6 +398,7 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
     RST_HALO_CASE(128, 64, EPI_NHWC, MODE_RELU, SCH_C3, true)               // residual_block_0/conv0 (32 input channels)
     RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU, SCH_C3, true)
     RST_HALO_CASE(64, 64, EPI_NHWC, MODE_RELU, SCH_C3, true)
+    RST_HALO_CASE(64, 128, EPI_NHWC, STEM_MODE, SCH_STEM2, true)            // 9x9 stem, 17 channels, two pixels per GEMM row
     RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 1, true)      // 9x9 stem, 17 channels: 16 real + 1 windowed
     RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 0, true)      // 5..16 channels
     RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 2, true)     // 18 channels
@@ -478,6 +485,22 @@ bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, s
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (err) *err = "cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+bool encode_weight_unit_map(CUtensorMap* out, const void* base, int rows, std::string* err) {
+    if (!umma_init(err)) return false;
+    cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {32};
+    cuuint32_t box[2] = {16, 256};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled(weight units) failed with code " + std::to_string((int)r);
         return false;
     }
     return true;
@@ -793,7 +816,7 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
     if (p.x_f32 && p.residual) return cudaErrorInvalidValue;
     const bool blend = p.num_styles == 2 && p.weights != nullptr;
     if (!p.x_f32 && !p.y_f32 && p.act != ACT_SIGMOID && (p.C == 16 || p.C == 32 || p.C == 64 || p.C == 128)) {
-        const int pix_per_block = max(256, 65536 / p.C);          // >= 8 vectors per thread
+        const int pix_per_block = max(256, 131072 / p.C);         // long streams per CTA measured faster than many short CTAs
         dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
         if (blend && p.residual) cin_apply_fast_kernel<true, true><<<grid, 256, 0, s>>>(p, pix_per_block);
         else if (blend) cin_apply_fast_kernel<true, false><<<grid, 256, 0, s>>>(p, pix_per_block);

@@ -41,23 +41,39 @@ enum HaloEpi : int {
 // SCH_STEM + 4*REAL + NV: 9x9 taps over the 16 real channels (REAL) plus 9 row taps per windowed channel group (NV).
 // SCH_S2D: 3x3 stride-2 conv over the space-to-depth view (h2, row parity, w2, [col parity x channels]) of the input:
 //          row taps ky -> (h2 + ky/2, parity ky%2); column taps kx -> (w2 + kx/2, parity kx%2) = channel slice of the row.
-enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM = 10 };
+// SCH_STEM2: the 17-channel stem with TWO pixels per GEMM row (row = pixel pair = 2 x [16 real | 16 windowed] = 128 B):
+//          N = 2 x 32 output columns, 10 window pixels per row tap.  The block-Toeplitz weight matrix is never
+//          materialised: B is stored as 32-row "units" [0, W(ky,8), ..., W(ky,0), 0] per row tap and every K-step reads
+//          TWO ADJACENT units through a shifted SWIZZLE_32B descriptor (the halo trick applied to the weights).
+enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM2 = 4, SCH_STEM = 10 };
+__host__ __device__ constexpr bool sched_b_units(int sch) { return sch == SCH_STEM2; }
+constexpr int kStem2Units = 9 * 11 + 9 * 3;          // 126 units of 32 rows x 32 bytes
+constexpr int kStem2Boxes = (kStem2Units * 32 + 255) / 256;   // TMA boxes of 256 rows (8 KB)
+// unit index (1 KB each) where K-step ks of SCH_STEM2 starts reading its 64 B rows
+__host__ __device__ constexpr int sched_b_unit(int sch, int ks) {
+    return sch != SCH_STEM2 ? 0 : ks < 90 ? (ks / 10) * 11 + (9 - ks % 10) : 99 + ((ks - 90) / 2) * 3 + (1 - (ks - 90) % 2);
+}
 __host__ __device__ constexpr int sched_real_ksteps(int sch, int rowb) {
     return sch == SCH_C3 ? 9 * (rowb / 32) : sch == SCH_T2 ? 4 * (rowb / 32) : sch == SCH_HEAD ? 108
-           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64)
+           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 108
            : 81 * ((sch - SCH_STEM) / 4) + 9 * ((sch - SCH_STEM) % 4);
 }
 __host__ __device__ constexpr int sched_ksteps(int sch, int rowb) { return (sched_real_ksteps(sch, rowb) + 3) / 4 * 4; }
 __host__ __device__ constexpr int sched_halo_h(int sch) { return sch == SCH_C3 ? 10 : sch == SCH_T2 ? 9 : sch == SCH_S2D ? 18 : 16; }
-__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : 24; }
+__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : sch == SCH_STEM2 ? 20 : 24; }
 __host__ __device__ constexpr int sched_oy(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : -4; }
-__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD ? -1 : -4; }
+__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD ? -1 : sch == SCH_STEM2 ? -2 : -4; }
 // byte offset of K-step ks into the halo patch
 __host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
     if (ks >= sched_real_ksteps(sch, rowb)) return 0;
     if (sch == SCH_C3) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 3) * 10 + tap / 3) * rowb + (ks % kper) * 32; }
     if (sch == SCH_T2) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 2) * 9 + tap / 2) * rowb + (ks % kper) * 32; }
     if (sch == SCH_HEAD) { const int dy = ks / 12, kx = ks % 12; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
+    if (sch == SCH_STEM2) {
+        if (ks < 90) { const int ky = ks / 10, kxp = ks % 10; return ((kxp / 2) * 16 + ky) * 128 + (kxp % 2) * 64; }
+        const int ky = (ks - 90) / 2, j = (ks - 90) % 2;
+        return (2 * 16 + ky) * 128 + j * 64 + 32;
+    }
     if (sch == SCH_S2D) {
         // per row tap: kper slices at w2+0 (column taps 0,1) then kper/2 slices at w2+1 (column tap 2)
         const int kper = rowb / 32, per_ky = kper + kper / 2, ky = ks / per_ky, l = ks % per_ky;
@@ -115,6 +131,8 @@ bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, 
 // Space-to-depth view of an NHWC tensor (B, H, W, C), H and W even: dims (2C, H/2, 2, W/2, B), box (2C, 9, 2, 17, 1).
 bool encode_s2d_map(CUtensorMap* out, const void* base, int B, int H, int W, int C, std::string* err);
 bool encode_weight_map(CUtensorMap* out, const void* base, int nblocks, int N, std::string* err, int box_rows = 0);
+// Weight units (SCH_STEM2): rows of 16 bf16 (32 B), box = (16, 256), SWIZZLE_32B.
+bool encode_weight_unit_map(CUtensorMap* out, const void* base, int rows, std::string* err);
 
 // 2-CTA (cta_group::2) weight-resident kernel for the 128-filter 3x3 bottleneck convs (halo_gemm2.cu); tmB_half has a 64-row box.
 size_t halo_gemm2_smem_bytes(int n_groups);

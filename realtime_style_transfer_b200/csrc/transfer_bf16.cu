@@ -60,7 +60,9 @@ struct HaloConv {
         if (launch.sched == SCH_S2D) {
             if (!encode_s2d_map(&tmA, x, B, 2 * H, 2 * WRU, in_C / 2, err)) return false;
         } else if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
-        if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
+        if (sched_b_units(launch.sched)) {
+            if (!encode_weight_unit_map(&tmB, w_packed, kStem2Boxes * 256, err)) return false;
+        } else if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
         const char* env = getenv("RST_TRUNK_2CTA");
         two_cta = launch.sched == SCH_C3 && launch.N == 128 && launch.row_bytes == 128 && launch.epi == EPI_NHWC &&
                   launch.mode == HALO_MODE_RELU && !(env && env[0] == '0') &&
@@ -72,7 +74,8 @@ struct HaloConv {
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
-        if (getenv("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiment only (wrong results)
+        if (getenv("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiments only (wrong results)
+        if (getenv("RST_EXP_NOSTORE")) q.H = 0;
         if (two_cta && !y_f32) return launch_halo_gemm2(tmA, tmB_half, q, num_sms, s);
         return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
     }
@@ -147,6 +150,34 @@ static bool setup_stem(HaloConv* c, int C, int co, const float* k, const float* 
     col_scale->assign(bn_scale, bn_scale + co);
     col_shift->assign(bn_shift, bn_shift + co);
     return true;
+}
+
+// 17-channel 9x9 stem with two pixels per GEMM row (SCH_STEM2): input rows are pixel PAIRS of the packed tensor
+// (B, H, W/2, 64), output is (B, H, W/2, 2 x 32) = the same bytes as NHWC-32.  Weights are stored as 32-row units.
+static void setup_stem2(HaloConv* c, const float* k, const float* bias, const float* bn_scale, const float* bn_shift,
+                        std::vector<__nv_bfloat16>* packed, std::vector<float>* col_bias, std::vector<float>* col_scale,
+                        std::vector<float>* col_shift) {
+    const int C = 17, co = 32;
+    c->launch.N = 64; c->launch.row_bytes = 128; c->launch.epi = EPI_NHWC;
+    c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST;
+    c->in_C = 64; c->p.n_groups = 1;
+    use_sched(c, SCH_STEM2);
+    c->p.out_C = 64; c->p.stats_c = 64;
+    packed->assign((size_t)kStem2Boxes * 256 * 16, __float2bfloat16(0.f));
+    auto put = [&](int unit, int row, int e, float w) { (*packed)[((size_t)unit * 32 + row) * 16 + e] = __float2bfloat16(w); };
+    for (int ky = 0; ky < 9; ++ky) {
+        for (int s = 1; s <= 9; ++s) {                       // unit s of the sequence holds column tap kx = 9 - s
+            const int kx = 9 - s;
+            for (int o = 0; o < co; ++o)
+                for (int e = 0; e < 16; ++e) put(ky * 11 + s, o, e, k[((size_t)(ky * 9 + kx) * C + e) * co + o]);
+        }
+        for (int o = 0; o < co; ++o)                         // windowed 17th channel: element e = column tap
+            for (int e = 0; e < 9; ++e) put(99 + ky * 3 + 1, o, e, k[((size_t)(ky * 9 + e) * C + 16) * co + o]);
+    }
+    col_bias->resize(64); col_scale->resize(64); col_shift->resize(64);
+    for (int n = 0; n < 64; ++n) {
+        (*col_bias)[n] = bias[n % co]; (*col_scale)[n] = bn_scale[n % co]; (*col_shift)[n] = bn_shift[n % co];
+    }
 }
 
 // 3x3 stride-2 'same' conv on even-sized inputs (TF pads 0 before / 1 after), Keras kernel (3,3,ci,co), followed by
@@ -303,11 +334,17 @@ int bf16_commit(rst_ctx* c) {
         std::vector<float> scale(L.co), shift(L.co);
         RST_CUDA(c, cudaMemcpy(scale.data(), c->folded[L.name + "/bn/scale"], L.co * 4, cudaMemcpyDeviceToHost));
         RST_CUDA(c, cudaMemcpy(shift.data(), c->folded[L.name + "/bn/shift"], L.co * 4, cudaMemcpyDeviceToHost));
-        if (!setup_stem(&st->stem, L.ci, L.co, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb, &cs, &csh))
+        const char* env2 = getenv("RST_STEM_PAIRS");
+        const bool pairs = L.ci == 17 && L.co == 32 && L.wi % 2 == 0 && !(env2 && env2[0] == '0');
+        if (pairs) {
+            setup_stem2(&st->stem, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb, &cs, &csh);
+        } else if (!setup_stem(&st->stem, L.ci, L.co, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb,
+                               &cs, &csh)) {
             return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: stem channel layout");
+        }
         RST_CUDA(c, st->stem.upload(packed, cb, &cs, &csh));
-        st->stem.p.out_H = L.ho; st->stem.p.out_W = L.wo;
-        if (!st->stem.bind_input(st->s_in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        st->stem.p.out_H = L.ho; st->stem.p.out_W = pairs ? L.wo / 2 : L.wo;
+        if (!st->stem.bind_input(st->s_in, B, L.hi, pairs ? L.wi / 2 : L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
     }
     // ---- strided encoder convs ----
     for (size_t i = 1; i < c->contract.size(); ++i) {
@@ -494,13 +531,18 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
     std::vector<float> cb, cs, csh;
     StemLayout SL{};
     int oh = h, ow = w, wru = w;
-    bool y_f32 = false;
+    bool y_f32 = false, stem_pairs = false;
     if (kind == K3) {
         setup_conv3x3(&hc, ci, co, hk.data(), hb.data(), act, &packed, &cb);
     } else if (kind == STEM) {
         std::vector<float> one(co, 1.f), zero(co, 0.f);
         stem_layout(ci, &SL);
-        setup_stem(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
+        if (ci == 17 && w % 2 == 0 && !getenv("RST_STEM_PAIRS_OFF")) {
+            setup_stem2(&hc, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
+            wru = w / 2; stem_pairs = true;
+        } else {
+            setup_stem(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
+        }
     } else if (kind == S2) {
         std::vector<float> one(co, 1.f), zero(co, 0.f);
         setup_conv_s2(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
@@ -524,7 +566,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
         else e = launch_f32_to_bf16_pad(d_x, xb, pin, ci, in_c_dev, s);
     }
     if (e == cudaSuccess) {
-        hc.p.out_H = oh; hc.p.out_W = ow;
+        hc.p.out_H = oh; hc.p.out_W = stem_pairs ? ow / 2 : ow;
         if (!hc.bind_input(xb, batch, kind == S2 ? oh : h, wru, err)) rc = RST_ERR_CUDA;
     }
     if (e == cudaSuccess && rc == RST_OK) {
