@@ -224,6 +224,7 @@ static void free_ctx(rst_ctx* c) {
     for (float* p : {c->st_content, c->st_params, c->st_weights, c->st_out, c->st_style}) if (p) cudaFree(p);
     for (auto& kv : c->taps) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     c->bf16.reset();
     c->train.reset();
     if (c->pipe.ready) {
@@ -402,6 +403,8 @@ extern "C" int rst_commit_weights(rst_ctx* ctx) {
         int rc = bf16_commit(ctx);
         if (rc) return rc;
     }
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);     // captured graphs hold the old operands
+    ctx->graphs.clear();
     ctx->committed = true;
     return RST_OK;
 }
@@ -587,9 +590,48 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
     cudaSetDevice(ctx->device);
     ctx->launches = 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (ctx->cfg.precision == RST_PRECISION_BF16)
-        return bf16_transfer_forward(ctx, d_content, d_style_params, d_style_weights, d_out, batch, s);
-    return fp32_transfer_forward(ctx, d_content, d_style_params, d_style_weights, d_out, batch, s);
+    auto run = [&]() -> int {
+        if (ctx->cfg.precision == RST_PRECISION_BF16)
+            return bf16_transfer_forward(ctx, d_content, d_style_params, d_style_weights, d_out, batch, s);
+        return fp32_transfer_forward(ctx, d_content, d_style_params, d_style_weights, d_out, batch, s);
+    };
+    // Replay a captured CUDA graph when the same buffers come back (video loop / pipelined host API); the legacy default
+    // stream cannot be captured, profiling and taps need the eager path.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool graphable = ctx->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+                           !ctx->profiling && !ctx->keep_taps &&
+                           cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    if (!graphable) return run();
+    for (auto& g : ctx->graphs)
+        if (g.batch == batch && g.content == d_content && g.params == d_style_params && g.weights == d_style_weights &&
+            g.out == d_out) {
+            RST_CUDA(ctx, cudaGraphLaunch(g.exec, s));
+            ctx->launches = g.launches;
+            return RST_OK;
+        }
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return run();
+    }
+    int rc = run();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc != RST_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->use_graphs = false;                 // do not retry capture on this context
+        return rc != RST_OK ? rc : run();
+    }
+    rst_ctx::GraphEntry ge;
+    ge.batch = batch; ge.content = d_content; ge.params = d_style_params; ge.weights = d_style_weights; ge.out = d_out;
+    ge.launches = ctx->launches;
+    e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); ctx->use_graphs = false; return run(); }
+    if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+    ctx->graphs.push_back(ge);
+    RST_CUDA(ctx, cudaGraphLaunch(ge.exec, s));
+    return RST_OK;
 }
 
 extern "C" int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,

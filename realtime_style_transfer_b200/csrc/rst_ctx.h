@@ -96,6 +96,14 @@ struct rst_ctx {
     std::shared_ptr<rst::Bf16State> bf16;
     std::shared_ptr<rst::TrainState> train;
 
+    // ---- CUDA-graph cache of whole forwards (launch-bound inner loop: ~30 kernels per batch) ----
+    struct GraphEntry {
+        int batch = 0; const void *content = nullptr, *params = nullptr, *weights = nullptr, *out = nullptr;
+        cudaGraphExec_t exec = nullptr; int64_t launches = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graphs = true;
+
     // ---- debug / accounting ----
     bool keep_taps = false;
     std::map<std::string, rst::Tap> taps;
