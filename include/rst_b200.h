@@ -141,6 +141,26 @@ int rst_op_apply_style_weights(const float* d_weights, const float* d_params, fl
 /* get_gram_matrix_model (styleLoss.py:11-18): (B,H,W,C) -> (B,C,C), divided by H*W. */
 int rst_op_gram(const float* d_x, float* d_gram, int batch, int h, int w, int c, void* stream);
 
+/* ---- training loss (models/styleLoss.py) ------------------------------------------------------------------------ */
+typedef struct rst_loss rst_loss;
+/* StyleLossModelVGG(input_shape) + make_style_loss_function(loss_model, output_shape, num_styles=1, with_depth_loss=False)
+ * (styleLoss.py:69-109, :295-369): VGG16 to block5_conv3 with style taps block{1,2}_conv2, block{3,4}_conv3. */
+int rst_loss_create(int h, int w, int max_batch, int device, rst_loss** out);
+int rst_loss_destroy(rst_loss* loss);
+const char* rst_loss_last_error(const rst_loss* loss);
+/* Keras VGG16 variables: "block1_conv1/kernel" (3,3,ci,co), "block1_conv1/bias", ... "block5_conv3/bias". */
+int rst_loss_set_weight(rst_loss* loss, const char* name, const float* h_data, const int64_t* shape, int ndim);
+int rst_loss_commit(rst_loss* loss);
+/* content / style / total-variation factors (defaults 1e4, 1e-3, 1e-1: styleLoss.py:101-104) */
+int rst_loss_set_factors(rst_loss* loss, float content, float style, float tv);
+/* compute_loss(y_pred, y_true) (styleLoss.py:363-367): d_losses (B,4) = [loss, feature_loss, style_loss,
+ * total_variation_loss], each a per-sample value like the reference's (B,) vectors. */
+int rst_loss_forward(rst_loss* loss, const float* d_pred, const float* d_gt_content, const float* d_gt_style,
+                     float* d_losses, int batch, void* stream);
+/* Gradient of sum_b loss[b] w.r.t. the prediction (Keras differentiates the loss VECTOR, i.e. its batch sum:
+ * styleTransferTrainingModel.py:26-29), using the activations saved by the last rst_loss_forward. */
+int rst_loss_backward(rst_loss* loss, const float* d_pred, float* d_grad_pred, int batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

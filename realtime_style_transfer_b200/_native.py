@@ -72,6 +72,14 @@ SIGNATURES = {
     "rst_op_cin": (C.c_int, [_vp, _vp, _vp, _vp] + [C.c_int] * 6 + [_vp]),
     "rst_op_apply_style_weights": (C.c_int, [_vp, _vp, _vp] + [C.c_int] * 4 + [_vp]),
     "rst_op_gram": (C.c_int, [_vp, _vp] + [C.c_int] * 4 + [_vp]),
+    "rst_loss_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "rst_loss_destroy": (C.c_int, [_vp]),
+    "rst_loss_last_error": (C.c_char_p, [_vp]),
+    "rst_loss_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, _i64p, C.c_int]),
+    "rst_loss_commit": (C.c_int, [_vp]),
+    "rst_loss_set_factors": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float]),
+    "rst_loss_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "rst_loss_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
 }
 
 _lib = None
@@ -282,3 +290,47 @@ def op_apply_style_weights(d_weights, d_params, d_out, batch, h, w, f, stream=0)
 
 def op_gram(d_x, d_gram, batch, h, w, c, stream=0):
     _op_check(load_library().rst_op_gram(_vp(d_x), _vp(d_gram), batch, h, w, c, _vp(stream) if stream else None))
+
+
+class NativeLoss:
+    """Owns one rst_loss (VGG16 content / Gram style / total-variation loss, forward and backward)."""
+
+    def __init__(self, h: int, w: int, max_batch: int, device: int = 0):
+        self.lib = load_library()
+        handle = _vp()
+        rc = self.lib.rst_loss_create(int(h), int(w), int(max_batch), device, C.byref(handle))
+        if rc != 0:
+            raise RstError(rc, (self.lib.rst_loss_last_error(None) or b"").decode())
+        self.handle, self.h, self.w, self.max_batch, self.device = handle, h, w, max_batch, device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RstError(rc, (self.lib.rst_loss_last_error(self.handle) or b"").decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.rst_loss_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, weights: Dict[str, np.ndarray]):
+        for name, value in weights.items():
+            arr = _host_f32(value)
+            shape = (C.c_int64 * arr.ndim)(*arr.shape)
+            self._check(self.lib.rst_loss_set_weight(self.handle, name.encode(), _ptr(arr), shape, arr.ndim))
+        self._check(self.lib.rst_loss_commit(self.handle))
+
+    def set_factors(self, content: float, style: float, tv: float):
+        self._check(self.lib.rst_loss_set_factors(self.handle, content, style, tv))
+
+    def forward(self, d_pred: int, d_content: int, d_style: int, d_losses: int, batch: int, stream: int = 0):
+        self._check(self.lib.rst_loss_forward(self.handle, _vp(d_pred), _vp(d_content), _vp(d_style), _vp(d_losses), batch,
+                                              _vp(stream) if stream else None))
+
+    def backward(self, d_pred: int, d_grad: int, batch: int, stream: int = 0):
+        self._check(self.lib.rst_loss_backward(self.handle, _vp(d_pred), _vp(d_grad), batch, _vp(stream) if stream else None))
