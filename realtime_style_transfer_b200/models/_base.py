@@ -117,12 +117,17 @@ class NativeModel:
     def _mark_dirty(self):
         self._dirty = True
 
-    def save_weights(self, filepath):
+    def save_weights(self, filepath, save_format=None):
+        """``*.npz`` -> numpy archive; anything else -> a TF2 object-based checkpoint prefix (Keras' default 'tf' format:
+        ``<prefix>.index`` + ``<prefix>.data-00000-of-00001``), readable by load_weights."""
         path = str(filepath)
-        if not path.endswith(".npz"):
-            path += ".npz"
-        np.savez(path, **self._all_variables())
-        return path
+        if path.endswith(".npz") or save_format == "npz":
+            if not path.endswith(".npz"):
+                path += ".npz"
+            np.savez(path, **self._all_variables())
+            return path
+        from ..checkpoint import write_checkpoint
+        return write_checkpoint(path, self._all_variables())
 
     def _all_variables(self) -> Dict[str, np.ndarray]:
         return self._variables
@@ -132,8 +137,8 @@ class NativeModel:
         (tracing/checkpoint.py:37 writes those); returns a status object like TF's."""
         from ..checkpoint import read_checkpoint_variables, match_checkpoint_to_model
         path = str(filepath)
-        if os.path.exists(path) and path.endswith(".npz") or os.path.exists(path + ".npz"):
-            data = np.load(path if path.endswith(".npz") else path + ".npz")
+        if path.endswith(".npz") and os.path.exists(path):
+            data = np.load(path)
             source = {k: data[k] for k in data.files}
             mine = self._all_variables()
             matched = [k for k in mine if k in source and source[k].shape == mine[k].shape]
