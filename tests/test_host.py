@@ -199,3 +199,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f"{f} reaches into oracle/"
+
+
+def test_tensorbuffer_roundtrip(tmp_path):
+    from realtime_style_transfer_b200.dataloaders import tensorbuffer
+    x = np.random.default_rng(0).standard_normal((6, 8, 17)).astype(np.float32)
+    tensorbuffer.save_tensor_to_buffer(tmp_path / "f0.bin", x)
+    tensorbuffer.save_tensor_to_buffer(tmp_path / "f1.bin", x * 2)
+    np.testing.assert_array_equal(tensorbuffer.load_tensor_from_buffer(tmp_path / "f0.bin", (6, 8, 17)), x)
+    batches = list(tensorbuffer.iter_tensor_buffers([tmp_path / "f0.bin", tmp_path / "f1.bin", tmp_path / "f0.bin"], (6, 8, 17), 2))
+    assert [b.shape for b in batches] == [(2, 6, 8, 17), (1, 6, 8, 17)]
+    np.testing.assert_array_equal(batches[0][1], x * 2)
+    with pytest.raises(ValueError):
+        tensorbuffer.load_tensor_from_buffer(tmp_path / "f0.bin", (6, 8, 18))
