@@ -161,6 +161,41 @@ int rst_loss_forward(rst_loss* loss, const float* d_pred, const float* d_gt_cont
  * styleTransferTrainingModel.py:26-29), using the activations saved by the last rst_loss_forward. */
 int rst_loss_backward(rst_loss* loss, const float* d_pred, float* d_grad_pred, int batch, void* stream);
 
+/* ---- training step (models/styleTransferTrainingModel.py + Keras Model.fit's train_step) ------------------------------------ */
+typedef struct rst_trainer rst_trainer;
+/* make_style_transfer_training_model (styleTransferTrainingModel.py:39-70): predictor + transfer network with num_styles = 1,
+ * the VGG loss model, and tf.keras.optimizers.RMSprop state (train_network.py:102).  cfg->num_styles must be 1 and
+ * cfg->extractor must name a predictor; the model always trains in fp32.  The loss model works at (out_h, out_w). */
+int rst_train_create(const rst_config* cfg, int device, rst_trainer** out);
+int rst_train_destroy(rst_trainer* trainer);
+const char* rst_train_last_error(const rst_trainer* trainer);
+/* The trainer's model / loss contexts: set variables with rst_set_weight + rst_commit_weights and rst_loss_set_weight +
+ * rst_loss_commit before the first step.  The model context also serves rst_transfer_forward / rst_predict_style. */
+rst_ctx* rst_train_model(rst_trainer* trainer);
+rst_loss* rst_train_loss(rst_trainer* trainer);
+/* One forward + backward of Model.train_step: y_pred = model(x, training=True) [BatchNorm on batch statistics,
+ * moving statistics updated], compute_loss (styleTransferTrainingModel.py:26-29), gradient of the batch SUM of the loss vector
+ * w.r.t. every trainable variable, left in the flat gradient buffer.  d_losses (B,4) as rst_loss_forward.  d_style is the
+ * predictor input (B,style_h,style_w,3); d_gt_style the style image at (out_h,out_w) for the loss model. */
+int rst_train_forward_backward(rst_trainer* trainer, const float* d_content, const float* d_style, const float* d_gt_content,
+                               const float* d_gt_style, float* d_losses, int batch);
+/* Flat fp32 gradient buffer (device) holding every trainable variable's gradient: the buffer a data-parallel caller
+ * all-reduces (SUM) over NCCL between rst_train_forward_backward and rst_train_apply_gradients. */
+float* rst_train_gradients(rst_trainer* trainer);
+int64_t rst_train_num_gradient_elements(const rst_trainer* trainer);
+int rst_train_variable_range(const rst_trainer* trainer, const char* name, int64_t* offset, int64_t* elems);
+/* Keras RMSprop (momentum 0, not centred): rms = rho*rms + (1-rho)*g^2; var -= lr*g/(sqrt(rms)+epsilon).
+ * Defaults of RMSprop(): learning_rate 1e-3, rho 0.9, epsilon 1e-7. */
+int rst_train_apply_gradients(rst_trainer* trainer, float learning_rate, float rho, float epsilon);
+/* Device -> host registry and re-commit, so rst_get_weight / checkpoints / inference entry points see the trained values. */
+int rst_train_sync_weights(rst_trainer* trainer);
+int rst_train_read_gradient(rst_trainer* trainer, const char* name, float* h_out, int64_t capacity);
+int rst_train_read_prediction(rst_trainer* trainer, float* h_out, int64_t capacity);
+const float* rst_train_prediction(const rst_trainer* trainer);
+/* Debug: an activation of the last step (want_grad 0) or the gradient that reached it (want_grad 1) by name:
+ * "<layer>/conv", "<layer>/out", "style_params".  h_out NULL only queries the element count. */
+int rst_train_debug_read(rst_trainer* trainer, const char* name, int want_grad, float* h_out, int64_t capacity, int64_t* elems);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,7 @@ def conv2d_same(x: Tensor, kernel: Tensor, bias: Optional[Tensor], stride: int =
     pt, pb = tf_same_pad(x.shape[1], kh, stride)
     pl, pr = tf_same_pad(x.shape[2], kw, stride)
     xin = F.pad(_nchw(x), (pl, pr, pt, pb))
-    w = kernel.permute(3, 2, 0, 1)
+    w = kernel.permute(3, 2, 0, 1).contiguous()
     y = F.conv2d(xin, w, bias, stride=stride, groups=groups)
     return _nhwc(y)
 
@@ -68,7 +68,7 @@ def depthwise_conv2d(x: Tensor, kernel: Tensor, stride: int, pads: Tuple[int, in
     """Keras DepthwiseConv2D, kernel (kh,kw,C,1); explicit pads (top,bottom,left,right)."""
     c = x.shape[3]
     xin = F.pad(_nchw(x), (pads[2], pads[3], pads[0], pads[1]))
-    w = kernel.permute(2, 3, 0, 1)  # (C,1,kh,kw)
+    w = kernel.permute(2, 3, 0, 1).contiguous()  # (C,1,kh,kw)
     return _nhwc(F.conv2d(xin, w, None, stride=stride, groups=c))
 
 
@@ -83,16 +83,25 @@ def conv2d_transpose_same(x: Tensor, kernel: Tensor, bias: Optional[Tensor], str
     ho, wo = x.shape[1] * stride, x.shape[2] * stride
     pt, _ = tf_same_pad(ho, kh, stride)
     pl, _ = tf_same_pad(wo, kw, stride)
-    w = kernel.permute(3, 2, 0, 1)  # (in, out, kh, kw) -- torch conv_transpose2d layout
+    w = kernel.permute(3, 2, 0, 1).contiguous()  # (in, out, kh, kw) -- torch conv_transpose2d layout
     full = F.conv_transpose2d(_nchw(x), w, bias, stride=stride, padding=0)
     return _nhwc(full[:, :, pt:pt + ho, pl:pl + wo])
 
 
-def batchnorm(x: Tensor, gamma, beta, mean, var, eps: float = BN_EPS, training: bool = False):
-    """Keras BatchNormalization(axis=-1).  training=True uses batch statistics over (N,H,W)."""
+def batchnorm(x: Tensor, gamma, beta, mean, var, eps: float = BN_EPS, training: bool = False, moving_out=None,
+              momentum: float = 0.99):
+    """Keras BatchNormalization(axis=-1).  training=True uses batch statistics over (N,H,W).
+    moving_out (a list) receives the updated (moving_mean, moving_variance): Keras' fused path (4-D NHWC input) feeds the
+    Bessel-corrected batch variance into the moving average (normalization/batch_normalization.py,
+    `_bessels_correction_test_only` left True) -- parity unpinned, TF is un-vendored."""
     if training:
-        mean = x.mean(dim=(0, 1, 2))
-        var = x.var(dim=(0, 1, 2), unbiased=False)
+        bm = x.mean(dim=(0, 1, 2))
+        bv = x.var(dim=(0, 1, 2), unbiased=False)
+        if moving_out is not None:
+            n = x.shape[0] * x.shape[1] * x.shape[2]
+            ub = bv * (n / max(n - 1, 1))
+            moving_out.append(((momentum * mean + (1 - momentum) * bm).detach(), (momentum * var + (1 - momentum) * ub).detach()))
+        mean, var = bm, bv
     return (x - mean) * torch.rsqrt(var + eps) * gamma + beta
 
 
@@ -584,3 +593,117 @@ def synthetic_style_weights(batch: int, h: int, w: int, seed: int = 5) -> np.nda
     coarse = torch.rand((batch, 1, 8, 16), generator=g)
     fine = F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)
     return fine.permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# Training step (train_network.py:102-138 + Keras train_step; styleTransferTrainingModel.py:26-33)
+# --------------------------------------------------------------------------------------
+RMSPROP = dict(lr=1e-3, rho=0.9, eps=1e-7)      # tf.keras.optimizers.RMSprop() defaults in TF 2.9 (momentum 0, not centred)
+
+
+def training_forward_backward(spec: TransferSpec, transfer_w, extractor: str, predictor_w, vgg_w, content, style, gt_content,
+                              dtype=torch.float64, moving=None, tap_grads=None, pred_grad=None):
+    """One forward/backward of the reference's training model with num_styles == 1:
+    y_pred = transfer(content, predictor(style)) in training mode (BatchNorm uses batch statistics), loss vector from the
+    VGG loss model, gradient of the batch SUM of the loss w.r.t. every trainable variable (VGG is frozen).
+    pred_grad: back-propagate this d(loss)/d(y_pred) instead of the loss model's own gradient (isolates the network's
+    backward pass from the loss, whose gradient is very sensitive to rounding noise in y_pred).
+    Returns (losses dict of (B,) tensors, grads {name: tensor}, y_pred)."""
+    tw = {k: torch.as_tensor(v).to(dtype).requires_grad_(not k.endswith(("moving_mean", "moving_variance")))
+          for k, v in transfer_w.items()}
+    pw = {k: torch.as_tensor(v).to(dtype).requires_grad_(not k.endswith(("moving_mean", "moving_variance")))
+          for k, v in predictor_w.items()}
+    style_t = torch.as_tensor(style).to(dtype)
+    if style_t.dim() == 5:
+        style_t = style_t[:, 0]
+    params = _predictor_forward_t(extractor, pw, style_t, training=True)[:, None, :]
+    taps = {} if tap_grads is not None else None
+    y = _transfer_forward_t(spec, tw, torch.as_tensor(content).to(dtype), params, training=True, moving=moving, taps=taps)
+    if taps is not None:
+        taps["style_params"] = params
+    losses = style_loss_vgg(vgg_w, y, gt_content, style_t, dtype=dtype)
+    total = losses["loss"].sum()
+    names = [("t", k) for k, v in tw.items() if v.requires_grad] + [("p", k) for k, v in pw.items() if v.requires_grad]
+    tensors = [tw[k] if w == "t" else pw[k] for w, k in names]
+    tap_names = list(taps) if taps is not None else []
+    if pred_grad is not None:
+        gs = torch.autograd.grad(y, tensors + [taps[k] for k in tap_names], grad_outputs=torch.as_tensor(pred_grad).to(dtype),
+                                 allow_unused=True)
+    else:
+        gs = torch.autograd.grad(total, tensors + [taps[k] for k in tap_names], allow_unused=True)
+    if tap_grads is not None:      # name -> (activation, d loss-sum / d activation) of the "<layer>/out" tensors
+        for k, g in zip(tap_names, gs[len(tensors):]):
+            tap_grads[k] = (taps[k].detach(), g)
+    gs = gs[:len(tensors)]
+    grads = {k: (g if g is not None else torch.zeros_like(t)) for (w, k), g, t in zip(names, gs, tensors)}
+    return {k: v.detach() for k, v in losses.items()}, grads, y.detach()
+
+
+def _transfer_forward_t(spec, W, x, style_params, training, moving=None, taps=None):
+    """transfer_forward on already-converted torch tensors (keeps the autograd graph), single style.
+    moving (a dict) receives the updated BatchNorm moving statistics of a training-mode call."""
+    sp = style_params.unsqueeze(1)
+    cursor = 0
+    for name, _, co, k, s in spec.contract:
+        p = f"contract_{name}"
+        x = F.relu(conv2d_same(x, W[f"{p}/conv/kernel"], W[f"{p}/conv/bias"], s))
+        mo = [] if moving is not None else None
+        x = F.relu(batchnorm(x, W[f"{p}/bn/gamma"], W[f"{p}/bn/beta"], W[f"{p}/bn/moving_mean"],
+                             W[f"{p}/bn/moving_variance"], training=training, moving_out=mo))
+        if mo:
+            moving[f"{p}/bn/moving_mean"], moving[f"{p}/bn/moving_variance"] = mo[0]
+        if taps is not None:
+            taps[f"{p}/out"] = x
+    f = spec.filters
+    for b in range(5):
+        params = sp[..., cursor:cursor + 4 * f]
+        cursor += 4 * f
+        fx = x
+        for i in range(2):
+            p = f"residual_block_{b}/conv{i}"
+            fx = F.relu(conv2d_same(fx, W[f"{p}/kernel"], W[f"{p}/bias"], 1))
+            sl = params[..., 2 * f * i: 2 * f * (i + 1)]
+            fx = cin(fx, sl[..., :f], sl[..., f:])
+            if i == 0:
+                fx = F.relu(fx)
+                if taps is not None:
+                    taps[f"{p}/out"] = fx
+        x = fx if b == 0 else x + fx
+        if taps is not None:
+            taps[f"residual_block_{b}/conv1/out"] = x
+    for name, _, co, k, s in spec.expand:
+        p = f"expand_{name}"
+        params = sp[..., cursor:cursor + 2 * co]
+        cursor += 2 * co
+        x = conv2d_transpose_same(x, W[f"{p}/conv/kernel"], W[f"{p}/conv/bias"], s)
+        x = cin(x, params[..., :co], params[..., co:])
+        x = torch.sigmoid(x) if name == "last" else F.relu(x)
+        if taps is not None:
+            taps[f"{p}/out"] = x
+    return x
+
+
+def _predictor_forward_t(extractor, W, x, training):
+    if extractor == "DUMMY":
+        x = conv2d_same(x, W["dummy_conv/kernel"], W["dummy_conv/bias"], 5)
+    elif extractor == "MOBILE_NET":
+        x = mobilenet_v3_small(W, x * 2.0 - 1.0, training)
+    else:
+        raise ValueError(f"{extractor} is not a valid value for feature_extractor")
+    x = x.mean(dim=(1, 2), keepdim=True)
+    x = conv2d_same(x, W["StylePredictor/kernel"], W["StylePredictor/bias"])
+    x = conv2d_same(x, W["StyleNormPredictor/kernel"], W["StyleNormPredictor/bias"])
+    return x[:, 0, 0, :]
+
+
+def rmsprop_update(weights: Dict[str, np.ndarray], grads: Dict[str, Tensor], slots: Dict[str, np.ndarray],
+                   lr=RMSPROP["lr"], rho=RMSPROP["rho"], eps=RMSPROP["eps"]):
+    """Keras RMSprop (TF 2.9 optimizer_v2/rmsprop.py, momentum 0, centered False):
+    rms = rho*rms + (1-rho)*g^2 ;  var -= lr * g / (sqrt(rms) + eps).   parity unpinned (TF is un-vendored)."""
+    new_w, new_s = dict(weights), dict(slots)
+    for k, g in grads.items():
+        g = g.detach().double().numpy()
+        rms = rho * slots.get(k, np.zeros_like(g)) + (1 - rho) * g * g
+        new_s[k] = rms
+        new_w[k] = (weights[k].astype(np.float64) - lr * g / (np.sqrt(rms) + eps)).astype(np.float32)
+    return new_w, new_s

@@ -80,6 +80,21 @@ SIGNATURES = {
     "rst_loss_set_factors": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float]),
     "rst_loss_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rst_loss_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "rst_train_create": (C.c_int, [C.POINTER(RstConfig), C.c_int, C.POINTER(_vp)]),
+    "rst_train_destroy": (C.c_int, [_vp]),
+    "rst_train_last_error": (C.c_char_p, [_vp]),
+    "rst_train_model": (_vp, [_vp]),
+    "rst_train_loss": (_vp, [_vp]),
+    "rst_train_forward_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "rst_train_gradients": (_vp, [_vp]),
+    "rst_train_num_gradient_elements": (C.c_int64, [_vp]),
+    "rst_train_variable_range": (C.c_int, [_vp, C.c_char_p, _i64p, _i64p]),
+    "rst_train_apply_gradients": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float]),
+    "rst_train_sync_weights": (C.c_int, [_vp]),
+    "rst_train_read_gradient": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int64]),
+    "rst_train_read_prediction": (C.c_int, [_vp, _vp, C.c_int64]),
+    "rst_train_prediction": (_vp, [_vp]),
+    "rst_train_debug_read": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, C.c_int64, _i64p]),
 }
 
 _lib = None
@@ -137,12 +152,22 @@ class NativeContext:
         cfg.predictor_num_params = int(predictor_num_params)
         self.cfg = cfg
         self.device = device
+        self._owns = True
         handle = _vp()
         rc = self.lib.rst_create(C.byref(cfg), device, C.byref(handle))
         if rc != 0:
             raise RstError(rc, (self.lib.rst_last_error(None) or b"").decode())
         self.handle = handle
         self.num_style_params = self.lib.rst_num_style_params(self.handle)
+
+    @classmethod
+    def _view(cls, handle, cfg: "RstConfig", device: int) -> "NativeContext":
+        """Non-owning wrapper of a context that belongs to a trainer."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.cfg, self.device, self.handle, self._owns = cfg, device, _vp(handle), False
+        self.num_style_params = self.lib.rst_num_style_params(self.handle)
+        return self
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -151,7 +176,8 @@ class NativeContext:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.rst_destroy(self.handle)
+            if getattr(self, "_owns", True):
+                self.lib.rst_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -302,6 +328,14 @@ class NativeLoss:
         if rc != 0:
             raise RstError(rc, (self.lib.rst_loss_last_error(None) or b"").decode())
         self.handle, self.h, self.w, self.max_batch, self.device = handle, h, w, max_batch, device
+        self._owns = True
+
+    @classmethod
+    def _view(cls, handle, h: int, w: int, max_batch: int, device: int) -> "NativeLoss":
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.handle, self.h, self.w, self.max_batch, self.device, self._owns = _vp(handle), h, w, max_batch, device, False
+        return self
 
     def _check(self, rc):
         if rc != 0:
@@ -309,7 +343,8 @@ class NativeLoss:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.rst_loss_destroy(self.handle)
+            if getattr(self, "_owns", True):
+                self.lib.rst_loss_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -334,3 +369,78 @@ class NativeLoss:
 
     def backward(self, d_pred: int, d_grad: int, batch: int, stream: int = 0):
         self._check(self.lib.rst_loss_backward(self.handle, _vp(d_pred), _vp(d_grad), batch, _vp(stream) if stream else None))
+
+
+class NativeTrainer:
+    """Owns one rst_trainer: predictor + transfer network in training mode, VGG loss model, RMSprop state."""
+
+    def __init__(self, *, in_shape, out_shape, bottleneck_res_y, bottleneck_num_filters, max_batch, extractor, style_shape,
+                 device: int = 0):
+        self.lib = load_library()
+        cfg = RstConfig()
+        cfg.in_h, cfg.in_w, cfg.in_c = (int(v) for v in in_shape)
+        cfg.out_h, cfg.out_w = int(out_shape[0]), int(out_shape[1])
+        cfg.bottleneck_res_y, cfg.bottleneck_num_filters = int(bottleneck_res_y), int(bottleneck_num_filters)
+        cfg.num_styles, cfg.max_batch, cfg.precision, cfg.extractor = 1, int(max_batch), PRECISION_FP32, int(extractor)
+        cfg.style_h, cfg.style_w = int(style_shape[0]), int(style_shape[1])
+        self.cfg, self.device = cfg, device
+        handle = _vp()
+        rc = self.lib.rst_train_create(C.byref(cfg), device, C.byref(handle))
+        if rc != 0:
+            raise RstError(rc, (self.lib.rst_train_last_error(None) or b"").decode())
+        self.handle = handle
+        self.model = NativeContext._view(self.lib.rst_train_model(handle), cfg, device)
+        self.loss = NativeLoss._view(self.lib.rst_train_loss(handle), cfg.out_h, cfg.out_w, cfg.max_batch, device)
+        self.num_gradient_elements = int(self.lib.rst_train_num_gradient_elements(handle))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RstError(rc, (self.lib.rst_train_last_error(self.handle) or b"").decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.model.handle = None
+            self.loss.handle = None
+            self.lib.rst_train_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward_backward(self, d_content: int, d_style: int, d_gt_content: int, d_gt_style: int, d_losses: int, batch: int):
+        self._check(self.lib.rst_train_forward_backward(self.handle, _vp(d_content), _vp(d_style), _vp(d_gt_content),
+                                                        _vp(d_gt_style), _vp(d_losses), batch))
+
+    def gradients_ptr(self) -> int:
+        return int(self.lib.rst_train_gradients(self.handle) or 0)
+
+    def variable_range(self, name: str):
+        off, n = C.c_int64(), C.c_int64()
+        self._check(self.lib.rst_train_variable_range(self.handle, name.encode(), C.byref(off), C.byref(n)))
+        return int(off.value), int(n.value)
+
+    def apply_gradients(self, learning_rate: float = 1e-3, rho: float = 0.9, epsilon: float = 1e-7):
+        self._check(self.lib.rst_train_apply_gradients(self.handle, learning_rate, rho, epsilon))
+
+    def sync_weights(self):
+        self._check(self.lib.rst_train_sync_weights(self.handle))
+
+    def read_gradient(self, name: str, shape: Sequence[int]) -> np.ndarray:
+        out = np.empty(tuple(shape), np.float32)
+        self._check(self.lib.rst_train_read_gradient(self.handle, name.encode(), _ptr(out), out.size))
+        return out
+
+    def debug_read(self, name: str, want_grad: bool = False) -> np.ndarray:
+        n = C.c_int64()
+        self._check(self.lib.rst_train_debug_read(self.handle, name.encode(), int(want_grad), None, 0, C.byref(n)))
+        out = np.empty((int(n.value),), np.float32)
+        self._check(self.lib.rst_train_debug_read(self.handle, name.encode(), int(want_grad), _ptr(out), out.size, None))
+        return out
+
+    def read_prediction(self, batch: int) -> np.ndarray:
+        out = np.empty((batch, self.cfg.out_h, self.cfg.out_w, 3), np.float32)
+        self._check(self.lib.rst_train_read_prediction(self.handle, _ptr(out), out.size))
+        return out

@@ -214,7 +214,8 @@ extern "C" const char* rst_version(void) { return "rst_b200 0.1 (sm_100a)"; }
 static void free_ctx(rst_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (auto& w : c->weights) if (w.dev) cudaFree(w.dev);
+    if (c->weight_arena) cudaFree(c->weight_arena);
+    else for (auto& w : c->weights) if (w.dev) cudaFree(w.dev);
     for (auto& kv : c->folded) if (kv.second) cudaFree(kv.second);
     for (auto& a : c->act) if (a) cudaFree(a);
     for (auto& a : c->pact) if (a) cudaFree(a);
@@ -226,7 +227,6 @@ static void free_ctx(rst_ctx* c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     c->bf16.reset();
-    c->train.reset();
     if (c->pipe.ready) {
         for (int i = 0; i < 2; ++i) {
             for (float* q : {c->pipe.content[i], c->pipe.params[i], c->pipe.weights[i], c->pipe.out[i]}) if (q) cudaFree(q);

@@ -44,7 +44,6 @@ struct ProfileGroup {
 };
 
 struct Bf16State;           // defined in transfer_bf16.cu
-struct TrainState;          // defined in training.cu
 
 }  // namespace rst
 
@@ -65,6 +64,7 @@ struct rst_ctx {
     // ---- weights ----
     std::vector<rst::Weight> weights;
     std::map<std::string, int> weight_index;
+    float* weight_arena = nullptr;          // when set (trainer), every Weight::dev points into this one allocation
     std::map<std::string, float*> folded;   // "<bn prefix>/scale", "<bn prefix>/shift" device arrays
 
     // ---- workspaces (fp32 path) ----
@@ -94,7 +94,6 @@ struct rst_ctx {
 
     // ---- bf16 tensor-core path ----
     std::shared_ptr<rst::Bf16State> bf16;
-    std::shared_ptr<rst::TrainState> train;
 
     // ---- CUDA-graph cache of whole forwards (launch-bound inner loop: ~30 kernels per batch) ----
     struct GraphEntry {

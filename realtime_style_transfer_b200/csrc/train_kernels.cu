@@ -1,0 +1,409 @@
+// fp32 kernels for the training step: weight gradients, normalisation forward (training mode) and backward,
+// activation backward, RMSprop.  Correctness-first CUDA-core kernels (the tensor-core training path is future work).
+#include "train_kernels.cuh"
+
+namespace rst {
+
+static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient of Conv2D / Conv2DTranspose ('same'), split over base pixels with fp32 atomics.
+//   conv : dW[ky,kx,ci,co] = sum_{n,oy,ox} x[n, oy*s - pt + ky, ox*s - pl + kx, ci] * g[n,oy,ox,co]     (base = output grid)
+//   convT: dW[ky,kx,co,ci] = sum_{n,i,j}  x[n,i,j,ci] * g[n, i*s + ky - pt, j*s + kx - pl, co]         (base = input grid)
+// One CTA = one filter tap x 32 input channels x 32 output channels x a slab of base pixels.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci_blocks, int pix_per_split) {
+    __shared__ float As[32][33];      // [pixel][ci]
+    __shared__ float Gs[32][33];      // [pixel][co]
+    const int tap = blockIdx.x / ci_blocks, ci0 = (blockIdx.x % ci_blocks) * 32, c0 = blockIdx.y * 32;
+    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+    const long long NP = (long long)p.B * p.Hb * p.Wb;
+    const long long p0 = (long long)blockIdx.z * pix_per_split;
+    const long long p1 = min(NP, p0 + pix_per_split);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const int ci = ci0 + tx, co = c0 + tx;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long pp = p0; pp < p1; pp += 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pl_ = ty + 8 * i;
+            const long long pix = pp + pl_;
+            float a = 0.f, g = 0.f;
+            if (pix < p1) {
+                const int bx = (int)(pix % p.Wb);
+                const long long t = pix / p.Wb;
+                const int by = (int)(t % p.Hb);
+                const int n = (int)(t / p.Hb);
+                int xy = by, xx = bx, gy_ = by, gx_ = bx;
+                if (!p.transposed) { xy = by * p.stride - p.pad_t + ky; xx = bx * p.stride - p.pad_l + kx; }
+                else { gy_ = by * p.stride + ky - p.pad_t; gx_ = bx * p.stride + kx - p.pad_l; }
+                if (ci < p.Ci && xy >= 0 && xy < p.Hx && xx >= 0 && xx < p.Wx)
+                    a = fmaf(__ldg(p.x + (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci + ci), p.in_scale, p.in_shift);
+                if (co < p.Co && gy_ >= 0 && gy_ < p.Hg && gx_ >= 0 && gx_ < p.Wg)
+                    g = __ldg(p.g + (((long long)n * p.Hg + gy_) * p.Wg + gx_) * p.Co + co);
+            }
+            As[pl_][tx] = a;
+            Gs[pl_][tx] = g;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const float gv = Gs[q][tx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(As[q][ty + 8 * i], gv, acc[i]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int cin = ci0 + ty + 8 * i;
+        if (cin < p.Ci && co < p.Co) {
+            const long long idx = !p.transposed ? ((long long)tap * p.Ci + cin) * p.Co + co : ((long long)tap * p.Co + co) * p.Ci + cin;
+            atomicAdd(p.dw + idx, acc[i]);
+        }
+    }
+}
+
+cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
+    const long long NP = (long long)p.B * p.Hb * p.Wb;
+    if (NP == 0) return cudaSuccess;
+    const int ci_blocks = ceil_div(p.Ci, 32);
+    const int pix_per_split = 2048;
+    dim3 grid((unsigned)(p.kh * p.kw * ci_blocks), (unsigned)ceil_div(p.Co, 32), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
+    wgrad_f32_kernel<<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// normalisation helpers.  stats (G, C, 2) doubles [sum, sumsq] per group g (CIN: g = sample, BatchNorm: one group).
+// ---------------------------------------------------------------------------------------------------------------
+// per-(n,c) sums -> per-c sums (BatchNorm over the batch)
+__global__ void reduce_over_batch_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int C2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C2) return;
+    double s = 0.0;
+    for (int n = 0; n < B; ++n) s += in[(long long)n * C2 + i];
+    out[i] = s;
+}
+cudaError_t launch_reduce_over_batch(const double* in, double* out, int B, int C2, cudaStream_t s) {
+    reduce_over_batch_kernel<<<nblk(C2), 256, 0, s>>>(in, out, B, C2);
+    return cudaGetLastError();
+}
+
+// mean / inv-std per (group, channel); optional affine coefficients y = x*a + b with a = inv*scale, b = bias - mean*a.
+// scale/bias: per (group, channel) with strides (CIN: style params) or per channel (BatchNorm: gamma/beta, gstride 0).
+// BatchNorm also updates the moving statistics: mm = m*mm + (1-m)*mean, mv = m*mv + (1-m)*var*N/(N-1) (Keras fused BN).
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, int G, int C, double count, float eps,
+                                     const float* __restrict__ scale, const float* __restrict__ bias, long long gstride,
+                                     float* __restrict__ mean, float* __restrict__ inv, float* __restrict__ a,
+                                     float* __restrict__ b, float* moving_mean, float* moving_var, float momentum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * C) return;
+    const int g = i / C, c = i % C;
+    const double m = stats[(long long)i * 2] / count;
+    double var = stats[(long long)i * 2 + 1] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float iv = (float)(1.0 / sqrt(var + (double)eps));
+    mean[i] = (float)m;
+    inv[i] = iv;
+    const float sc = scale[g * gstride + c], bi = bias[g * gstride + c];
+    a[i] = iv * sc;
+    b[i] = bi - (float)m * iv * sc;
+    if (moving_mean) {
+        moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)unbiased;
+    }
+}
+cudaError_t launch_norm_finalize(const double* stats, int G, int C, double count, float eps, const float* scale,
+                                 const float* bias, long long gstride, float* mean, float* inv, float* a, float* b,
+                                 float* moving_mean, float* moving_var, float momentum, cudaStream_t s) {
+    norm_finalize_kernel<<<nblk((long long)G * C), 256, 0, s>>>(stats, G, C, count, eps, scale, bias, gstride, mean, inv, a, b,
+                                                               moving_mean, moving_var, momentum);
+    return cudaGetLastError();
+}
+
+// y = act(x*a[g,c] + b[g,c]) (+ residual);  g = sample index when per_sample, else 0
+__global__ void affine_act_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ a,
+                                  const float* __restrict__ b, const float* __restrict__ residual, long long PC, int C,
+                                  int per_sample, int act, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const long long gidx = per_sample ? (i / PC) * C + c : c;
+    float v = fmaf(x[i], a[gidx], b[gidx]);
+    if (act == ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    else if (act == ACT_HSIGMOID) v = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    else if (act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    if (residual) v += residual[i];
+    y[i] = v;
+}
+cudaError_t launch_affine_act(const float* x, float* y, const float* a, const float* b, const float* residual, int B, long long P,
+                              int C, int per_sample, int act, cudaStream_t s) {
+    const long long total = (long long)B * P * C;
+    if (total == 0) return cudaSuccess;
+    affine_act_kernel<<<nblk(total), 256, 0, s>>>(x, y, a, b, residual, P * C, C, per_sample, act, total);
+    return cudaGetLastError();
+}
+
+// g *= act'(out)   (ReLU: out > 0;  sigmoid: out*(1-out))
+__global__ void act_bwd_kernel(float* __restrict__ g, const float* __restrict__ out, int act, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float o = out[i];
+    if (act == ACT_RELU) { if (!(o > 0.f)) g[i] = 0.f; }
+    else if (act == ACT_SIGMOID) g[i] *= o * (1.f - o);
+    else if (act == ACT_HSIGMOID) g[i] = (o > 0.f && o < 1.f) ? g[i] * (1.f / 6.f) : 0.f;
+}
+cudaError_t launch_act_bwd(float* g, const float* out, int act, long long n, cudaStream_t s) {
+    if (n == 0 || act == ACT_NONE) return cudaSuccess;
+    act_bwd_kernel<<<nblk(n), 256, 0, s>>>(g, out, act, n);
+    return cudaGetLastError();
+}
+
+// g *= act'(u), u = x*a[g,c] + b[g,c] recomputed from the saved pre-normalisation tensor
+__global__ void affine_act_bwd_kernel(float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ a,
+                                      const float* __restrict__ b, long long PC, int C, int per_sample, int act, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const long long gidx = per_sample ? (i / PC) * C + c : c;
+    const float u = fmaf(x[i], a[gidx], b[gidx]);
+    float d = 1.f;
+    if (act == ACT_RELU) d = u > 0.f ? 1.f : 0.f;
+    else if (act == ACT_SIGMOID) { const float sg = 1.f / (1.f + expf(-u)); d = sg * (1.f - sg); }
+    else if (act == ACT_HSIGMOID) d = (u > -3.f && u < 3.f) ? 1.f / 6.f : 0.f;
+    else if (act == ACT_HSWISH) d = u <= -3.f ? 0.f : (u >= 3.f ? 1.f : (2.f * u + 3.f) / 6.f);
+    g[i] *= d;
+}
+cudaError_t launch_affine_act_bwd(float* g, const float* x, const float* a, const float* b, int B, long long P, int C,
+                                  int per_sample, int act, cudaStream_t s) {
+    const long long total = (long long)B * P * C;
+    if (total == 0 || act == ACT_NONE) return cudaSuccess;
+    affine_act_bwd_kernel<<<nblk(total), 256, 0, s>>>(g, x, a, b, P * C, C, per_sample, act, total);
+    return cudaGetLastError();
+}
+
+// per-(n,c): r[.,0] = sum_p g, r[.,1] = sum_p g * xhat, xhat = (x - mean)*inv   (mean/inv indexed per sample or per channel)
+__global__ void norm_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
+                                       const float* __restrict__ inv, double* __restrict__ r, int P, int C, int per_sample,
+                                       int pix_per_block) {
+    extern __shared__ double sm[];
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+    const long long base = (long long)n * P * C;
+    const int T = blockDim.x;
+    if (C <= T) {
+        const int G = T / C, c = threadIdx.x % C, gi = threadIdx.x / C;
+        double s1 = 0.0, s2 = 0.0;
+        if (gi < G) {
+            const float m = mean ? mean[per_sample ? n * C + c : c] : 0.f, iv = inv ? inv[per_sample ? n * C + c : c] : 1.f;
+            for (int pp = p0 + gi; pp < p1; pp += G) {
+                const float gv = g[base + (long long)pp * C + c];
+                const float xh = (x[base + (long long)pp * C + c] - m) * iv;
+                s1 += gv;
+                s2 += (double)gv * xh;
+            }
+        }
+        sm[threadIdx.x] = s1;
+        sm[T + threadIdx.x] = s2;
+        __syncthreads();
+        if (gi == 0) {
+            for (int j = 1; j < G; ++j) { s1 += sm[j * C + c]; s2 += sm[T + j * C + c]; }
+            atomicAdd(&r[((long long)n * C + c) * 2], s1);
+            atomicAdd(&r[((long long)n * C + c) * 2 + 1], s2);
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += T) {
+            const float m = mean ? mean[per_sample ? n * C + c : c] : 0.f, iv = inv ? inv[per_sample ? n * C + c : c] : 1.f;
+            double s1 = 0.0, s2 = 0.0;
+            for (int pp = p0; pp < p1; ++pp) {
+                const float gv = g[base + (long long)pp * C + c];
+                s1 += gv;
+                s2 += (double)gv * ((x[base + (long long)pp * C + c] - m) * iv);
+            }
+            atomicAdd(&r[((long long)n * C + c) * 2], s1);
+            atomicAdd(&r[((long long)n * C + c) * 2 + 1], s2);
+        }
+    }
+}
+cudaError_t launch_norm_bwd_reduce(const float* g, const float* x, const float* mean, const float* inv, double* r, int B, int P,
+                                   int C, int per_sample, cudaStream_t s) {
+    if (B == 0 || P == 0) return cudaSuccess;
+    const int threads = C <= 256 ? C * (256 / C) : 256;
+    const int pix_per_block = 2048;
+    dim3 grid((unsigned)ceil_div(P, pix_per_block), (unsigned)B);
+    norm_bwd_reduce_kernel<<<grid, threads, 2 * threads * sizeof(double), s>>>(g, x, mean, inv, r, P, C, per_sample, pix_per_block);
+    return cudaGetLastError();
+}
+
+// gx = a[g,c] * (g - r1/N - xhat * r2/N);   r indexed per sample (CIN) or per channel (BatchNorm, already reduced over n)
+__global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
+                                      const float* __restrict__ inv, const float* __restrict__ a, const double* __restrict__ r,
+                                      float* __restrict__ gx, long long PC, int C, int per_sample, double invN, int accumulate,
+                                      long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const long long gi = per_sample ? (i / PC) * C + c : c;
+    const float xh = (x[i] - mean[gi]) * inv[gi];
+    const float m1 = (float)(r[gi * 2] * invN), m2 = (float)(r[gi * 2 + 1] * invN);
+    const float v = a[gi] * (g[i] - m1 - xh * m2);
+    gx[i] = accumulate ? gx[i] + v : v;
+}
+cudaError_t launch_norm_bwd_apply(const float* g, const float* x, const float* mean, const float* inv, const float* a,
+                                  const double* r, float* gx, int B, long long P, int C, int per_sample, double count,
+                                  int accumulate, cudaStream_t s) {
+    const long long total = (long long)B * P * C;
+    if (total == 0) return cudaSuccess;
+    norm_bwd_apply_kernel<<<nblk(total), 256, 0, s>>>(g, x, mean, inv, a, r, gx, P * C, C, per_sample, 1.0 / count, accumulate, total);
+    return cudaGetLastError();
+}
+
+// CIN parameter gradients: d scale[n,c] = r[n,c,1], d bias[n,c] = r[n,c,0], accumulated into the (B, Ptotal) style-parameter
+// gradient at columns [off, off+C) and [off+C, off+2C)
+__global__ void cin_param_grad_kernel(const double* __restrict__ r, float* __restrict__ pg, int B, int C, long long ptotal, int off) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int n = i / C, c = i % C;
+    pg[n * ptotal + off + c] += (float)r[(long long)i * 2 + 1];
+    pg[n * ptotal + off + C + c] += (float)r[(long long)i * 2];
+}
+cudaError_t launch_cin_param_grad(const double* r, float* pg, int B, int C, long long ptotal, int off, cudaStream_t s) {
+    if (B * C == 0) return cudaSuccess;
+    cin_param_grad_kernel<<<nblk((long long)B * C), 256, 0, s>>>(r, pg, B, C, ptotal, off);
+    return cudaGetLastError();
+}
+
+// out[i] (+)= (float) in[i*stride + offset]   (pull sums out of the double reduction buffers)
+__global__ void gather_f64_kernel(const double* __restrict__ in, float* __restrict__ out, int n, int stride, int offset, int accumulate) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = (float)in[(long long)i * stride + offset];
+    out[i] = accumulate ? out[i] + v : v;
+}
+cudaError_t launch_gather_f64(const double* in, float* out, int n, int stride, int offset, int accumulate, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    gather_f64_kernel<<<nblk(n), 256, 0, s>>>(in, out, n, stride, offset, accumulate);
+    return cudaGetLastError();
+}
+
+// a[i] += b[i]
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+cudaError_t launch_add_inplace(float* a, const float* b, long long n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    add_inplace_kernel<<<nblk(n), 256, 0, s>>>(a, b, n);
+    return cudaGetLastError();
+}
+// global-average-pool backward: gx[n,p,c] = g[n,c] / P
+__global__ void gap_bwd_kernel(const float* __restrict__ g, float* __restrict__ gx, long long PC, int C, float invP, int accumulate,
+                               long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float v = g[(i / PC) * C + (i % C)] * invP;
+    gx[i] = accumulate ? gx[i] + v : v;
+}
+cudaError_t launch_gap_bwd(const float* g, float* gx, int B, long long P, int C, int accumulate, cudaStream_t s) {
+    const long long total = (long long)B * P * C;
+    if (total == 0) return cudaSuccess;
+    gap_bwd_kernel<<<nblk(total), 256, 0, s>>>(g, gx, P * C, C, 1.f / (float)P, accumulate, total);
+    return cudaGetLastError();
+}
+// squeeze-excite multiply backward w.r.t. the feature map: gx (+)= g * z[n,c]
+__global__ void scale_channels_bwd_kernel(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ gx,
+                                          long long PC, int C, int accumulate, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float v = g[i] * z[(i / PC) * C + (i % C)];
+    gx[i] = accumulate ? gx[i] + v : v;
+}
+cudaError_t launch_scale_channels_bwd(const float* g, const float* z, float* gx, int B, long long P, int C, int accumulate,
+                                      cudaStream_t s) {
+    const long long total = (long long)B * P * C;
+    if (total == 0) return cudaSuccess;
+    scale_channels_bwd_kernel<<<nblk(total), 256, 0, s>>>(g, z, gx, P * C, C, accumulate, total);
+    return cudaGetLastError();
+}
+
+// depthwise conv input gradient: gx[n,iy,ix,c] (+)= sum_k g[n,(iy+pt-ky)/s,(ix+pl-kx)/s,c] * w[k,c]
+__global__ void depthwise_dgrad_kernel(const DepthwiseF32 p, const float* __restrict__ g, float* __restrict__ gx, int accumulate,
+                                       long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % p.C);
+    long long t = idx / p.C;
+    const int ix = (int)(t % p.Wi);
+    t /= p.Wi;
+    const int iy = (int)(t % p.Hi);
+    const int n = (int)(t / p.Hi);
+    float acc = 0.f;
+    for (int ky = 0; ky < p.k; ++ky) {
+        const int ty = iy + p.pad_t - ky;
+        if (ty < 0 || ty % p.stride) continue;
+        const int oy = ty / p.stride;
+        if (oy >= p.Ho) continue;
+        for (int kx = 0; kx < p.k; ++kx) {
+            const int tx = ix + p.pad_l - kx;
+            if (tx < 0 || tx % p.stride) continue;
+            const int ox = tx / p.stride;
+            if (ox >= p.Wo) continue;
+            acc = fmaf(__ldg(g + (((long long)n * p.Ho + oy) * p.Wo + ox) * p.C + c), __ldg(p.w + (ky * p.k + kx) * p.C + c), acc);
+        }
+    }
+    gx[idx] = accumulate ? gx[idx] + acc : acc;
+}
+cudaError_t launch_depthwise_dgrad(const DepthwiseF32& p, const float* g, float* gx, int accumulate, cudaStream_t s) {
+    const long long total = (long long)p.B * p.Hi * p.Wi * p.C;
+    if (total == 0) return cudaSuccess;
+    depthwise_dgrad_kernel<<<nblk(total), 256, 0, s>>>(p, g, gx, accumulate, total);
+    return cudaGetLastError();
+}
+// depthwise conv weight gradient: dw[k,c] += sum_{n,oy,ox} x[n,oy*s-pt+ky,ox*s-pl+kx,c] * g[n,oy,ox,c]   (dw zeroed by the caller)
+__global__ void depthwise_wgrad_kernel(const DepthwiseF32 p, const float* __restrict__ g, float* __restrict__ dw, int pix_per_block) {
+    const int tap = blockIdx.x, ky = tap / p.k, kx = tap - ky * p.k;
+    const long long NP = (long long)p.B * p.Ho * p.Wo;
+    const long long p0 = (long long)blockIdx.y * pix_per_block, p1 = min(NP, p0 + pix_per_block);
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        float acc = 0.f;
+        for (long long pix = p0; pix < p1; ++pix) {
+            const int ox = (int)(pix % p.Wo);
+            const long long t = pix / p.Wo;
+            const int oy = (int)(t % p.Ho);
+            const int n = (int)(t / p.Ho);
+            const int iy = oy * p.stride - p.pad_t + ky, ix = ox * p.stride - p.pad_l + kx;
+            if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+            acc = fmaf(__ldg(p.x + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.C + c), __ldg(g + pix * p.C + c), acc);
+        }
+        atomicAdd(dw + tap * p.C + c, acc);
+    }
+}
+cudaError_t launch_depthwise_wgrad(const DepthwiseF32& p, const float* g, float* dw, cudaStream_t s) {
+    const long long NP = (long long)p.B * p.Ho * p.Wo;
+    if (NP == 0) return cudaSuccess;
+    const int pix_per_block = 64;
+    dim3 grid((unsigned)(p.k * p.k), (unsigned)((NP + pix_per_block - 1) / pix_per_block));
+    depthwise_wgrad_kernel<<<grid, 128, 0, s>>>(p, g, dw, pix_per_block);
+    return cudaGetLastError();
+}
+
+// Keras RMSprop (TF 2.9, momentum 0, not centred): rms = rho*rms + (1-rho)*g^2;  w -= lr * g / (sqrt(rms) + eps)
+__global__ void rmsprop_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ rms, float lr, float rho,
+                               float eps, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gv = g[i];
+    const float r = rho * rms[i] + (1.f - rho) * gv * gv;
+    rms[i] = r;
+    w[i] -= lr * gv / (sqrtf(r) + eps);
+}
+cudaError_t launch_rmsprop(float* w, const float* g, float* rms, float lr, float rho, float eps, long long n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    rmsprop_kernel<<<nblk(n), 256, 0, s>>>(w, g, rms, lr, rho, eps, n);
+    return cudaGetLastError();
+}
+
+}  // namespace rst

@@ -1,0 +1,176 @@
+"""GPU parity of the training step (predictor + transfer network in training mode, VGG loss, back-propagation, RMSprop)
+against the oracle: fp64 autograd of the restated model (oracle/rst_oracle.py::training_forward_backward).
+Bars: prediction within 1e-4 max abs (fp32 path), losses within 1e-3 relative (north_star), RMSprop arithmetic within 2e-6.
+Gradients are checked twice:
+  * the network's backward pass alone -- the oracle back-propagates the SAME d(loss)/d(prediction) the native step used --
+    within VJP_TOL relative L2 per variable;
+  * end to end within GRAD_TOL.  That bar is loose on purpose: at this test point the fp64 loss gradient itself moves by
+    4e-3 (relative L2) when the prediction is perturbed by 1e-6 (ReLU / max-pool routing flips inside VGG), and an fp32
+    forward pass carries about that much rounding noise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rst_oracle as O
+from realtime_style_transfer_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+IN_SHAPE, OUT_SHAPE, RES_Y, FILTERS = (64, 96, 5), (64, 96, 3), 16, 8
+GRAD_TOL = 1e-2     # end to end, relative L2 per variable against the fp64 gradient
+VJP_TOL = 5e-4      # network backward alone (same upstream gradient)
+
+
+def _setup(extractor_name, batch, seed=0):
+    spec = O.TransferSpec(IN_SHAPE, OUT_SHAPE, RES_Y, FILTERS, 1)
+    tw = O.init_transfer_weights(spec, seed=11, trained_like=True)
+    pw = O.init_predictor_weights(extractor_name, spec.num_style_parameters, seed=12)
+    vgg = O.init_vgg16_weights(seed=3)
+    rng = np.random.default_rng(seed)
+    content = rng.uniform(0, 1, (batch,) + IN_SHAPE).astype(np.float32)
+    style = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+    gt = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+    return spec, tw, pw, vgg, content, style, gt
+
+
+def _trainer(extractor, batch, tw, pw, vgg):
+    tr = _native.NativeTrainer(in_shape=IN_SHAPE, out_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=FILTERS,
+                               max_batch=batch, extractor=extractor, style_shape=OUT_SHAPE[:2])
+    tr.model.set_weights({**tw, **pw})
+    tr.loss.set_weights(vgg)
+    return tr
+
+
+def _step(tr, dev, content, style, gt):
+    b = content.shape[0]
+    d = [torch.tensor(a).to(dev) for a in (content, style, gt)]
+    d_l = torch.empty((b, 4), device=dev)
+    torch.cuda.synchronize()
+    tr.forward_backward(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[1].data_ptr(), d_l.data_ptr(), b)
+    return d_l.cpu().numpy()
+
+
+def _rel_l2(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+@pytest.mark.parametrize("extractor_name,extractor", [("DUMMY", _native.EXTRACTOR_DUMMY), ("MOBILE_NET", _native.EXTRACTOR_MOBILE_NET)])
+def test_training_step_matches_autograd(cuda_device, extractor_name, extractor):
+    batch = 2
+    spec, tw, pw, vgg, content, style, gt = _setup(extractor_name, batch)
+    moving = {}
+    tap_grads = {}
+    ref_losses, ref_grads, ref_pred = O.training_forward_backward(spec, tw, extractor_name, pw, vgg, content, style, gt, moving=moving,
+                                                                  tap_grads=tap_grads)
+    tr = _trainer(extractor, batch, tw, pw, vgg)
+    losses = _step(tr, cuda_device, content, style, gt)
+    # gradients that reached each layer output (the native pass has already applied the output activation's derivative)
+    for name, (act, g) in tap_grads.items():
+        act, g = act.numpy(), g.numpy()
+        if name == "expand_last/out":
+            g = g * act * (1 - act)
+        elif name != "style_params" and not name.endswith("conv1/out"):
+            g = g * (act > 0)
+        got_act = tr.debug_read(name).reshape(act.shape)
+        got = tr.debug_read(name, want_grad=True).reshape(g.shape)
+        print(f"tap {name}: activation max abs err {np.abs(got_act - act).max():.2e}  gradient rel l2 {_rel_l2(got, g):.2e}")
+        assert _rel_l2(got, g) < GRAD_TOL, name
+    pred = tr.read_prediction(batch)
+    err = np.abs(pred - ref_pred.numpy()).max()
+    print("prediction max abs err", err)
+    assert err < 1e-4
+    for i, key in enumerate(("loss", "feature_loss", "style_loss", "total_variation_loss")):
+        r = ref_losses[key].numpy()
+        rel = np.abs(losses[:, i] - r).max() / np.abs(r).max()
+        print(key, rel)
+        assert rel < 1e-3, key
+    # network backward alone: hand the oracle the loss gradient the native step back-propagated
+    y_nat = tr.debug_read("expand_last/out").reshape(ref_pred.shape).astype(np.float64)
+    g_nat = tr.debug_read("expand_last/out", want_grad=True).reshape(ref_pred.shape) / (y_nat * (1 - y_nat))
+    _, vjp_grads, _ = O.training_forward_backward(spec, tw, extractor_name, pw, vgg, content, style, gt, pred_grad=g_nat)
+    _, vjp32, _ = O.training_forward_backward(spec, tw, extractor_name, pw, vgg, content, style, gt, pred_grad=g_nat, dtype=torch.float32)
+    vrep = []
+    for name, g in vjp_grads.items():
+        ref = g.numpy()
+        norm = np.sqrt((ref ** 2).sum())
+        got = tr.read_gradient(name, tuple(g.shape))
+        vrep.append((np.sqrt(((got - ref) ** 2).sum()) / max(norm, 1e-300),
+                     np.sqrt(((vjp32[name].double().numpy() - ref) ** 2).sum()) / max(norm, 1e-300), norm, name))
+    vrep.sort(reverse=True)
+    for rel, rel32, norm, name in vrep[:10]:
+        print(f"vjp {name}: |ref| {norm:.2e} native {rel:.2e}  torch-fp32 {rel32:.2e}")
+    print("vjp median native", np.median([r[0] for r in vrep]), "median torch-fp32", np.median([r[1] for r in vrep]))
+    for rel, rel32, norm, name in vrep:
+        assert rel < VJP_TOL or rel <= 4 * rel32, (name, rel, rel32, norm)
+    # the same model differentiated by torch in float32 shows how well conditioned each gradient is at this precision
+    _, f32_grads, _ = O.training_forward_backward(spec, tw, extractor_name, pw, vgg, content, style, gt, dtype=torch.float32)
+    report = []
+    for name, g in ref_grads.items():
+        got = tr.read_gradient(name, tuple(g.shape))
+        ref = g.numpy()
+        norm = np.sqrt((ref ** 2).sum())
+        report.append((np.sqrt(((got - ref) ** 2).sum()) / max(norm, 1e-300),
+                       np.sqrt(((f32_grads[name].double().numpy() - ref) ** 2).sum()) / max(norm, 1e-300), norm, name))
+    report.sort(reverse=True)
+    for rel, rel32, norm, name in report[:6]:
+        print(f"grad {name}: |ref| {norm:.2e} native {rel:.2e}  torch-fp32 {rel32:.2e}")
+    print("variables", len(report), "median native", np.median([r[0] for r in report]), "median torch-fp32", np.median([r[1] for r in report]))
+    # Biases in front of an instance normalisation have an exactly-zero gradient (the norm removes the mean); fp64 leaves
+    # ~1e-18 there and any fp32 evaluation leaves rounding noise, so those are bounded by torch-fp32's own noise instead.
+    for rel, rel32, norm, name in report:
+        assert rel < GRAD_TOL or rel <= 4 * rel32, (name, rel, rel32, norm)
+    # flat buffer layout: every trainable variable has a range, ranges do not overlap
+    ranges = sorted(tr.variable_range(n) for n in ref_grads)
+    for (o0, n0), (o1, _) in zip(ranges, ranges[1:]):
+        assert o0 + n0 <= o1
+    assert ranges[-1][0] + ranges[-1][1] <= tr.num_gradient_elements
+    # BatchNorm moving statistics of the transfer network were updated from the batch statistics (momentum 0.99)
+    tr.sync_weights()
+    for name, value in moving.items():
+        got = tr.model.get_weight(name, tuple(value.shape))
+        assert np.abs(got - value.numpy()).max() < 1e-5 * max(1.0, np.abs(value.numpy()).max()), name
+    tr.close()
+
+
+def test_rmsprop_update_and_second_step(cuda_device):
+    batch = 2
+    spec, tw, pw, vgg, content, style, gt = _setup("DUMMY", batch, seed=5)
+    tr = _trainer(_native.EXTRACTOR_DUMMY, batch, tw, pw, vgg)
+    weights = {k: np.asarray(v, np.float64) for k, v in {**tw, **pw}.items() if not k.endswith(("moving_mean", "moving_variance"))}
+    slots = {k: np.zeros_like(v) for k, v in weights.items()}
+    first_loss = None
+    for step in range(2):
+        losses = _step(tr, cuda_device, content, style, gt)
+        first_loss = losses[:, 0].sum() if first_loss is None else first_loss
+        grads = {k: torch.tensor(tr.read_gradient(k, v.shape)) for k, v in weights.items()}
+        weights, slots = O.rmsprop_update(weights, grads, slots)
+        tr.apply_gradients()
+        tr.sync_weights()
+        for k, v in weights.items():
+            got = tr.model.get_weight(k, v.shape)
+            assert np.abs(got - v).max() < 2e-6 * max(1.0, np.abs(v).max()), (step, k)
+    # the trained weights serve inference through the same context (BatchNorm folded from the updated moving statistics)
+    params = np.zeros((batch, 1, tr.model.num_style_params), np.float32)
+    out = tr.model.transfer_forward_host(content, params)
+    assert out.shape == (batch,) + OUT_SHAPE and np.isfinite(out).all()
+    tr.close()
+
+
+def test_training_reduces_the_loss(cuda_device):
+    """A few RMSprop steps on one fixed batch lower its loss (sanity of sign conventions end to end)."""
+    batch = 2
+    spec, tw, pw, vgg, content, style, gt = _setup("DUMMY", batch, seed=7)
+    tr = _trainer(_native.EXTRACTOR_DUMMY, batch, tw, pw, vgg)
+    history = []
+    for _ in range(8):
+        history.append(float(_step(tr, cuda_device, content, style, gt)[:, 0].sum()))
+        tr.apply_gradients(learning_rate=1e-3)
+    print(history)
+    assert history[-1] < history[0]
+    tr.close()
+
+
+def test_trainer_rejects_bad_configs():
+    with pytest.raises(_native.RstError):
+        _native.NativeTrainer(in_shape=IN_SHAPE, out_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=FILTERS,
+                              max_batch=1, extractor=_native.EXTRACTOR_NONE, style_shape=OUT_SHAPE[:2])
