@@ -57,3 +57,13 @@ def aggregate_throughput(frames_this_rank: int, seconds_this_rank: float, device
     total = sum_over_ranks([frames_this_rank], device)[0]
     slowest = max_over_ranks([seconds_this_rank], device)[0]
     return total / slowest if slowest > 0 else 0.0
+
+
+def allreduce_sum_(tensor):
+    """In-place SUM all-reduce of the flat gradient buffer over every rank (NCCL on GPUs, gloo in the CPU tests); a no-op
+    in a single process.  SUM, not mean: Keras differentiates the batch SUM of the (B,) loss vector, so the data-parallel
+    gradient of the global batch is the sum of the per-rank gradients."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor

@@ -67,6 +67,7 @@ class NativeModel:
         self._ctx: Optional[NativeContext] = None
         self._ctx_key = None
         self._dirty = True
+        self._version = 0           # bumped whenever a variable is assigned
         self._compiled = False
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("RST_DEVICE") is None \
             else int(os.environ["RST_DEVICE"])
@@ -116,6 +117,7 @@ class NativeModel:
 
     def _mark_dirty(self):
         self._dirty = True
+        self._version += 1
 
     def save_weights(self, filepath, save_format=None):
         """``*.npz`` -> numpy archive; anything else -> a TF2 object-based checkpoint prefix (Keras' default 'tf' format:

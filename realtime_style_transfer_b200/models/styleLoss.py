@@ -87,6 +87,7 @@ class StyleLossModelVGG(StyleLossModelBase):
                 raise ValueError(f"bad VGG16 variable {k!r} with shape {np.shape(v)}")
             self._variables[k] = np.ascontiguousarray(v, np.float32)
         self._dirty = True
+        self._version = getattr(self, "_version", 0) + 1
 
     def native(self, batch: int) -> "_native.NativeLoss":
         if self._native is None or self._native.max_batch < batch:

@@ -59,3 +59,36 @@ def test_two_rank_gloo_sharding_and_timing_rule():
     assert mx0 == mx1 == [2.0, 9.0]               # the slowest rank's time, the largest shard
     assert tot0 == tot1 == 17.0
     assert fps0 == fps1 == pytest.approx(17.0 / 2.0)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    D.init_process_group("gloo")
+    # each rank holds the gradient of its own batch shard in one flat buffer (what rst_train_gradients exposes)
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    out = D.allreduce_sum_(g)
+    assert out is g                                     # in place: the native RMSprop reads the same buffer
+    q.put((rank, g.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_is_a_sum():
+    """Keras differentiates the batch SUM of the loss vector, so data-parallel gradients add up (no averaging)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [3.0 * i for i in range(10)]
+    assert results[0][1] == expect and results[1][1] == expect
+
+
+def test_allreduce_is_a_noop_without_a_process_group():
+    g = torch.ones(4)
+    assert D.allreduce_sum_(g).tolist() == [1.0] * 4

@@ -174,3 +174,83 @@ def test_trainer_rejects_bad_configs():
     with pytest.raises(_native.RstError):
         _native.NativeTrainer(in_shape=IN_SHAPE, out_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=FILTERS,
                               max_batch=1, extractor=_native.EXTRACTOR_NONE, style_shape=OUT_SHAPE[:2])
+
+
+# ---- the Keras-flavoured surface (models/styleTransferTrainingModel.py) ---------------------------------------------------
+def _python_training_model(extractor="DUMMY"):
+    from realtime_style_transfer_b200.models import styleLoss, stylePrediction, styleTransfer, styleTransferTrainingModel
+    loss_model = styleLoss.StyleLossModelVGG(OUT_SHAPE, seed=3)
+    return styleTransferTrainingModel.make_style_transfer_training_model(
+        style_predictor_factory_func=lambda n: stylePrediction.create_style_prediction_model(OUT_SHAPE, extractor, n),
+        style_transfer_factory_func=lambda: styleTransfer.create_style_transfer_model(
+            input_shape=IN_SHAPE, output_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=FILTERS, num_styles=1),
+        style_loss_func_factory_func=lambda: styleLoss.make_style_loss_function(loss_model, OUT_SHAPE, 1, with_depth_loss=False))
+
+
+def _dataset(n_batches, batch, seed=0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_batches):
+        content = rng.uniform(0, 1, (batch,) + IN_SHAPE).astype(np.float32)
+        style = rng.uniform(0, 1, (batch, 1) + OUT_SHAPE).astype(np.float32)
+        gt = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+        out.append(({"content": content, "style": style}, {"content": gt, "style": style}))
+    return out
+
+
+def test_fit_like_train_network(cuda_device, tmp_path):
+    """train_network.py:102-138: compile(RMSprop()), fit(x, validation_data, epochs, callbacks); weights change, the loss of
+    the training set falls, callbacks see synced weights, save_weights / load_weights round-trips the trained model."""
+    from realtime_style_transfer_b200 import optimizers
+    models = _python_training_model()
+    data = _dataset(2, 2)
+    before = {k: v.copy() for k, v in models.inference.weights.items()}
+    seen = []
+
+    class Callback:
+        def set_model(self, model):
+            self.model = model
+
+        def on_epoch_end(self, epoch, logs=None):
+            seen.append((epoch, dict(logs), self.model.weights["residual_block_0/conv0/kernel"].copy()))
+
+    models.training.compile(run_eagerly=False, optimizer=optimizers.RMSprop())
+    history = models.training.fit(x=data, validation_data=data[:1], epochs=4, initial_epoch=1, callbacks=[Callback()])
+    assert history.epoch == [1, 2, 3] and [s[0] for s in seen] == [1, 2, 3]
+    assert set(seen[0][1]) == {"loss", "feature_loss", "style_loss", "total_variation_loss",
+                               "val_loss", "val_feature_loss", "val_style_loss", "val_total_variation_loss"}
+    assert history.history["loss"][-1] < history.history["loss"][0]
+    assert models.training.optimizer.iterations == 6
+    after = models.inference.weights
+    changed = [k for k in before if not np.array_equal(before[k], after[k])]
+    assert set(changed) == set(before), "every variable (moving statistics included) is updated by training"
+    assert not np.array_equal(seen[0][2], seen[-1][2])            # callbacks saw fresh weights every epoch
+    # the trained variables serve inference, and survive a save / load round trip
+    x = data[0][0]
+    y1 = models.inference.predict(x)
+    path = models.training.save_weights(str(tmp_path / "latest_epoch_weights"))
+    fresh = _python_training_model()       # fresh random initialisation
+    fresh.training.load_weights(path).assert_existing_objects_matched()
+    y2 = fresh.inference.predict(x)
+    assert np.array_equal(y1, y2)
+    spec = O.TransferSpec(IN_SHAPE, OUT_SHAPE, RES_Y, FILTERS, 1)
+    tw = {k: v for k, v in after.items() if k in models.transfer.weights}
+    pw = {k: v for k, v in after.items() if k in models.style_predictor.weights}
+    ref = O.inference_forward(spec, tw, "DUMMY", pw, x["content"], x["style"]).numpy()
+    assert np.abs(y1 - ref).max() < 1e-4
+    models.training.close()
+
+
+def test_data_parallel_two_gpus(cuda_device):
+    """One process per GPU over NCCL (tests/dp_train_worker.py); needs two GPUs, skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dp_train_worker.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    print(out.stdout[-2000:], out.stderr[-2000:])
+    assert out.returncode == 0 and "DP_TRAIN_OK 2" in out.stdout

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import realtime_style_transfer_b200 as rst
-from realtime_style_transfer_b200 import _native, mixed_precision
+from realtime_style_transfer_b200 import _native, mixed_precision, optimizers
 from realtime_style_transfer_b200._plan import PredictorPlan, TransferPlan
 from realtime_style_transfer_b200.models import (stylePrediction, styleTransfer, styleTransferInferenceModel,
                                                  styleTransferTrainingModel, styleLoss)
@@ -148,6 +148,20 @@ def test_training_factory_and_loss_guards():
         style_loss_func_factory_func=lambda: styleLoss.make_style_loss_function(loss_model, (480, 960, 3), 1,
                                                                                 with_depth_loss=False))
     assert tm.inference.output_shape == (None, 480, 960, 3)
+    # the Keras slice train_network.py:102-138 touches
+    assert tm.training.inference_model is tm.inference and tm.loss_model is loss_model
+    with pytest.raises(RuntimeError):
+        tm.training.train_step(({"content": np.zeros((1, 240, 480, 3)), "style": np.zeros((1, 1, 480, 960, 3))},
+                                {"content": np.zeros((1, 480, 960, 3)), "style": np.zeros((1, 1, 480, 960, 3))}))
+    with pytest.raises(NotImplementedError):
+        tm.training.compile(optimizer="adam")
+    opt = optimizers.RMSprop()
+    assert (opt.learning_rate, opt.rho, opt.epsilon, opt.momentum, opt.centered) == (1e-3, 0.9, 1e-7, 0.0, False)
+    with pytest.raises(NotImplementedError):
+        optimizers.RMSprop(momentum=0.9)
+    tm.training.compile(run_eagerly=False, optimizer=opt)
+    tm.training.build(input_shape={"content": (None, 240, 480, 3), "style": (None, 1, 480, 960, 3)})
+    assert set(tm.training.trainable_variables) == {k for k in tm.inference.weights if "moving_" not in k}
 
 
 def test_mixed_precision_policy():
