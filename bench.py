@@ -302,12 +302,14 @@ def main():
             # per step: 9 convs 128->128 and one 32->128 (executed as 64->128: padded input channels are not counted)
             gflop_per_launch = BATCH * (9 * TRUNK_CONV_GFLOP + RES0_CONV0_GFLOP) / 10.0
             achieved = gflop_per_launch / (g_ms / g_n)       # GFLOP / ms = TFLOP/s
-            roof = {"kernel": "halo_gemm_kernel<128,128,NHWC,RELU,SCH_C3> (tcgen05 halo GEMM, residual bottleneck convs)",
+            roof = {"kernel": "halo_gemm2_kernel (2-CTA tcgen05 halo GEMM, cta_group::2, UMMA 256x128x16; residual bottleneck "
+                              "convs 128->128; the 32->128 first conv runs the 1-CTA halo_gemm_kernel<128,64,...>)",
                     "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16_tflops"],
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                    # (profiles/r01_ncu_full_halo_gemm_raw_subset.csv); algorithmic in+out is 118 MB, input is L2-resident
-                    "traffic": 72.5e6, "peak_source": pk["source"] + ", burst figure (kernel timed alone between events)",
+                    # (profiles/r01_ncu_full_halo_gemm2_raw_subset.csv: 60.2 MB read + 10.7..13.8 MB written); algorithmic
+                    # in+out is 118 MB, most of the output stays in the 126 MB L2 for the norm pass that follows
+                    "traffic": 72.4e6, "peak_source": pk["source"] + ", burst figure (kernel timed alone between events)",
                     "avg_launch_ms": g_ms / g_n, "launches": g_n, "share_of_step": shares.get("conv3x3_umma")}
         whole = {"achieved_tflops": fps * GFLOP_PER_FRAME / 1e3 / world, "peak": pk["bf16_tflops_sustained"],
                  "frac_of_sustained_bf16": fps * GFLOP_PER_FRAME / 1e3 / world / pk["bf16_tflops_sustained"]}
