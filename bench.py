@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SPEC = "rst-960-120-128-17"
-BATCH = 8
+BATCH = int(os.environ.get("RST_BENCH_BATCH", "8"))     # BASELINE config: 8 frames per GPU; the override is for experiments
 GFLOP_PER_FRAME = 127.269           # convolution MACs x2, true channel counts
 TRUNK_CONV_GFLOP = 2 * 4.247        # one 128->128 3x3 conv at 120x240, per frame
 RES0_CONV0_GFLOP = 2 * 1.062

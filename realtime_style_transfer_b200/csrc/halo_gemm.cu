@@ -585,10 +585,94 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
     reinterpret_cast<uint4*>(y)[i] = o;
 }
+// Fast path for the G-buffer layouts (16 real channels + NV windowed ones, W % 64 == 0): one warp per 64-pixel row segment.
+// The segment plus a 4-pixel halo on each side is 72*C floats = 18*C aligned float4 (coalesced loads) staged in the warp's
+// own shared-memory slice; each lane then assembles two packed pixels (stride-C reads are bank-conflict free for C = 17).
+template <int NV>
+__global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
+                                                             long long total_segments) {
+    constexpr int C = 16 + NV, ROW = NV <= 1 ? 32 : 64, NF4 = 18 * C;
+    extern __shared__ float4 pack_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (seg >= total_segments) return;
+    const int segs_per_row = W / 64;
+    const int sx = (int)(seg % segs_per_row);
+    const long long row = seg / segs_per_row;                      // n*H + y
+    const long long pix0 = row * W + sx * 64;                      // first pixel of the segment
+    float4* s4 = pack_smem + warp * NF4;
+    const float4* g4 = reinterpret_cast<const float4*>(x + (pix0 - 4) * C);
+    const bool left_oob = sx == 0, right_oob = sx == segs_per_row - 1;
+#pragma unroll
+    for (int i = lane; i < NF4; i += 32) {
+        const bool oob = (left_oob && i < C) || (right_oob && i >= 17 * C);     // 4 pixels = C float4 on each side
+        s4[i] = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(g4 + i);
+    }
+    __syncwarp();
+    const float* sf = reinterpret_cast<const float*>(s4);
+    constexpr int V = ROW / 8;                                     // 16-byte vectors per packed pixel
+    uint32_t w[2][ROW / 2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int pl = lane + 32 * half;                           // pixel within the segment
+        const float* px = sf + (4 + pl) * C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(px[2 * j], px[2 * j + 1]);
+            w[half][j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+#pragma unroll
+        for (int g = 0; g < NV; ++g) {
+            float v[10];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) v[t] = sf[(pl + t) * C + 16 + g];        // channel 16+g at x + t - 4
+            v[9] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[half][8 + 8 * g + j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+#pragma unroll
+            for (int j = 5; j < 8; ++j) w[half][8 + 8 * g + j] = 0u;
+        }
+#pragma unroll
+        for (int j = 8 + 8 * NV; j < ROW / 2; ++j) w[half][j] = 0u;
+    }
+    // transpose through the (now consumed) staging slice so that the warp writes the 64 packed pixels as one contiguous,
+    // fully coalesced run; the vector index is XOR-swizzled by the pixel to keep the shared-memory stores conflict-free
+    __syncwarp();
+    uint4* so = reinterpret_cast<uint4*>(s4);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int pl = lane + 32 * half;
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+            so[pl * V + (j ^ ((pl >> (V == 4 ? 1 : 0)) & (V - 1)))] =
+                make_uint4(w[half][4 * j], w[half][4 * j + 1], w[half][4 * j + 2], w[half][4 * j + 3]);
+    }
+    __syncwarp();
+    uint4* out = reinterpret_cast<uint4*>(y + pix0 * ROW);
+#pragma unroll
+    for (int k = lane; k < 64 * V; k += 32) {
+        const int pl = k / V, j = k % V;
+        out[k] = so[pl * V + (j ^ ((pl >> (V == 4 ? 1 : 0)) & (V - 1)))];
+    }
+}
+
 cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
                                    cudaStream_t s) {
     long long total = (long long)B * H * W * (row_elems / 8);
     if (total == 0) return cudaSuccess;
+    const int nv = C - 16;
+    if (n_real == 16 && (nv == 1 || nv == 2) && W % 64 == 0 && row_elems == (nv <= 1 ? 32 : 64) &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const long long segments = (long long)B * H * (W / 64);
+        const unsigned blocks = (unsigned)((segments + 7) / 8);
+        const size_t smem = (size_t)8 * 18 * C * sizeof(float4);
+        if (nv == 1) pack_stem_rows_kernel<1><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        else pack_stem_rows_kernel<2><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        return cudaGetLastError();
+    }
     pack_stem_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, total);
     return cudaGetLastError();
 }
