@@ -277,10 +277,16 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (valid) {
                         __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
                         if (EPI == EPI_NHWC) {
-                            uint4* o4 = reinterpret_cast<uint4*>(yb + (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW);
+                            __nv_bfloat16* o = yb + (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW;
+                            if (CW % 16 == 0) {
 #pragma unroll
-                            for (int j = 0; j < CW / 8; ++j)
-                                o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                                for (int j = 0; j < CW / 16; ++j) st_global_v8(o + 16 * j, packed + 8 * j);   // full sectors
+                            } else {
+                                uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+                                for (int j = 0; j < CW / 8; ++j)
+                                    o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            }
                         } else if (EPI == EPI_CONVT2) {
                             // columns = phase*CQ + ch with CQ = N/4; a 32-column chunk holds 32/CQ phases
                             constexpr int CQ = N / 4 >= 8 ? N / 4 : 8;

@@ -203,11 +203,10 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     v[j + 1] = valid ? __high2float(h2) : 0.f;
                 }
                 if (valid) {
-                    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) +
-                                                         (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW);
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) +
+                                       (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW;
 #pragma unroll
-                    for (int j = 0; j < CW / 8; ++j)
-                        o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    for (int j = 0; j < CW / 16; ++j) st_global_v8(o + 16 * j, packed + 8 * j);      // full sectors per lane
                 }
                 if (do_stats) {
                     float sq[32];
