@@ -295,11 +295,17 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int sph = 0; sph < PER_CHUNK; ++sph) {
                                 const int phase = c * PER_CHUNK + sph;
                                 const int oy = 2 * gh + (phase >> 1), ox = 2 * gw + (phase & 1);
-                                uint4* o4 = reinterpret_cast<uint4*>(yb + (((size_t)n * p.out_H + oy) * p.out_W + ox) * CQ);
+                                __nv_bfloat16* o = yb + (((size_t)n * p.out_H + oy) * p.out_W + ox) * CQ;
+                                if (CQ % 16 == 0) {
 #pragma unroll
-                                for (int j = 0; j < CQ / 8; ++j)
-                                    o4[j] = make_uint4(packed[sph * (CQ / 2) + 4 * j], packed[sph * (CQ / 2) + 4 * j + 1],
-                                                       packed[sph * (CQ / 2) + 4 * j + 2], packed[sph * (CQ / 2) + 4 * j + 3]);
+                                    for (int j = 0; j < CQ / 16; ++j) st_global_v8(o + 16 * j, packed + sph * (CQ / 2) + 8 * j);
+                                } else {
+                                    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+                                    for (int j = 0; j < CQ / 8; ++j)
+                                        o4[j] = make_uint4(packed[sph * (CQ / 2) + 4 * j], packed[sph * (CQ / 2) + 4 * j + 1],
+                                                           packed[sph * (CQ / 2) + 4 * j + 2], packed[sph * (CQ / 2) + 4 * j + 3]);
+                                }
                             }
                         }
                     }

@@ -96,6 +96,13 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* w) {
                  : "memory");
 }
 
+// 256-bit read-only global load that does not allocate in L1 (streaming data, read once)
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* w) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
+
 // ---- tcgen05 ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp, ncols pow2 >= 32
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
