@@ -798,13 +798,14 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
     const int C = p.C, n = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int c0 = (threadIdx.x % vec_per_pix) * 8;
+    const double inv_p = 1.0 / (double)p.P;
     float a0[8], b0[8], a1[8], b1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        const double sum = p.stats[((long long)n * C + c) * 2 + 0], sq = p.stats[((long long)n * C + c) * 2 + 1];
-        const double mean = sum / (double)p.P;
-        double var = sq / (double)p.P - mean * mean;
+        const double2 st = *reinterpret_cast<const double2*>(p.stats + ((long long)n * C + c) * 2);
+        const double mean = st.x * inv_p;
+        double var = fma(st.y, inv_p, -mean * mean);
         if (var < 0.0) var = 0.0;
         const float inv = rsqrtf((float)var + p.eps), nmi = -(float)mean * inv;
         const float* ps = p.params + n * p.param_bstride;
@@ -912,7 +913,8 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
     if (p.x_f32 && p.residual) return cudaErrorInvalidValue;
     const bool blend = p.num_styles == 2 && p.weights != nullptr;
     if (!p.x_f32 && !p.y_f32 && p.act != ACT_SIGMOID && (p.C == 16 || p.C == 32 || p.C == 64 || p.C == 128)) {
-        const int pix_per_block = max(256, 131072 / p.C);         // long streams per CTA measured faster than many short CTAs
+        static const int ppb_scale = getenv("RST_NORM_PPB") ? atoi(getenv("RST_NORM_PPB")) : 65536;
+        const int pix_per_block = max(64, ppb_scale / p.C);       // swept on B200 (profiles/r01_03_experiments.md): ~3 CTAs per SM is the optimum
         dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
         if (blend && p.residual) cin_apply_fast_kernel<true, true><<<grid, 256, 0, s>>>(p, pix_per_block);
         else if (blend) cin_apply_fast_kernel<true, false><<<grid, 256, 0, s>>>(p, pix_per_block);
