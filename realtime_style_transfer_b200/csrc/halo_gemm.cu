@@ -210,8 +210,31 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* my_sq = my_sum + N;
         const bool do_stats = p.stats != nullptr;
         int cur_n = -1;
+        // Narrow kernels (N <= 64: few epilogue warps, registers to spare) keep per-thread column sums across all the tiles of
+        // a sample and pay for the 2 x 31-shuffle warp reduction once per sample instead of once per tile.
+        constexpr bool ACCUM = N <= 64 && NCH / ESPLIT == 1 && !(MODE & MODE_POST);
+        float acc_s[ACCUM ? 32 : 1], acc_q[ACCUM ? 32 : 1];
+#pragma unroll
+        for (int j = 0; j < (ACCUM ? 32 : 1); ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
         auto flush = [&]() {
             if (do_stats && cur_n >= 0) {
+                if constexpr (ACCUM) {
+                    const float s1 = warp_transpose_reduce(acc_s, lane);
+                    const float s2 = warp_transpose_reduce(acc_q, lane);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+                    const int col = c_begin * CW + lane;
+                    int ch = col;
+                    bool on = lane < CW;
+                    if (EPI == EPI_CONVT2) ch = col % p.stats_c;
+                    if (EPI == EPI_QUAD3) { ch = col % 3; on = on && col < 12; }
+                    if (on) {
+                        double* dst = p.stats + ((size_t)cur_n * p.stats_c + ch) * 2;
+                        atomicAdd(dst, (double)s1);
+                        atomicAdd(dst + 1, (double)s2);
+                    }
+                    return;
+                }
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; ++c) {
                     const int col = c * CW + lane;
@@ -310,7 +333,12 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                if (do_stats) {
+                if constexpr (ACCUM) {
+                    if (do_stats) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { acc_s[j] += v[j]; acc_q[j] = fmaf(v[j], v[j], acc_q[j]); }
+                    }
+                } else if (do_stats) {
                     float sq[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
