@@ -899,39 +899,62 @@ __global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
     const int n = blockIdx.y;
     if (threadIdx.x < 3) {
         const int c = threadIdx.x;
-        const double sum = p.stats[((long long)n * 3 + c) * 2 + 0], sq = p.stats[((long long)n * 3 + c) * 2 + 1];
-        const double mean = sum / (double)p.P;
-        double var = sq / (double)p.P - mean * mean;
+        const double inv_p = 1.0 / (double)p.P;
+        const double2 st = *reinterpret_cast<const double2*>(p.stats + ((long long)n * 3 + c) * 2);
+        const double mean = st.x * inv_p;
+        double var = fma(st.y, inv_p, -mean * mean);
         if (var < 0.0) var = 0.0;
         const float inv = rsqrtf((float)var + p.eps), nmi = -(float)mean * inv;
-        for (int st = 0; st < p.num_styles; ++st) {
-            const float* ps = p.params + n * p.param_bstride + st * p.param_sstride;
-            sa[st][c] = inv * ps[p.scale_off + c];
-            sb[st][c] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
+        for (int st_ = 0; st_ < p.num_styles; ++st_) {
+            const float* ps = p.params + n * p.param_bstride + st_ * p.param_sstride;
+            sa[st_][c] = inv * ps[p.scale_off + c];
+            sb[st_][c] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
         }
     }
     __syncthreads();
-    const long long total4 = (long long)p.P * 3 / 4;
-    const float4* x4 = reinterpret_cast<const float4*>(p.x) + (long long)n * total4;
-    float4* y4 = reinterpret_cast<float4*>(p.y) + (long long)n * total4;
+    // 4 pixels = 12 floats = 3 float4 per thread-iteration: the channel of every lane of every vector is a compile-time constant
+    const long long groups = (long long)p.P / 4;                     // P % 4 == 0 (checked by the launcher)
+    const float4* x4 = reinterpret_cast<const float4*>(p.x) + (long long)n * groups * 3;
+    float4* y4 = reinterpret_cast<float4*>(p.y) + (long long)n * groups * 3;
     const float2* w2 = BLEND ? reinterpret_cast<const float2*>(p.weights) + (long long)n * p.P : nullptr;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 xv = x4[i];
-        float in[4] = {xv.x, xv.y, xv.z, xv.w}, o[4];
+    float a[3], b[3], a1[3], b1[3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long e = i * 4 + j;
-            const int c = (int)(e % 3);
-            float a = sa[0][c], b = sb[0][c];
+    for (int c = 0; c < 3; ++c) { a[c] = sa[0][c]; b[c] = sb[0][c]; a1[c] = BLEND ? sa[1][c] : 0.f; b1[c] = BLEND ? sb[1][c] : 0.f; }
+    const int act = p.act;
+    auto one = [&](const float4 (&in)[3], long long g, float4 (&out)[3]) {
+        const float* xi = reinterpret_cast<const float*>(in);
+        float* xo = reinterpret_cast<float*>(out);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            const int c = e % 3;
+            float aa = a[c], bb = b[c];
             if (BLEND) {
-                const float2 w = w2[e / 3];
-                a = a * w.x + sa[1][c] * w.y;
-                b = b * w.x + sb[1][c] * w.y;
+                const float2 w = w2[g * 4 + e / 3];
+                aa = aa * w.x + a1[c] * w.y;
+                bb = bb * w.x + b1[c] * w.y;
             }
-            const float t = fmaf(in[j], a, b);
-            o[j] = p.act == ACT_SIGMOID ? 1.f / (1.f + __expf(-t)) : (p.act == ACT_RELU ? fmaxf(t, 0.f) : t);
+            const float t = fmaf(xi[e], aa, bb);
+            xo[e] = act == ACT_SIGMOID ? 1.f / (1.f + __expf(-t)) : (act == ACT_RELU ? fmaxf(t, 0.f) : t);
         }
-        y4[i] = make_float4(o[0], o[1], o[2], o[3]);
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + stride < groups; g += 2 * stride) {                   // two groups (6 independent 16-byte loads) in flight
+        float4 i0[3], i1[3], o0[3], o1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { i0[k] = __ldg(x4 + g * 3 + k); i1[k] = __ldg(x4 + (g + stride) * 3 + k); }
+        one(i0, g, o0);
+        one(i1, g + stride, o1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { y4[g * 3 + k] = o0[k]; y4[(g + stride) * 3 + k] = o1[k]; }
+    }
+    for (; g < groups; g += stride) {
+        float4 i0[3], o0[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) i0[k] = __ldg(x4 + g * 3 + k);
+        one(i0, g, o0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) y4[g * 3 + k] = o0[k];
     }
 }
 
@@ -950,10 +973,10 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
         else cin_apply_fast_kernel<false, false><<<grid, 256, 0, s>>>(p, pix_per_block);
         return cudaGetLastError();
     }
-    if (p.x_f32 && p.y_f32 && p.C == 3 && ((long long)p.P * 3) % 4 == 0) {
-        const long long total4 = (long long)p.P * 3 / 4;
-        const long long want = (total4 + 255) / 256;
-        dim3 grid((unsigned)(want < 148 * 8 ? want : 148 * 8), (unsigned)p.B);
+    if (p.x_f32 && p.y_f32 && p.C == 3 && p.P % 4 == 0) {
+        const long long want = ((long long)p.P / 4 + 255) / 256;
+        const long long per_sample = max(1, 148 * 4 / p.B);          // ~4 CTAs per SM in total, each streaming a long run
+        dim3 grid((unsigned)(want < per_sample ? want : per_sample), (unsigned)p.B);
         if (blend) cin_apply_c3_kernel<true><<<grid, 256, 0, s>>>(p);
         else cin_apply_c3_kernel<false><<<grid, 256, 0, s>>>(p);
         return cudaGetLastError();
