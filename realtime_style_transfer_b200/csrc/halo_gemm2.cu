@@ -75,7 +75,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        mbar_init(&b_full[0], 1);
+        mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 4 * ESPLIT); }
         fence_barrier_init();
     }
@@ -118,10 +118,14 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 1) {
         // ================= B producer (both CTAs): this CTA's 64 output channels of every block, once ==========
+        // one barrier per 64-channel group, so the first MMAs start after 72 KB instead of 144 KB have landed
         if (lane == 0 && pair_begin < pair_end) {
-            if (leader_cta) mbar_expect_tx(&b_full[0], 2 * nblocks * kBHalf);
-            for (int kb = 0; kb < nblocks; ++kb)
-                tma_load_2d_2sm(sB + kb * kBHalf, &tmB, &b_full[0], 0, kb * N + (int)rank * (N / 2));
+            const int per_group = kKS2 / 4;
+            for (int g = 0; g < p.n_groups; ++g) {
+                if (leader_cta) mbar_expect_tx(&b_full[g], 2 * per_group * kBHalf);
+                for (int kb = g * per_group; kb < (g + 1) * per_group; ++kb)
+                    tma_load_2d_2sm(sB + kb * kBHalf, &tmB, &b_full[g], 0, kb * N + (int)rank * (N / 2));
+            }
         }
     } else if (warp == 2) {
         // ================= MMA issuer: leader CTA only ==========================================================
@@ -131,7 +135,6 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t db_const = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
             const bool issuer = elect_one();
             uint32_t as = 0, aph = 0, cs = 0, cph = 0;
-            if (pair_begin < pair_end) mbar_wait(&b_full[0], 0);
             const uint32_t sB16 = __shfl_sync(0xffffffffu, smem_u32(sB) >> 4, 0);
             const uint32_t sA16 = __shfl_sync(0xffffffffu, smem_u32(sA) >> 4, 0);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -141,6 +144,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t tmem_d = tmem_u + cs * N;
                 for (int g = 0; g < p.n_groups; ++g) {
                     mbar_wait(&a_full[as], aph);
+                    if (pr == pair_begin) mbar_wait(&b_full[g], 0);      // weights of this group are resident from here on
                     tc_fence_after();
                     const uint32_t a_base16 = sA16 + as * (kAStage2 >> 4);
                     const uint32_t b_base16 = sB16 + g * (kKS2 / 4) * (kBHalf >> 4);
