@@ -226,3 +226,39 @@ def test_tensorbuffer_roundtrip(tmp_path):
     np.testing.assert_array_equal(batches[0][1], x * 2)
     with pytest.raises(ValueError):
         tensorbuffer.load_tensor_from_buffer(tmp_path / "f0.bin", (6, 8, 18))
+
+
+def test_exr_reader_roundtrip_and_screenshot_layout(tmp_path):
+    """dataloaders/hdrScreenshots.py:14-29 without pyroexr: scan-line EXR (NONE / ZIPS / ZIP, HALF / FLOAT)."""
+    from realtime_style_transfer_b200.dataloaders import exr, hdrScreenshots
+    rng = np.random.default_rng(0)
+    h, w = 37, 50                                          # not a multiple of the 16-line ZIP block
+    planes = {c: rng.uniform(0, 4, (h, w)).astype(np.float32) for c in "RGB"}
+    for comp in ("NONE", "ZIPS", "ZIP"):
+        for ptype, tol in (("FLOAT", 0.0), ("HALF", 2e-3)):
+            path = tmp_path / f"t_{comp}_{ptype}.exr"
+            exr.save(path, planes, compression=comp, pixel_type=ptype)
+            img = exr.load(path)
+            assert img.header["compression"] == comp and list(img.channels()) == ["B", "G", "R"] and img.shape == (h, w)
+            for c in "RGB":
+                assert np.abs(img.channel(c) - planes[c]).max() <= tol * 4
+    # smooth data really goes through the zlib path (compressed block smaller than raw)
+    smooth = {"R": np.tile(np.linspace(0, 1, w, dtype=np.float32), (h, 1))}
+    exr.save(tmp_path / "s.exr", smooth, compression="ZIP", pixel_type="FLOAT")
+    assert (tmp_path / "s.exr").stat().st_size < h * w * 4 // 2
+    assert np.array_equal(exr.load(tmp_path / "s.exr").channel("R"), smooth["R"])
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.exr").write_bytes(b"\0" * 64)
+        exr.load(tmp_path / "bad.exr")
+    # one screenshot = <stem>.png + <stem>_<Channel>.exr per plane, concatenated in ShapeConfig.channels order
+    cfg = ShapeConfig(hdr=True, num_styles=1)
+    truth = []
+    for name, n in cfg.channels:
+        data = rng.uniform(0, 1, (h, w, n)).astype(np.float32)
+        truth.append(data)
+        exr.save(tmp_path / f"shot_{name}.exr", {c: data[..., i] for i, c in enumerate("RGB"[:n])}, "ZIP", "FLOAT")
+    (tmp_path / "shot.png").write_bytes(b"")
+    arr, path = hdrScreenshots.load_unreal_hdr_screenshot(tmp_path / "shot.png", cfg.channels)
+    assert arr.shape == (h, w, sum(n for _, n in cfg.channels)) and np.array_equal(arr, np.concatenate(truth, axis=-1))
+    batches = list(hdrScreenshots.iter_unreal_hdr_screenshots(tmp_path, cfg.channels, batch=2))
+    assert len(batches) == 1 and batches[0].shape == (1,) + arr.shape
