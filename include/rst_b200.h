@@ -33,7 +33,9 @@ enum rst_status {
 
 enum rst_precision {
     RST_PRECISION_FP32 = 0,  /* CUDA-core fp32 path, bar: max abs err <= 1e-4 vs the oracle */
-    RST_PRECISION_BF16 = 1   /* tcgen05 bf16 path (fp32 accumulate), bar: <= 2e-2 relative */
+    RST_PRECISION_BF16 = 1,  /* tcgen05 bf16 path (fp32 accumulate), bar: <= 2e-2 relative */
+    RST_PRECISION_TF32 = 2   /* tcgen05 tf32 operands on fp32 tensors (what TensorFlow itself does with fp32 convolutions on
+                              * Ampere and later GPUs); operator level and the VGG16 loss model only, see rst_loss_set_math */
 };
 
 enum rst_extractor {         /* stylePrediction.StyleFeatureExtractor, stylePrediction.py:19-22 */
@@ -153,6 +155,10 @@ int rst_loss_set_weight(rst_loss* loss, const char* name, const float* h_data, c
 int rst_loss_commit(rst_loss* loss);
 /* content / style / total-variation factors (defaults 1e4, 1e-3, 1e-1: styleLoss.py:101-104) */
 int rst_loss_set_factors(rst_loss* loss, float content, float style, float tv);
+/* Arithmetic of the VGG16 convolutions with >= 64 input channels and of their input gradients: RST_PRECISION_TF32 (default:
+ * tf32 operands on the tensor cores, fp32 accumulation -- TensorFlow's own default for float32 convolutions on Ampere and
+ * later) or RST_PRECISION_FP32 (CUDA-core fp32).  Takes effect at the next rst_loss_commit. */
+int rst_loss_set_math(rst_loss* loss, int precision);
 /* compute_loss(y_pred, y_true) (styleLoss.py:363-367): d_losses (B,4) = [loss, feature_loss, style_loss,
  * total_variation_loss], each a per-sample value like the reference's (B,) vectors. */
 int rst_loss_forward(rst_loss* loss, const float* d_pred, const float* d_gt_content, const float* d_gt_style,

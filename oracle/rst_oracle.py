@@ -511,15 +511,42 @@ def init_vgg16_weights(seed: int = 3) -> Dict[str, np.ndarray]:
     return out
 
 
-def vgg16_features(W: Dict[str, Tensor], image01: Tensor) -> Dict[str, Tensor]:
-    """StyleLossModelVGG.call, styleLoss.py:69-109: x*255 -> caffe preprocess -> VGG16 taps."""
+class _RoundTF32(torch.autograd.Function):
+    """Round to the tf32 grid (8-bit exponent, 10 explicit mantissa bits), straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        m, e = torch.frexp(x)                        # x = m * 2**e, 0.5 <= |m| < 1: 11 significant bits -> scale by 2**11
+        return torch.ldexp(torch.round(m * 2048.0) / 2048.0, e)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def tf32_round(x: Tensor) -> Tensor:
+    return _RoundTF32.apply(x)
+
+
+def vgg16_features(W: Dict[str, Tensor], image01: Tensor, tf32: bool = False) -> Dict[str, Tensor]:
+    """StyleLossModelVGG.call, styleLoss.py:69-109: x*255 -> caffe preprocess -> VGG16 taps.
+    tf32=True restates TensorFloat-32 execution -- TensorFlow's default for float32 convolutions on Ampere-and-later GPUs
+    (tf.config.experimental.enable_tensor_float_32_execution): the operands of every convolution with >= 64 input channels
+    are rounded to tf32, products and sums stay exact (here: the dtype of the call).  The 3-channel first layer stays fp32."""
     x = image01 * 255.0
     x = x.flip(-1) - torch.tensor(VGG_CAFFE_MEAN_BGR, dtype=x.dtype)
     feats = {}
+    first = True
     for bi, (blk, n, _) in enumerate(VGG16_CFG):
         for i in range(1, n + 1):
-            x = F.relu(conv2d_same(x, W[f"{blk}_conv{i}/kernel"], W[f"{blk}_conv{i}/bias"]))
+            k = W[f"{blk}_conv{i}/kernel"]
+            if tf32 and not first:
+                k = tf32_round(k)
+            x = F.relu(conv2d_same(x, k, W[f"{blk}_conv{i}/bias"]))
+            if tf32:
+                x = tf32_round(x)                    # activations are stored on the tf32 grid: the next conv's operand
             feats[f"{blk}_conv{i}"] = x
+            first = False
         if bi < 4:
             x = _nhwc(F.max_pool2d(_nchw(x), 2))
     return feats
@@ -543,7 +570,7 @@ def total_variation(img: Tensor) -> Tensor:
 
 
 def style_loss_vgg(vgg_weights, prediction, gt_content, gt_style, dtype=torch.float32,
-                   content_factor=1e4, style_factor=1e-3, tv_factor=1e-1) -> Dict[str, Tensor]:
+                   content_factor=1e4, style_factor=1e-3, tv_factor=1e-1, tf32: bool = False) -> Dict[str, Tensor]:
     """make_style_loss_function with StyleLossModelVGG and with_depth_loss=False,
     styleLoss.py:295-369 (factors :101-104).  All outputs are (B,) vectors."""
     W = {k: torch.as_tensor(v).to(dtype) for k, v in vgg_weights.items()}
@@ -552,9 +579,9 @@ def style_loss_vgg(vgg_weights, prediction, gt_content, gt_style, dtype=torch.fl
     if gt_style.dim() == 5:
         assert gt_style.shape[1] == 1, "Loss model does not support multiple styles."
         gt_style = gt_style[:, 0]
-    fc = vgg16_features(W, torch.as_tensor(gt_content).to(dtype))
-    fs = vgg16_features(W, gt_style)
-    fp = vgg16_features(W, pred)
+    fc = vgg16_features(W, torch.as_tensor(gt_content).to(dtype), tf32)
+    fs = vgg16_features(W, gt_style, tf32)
+    fp = vgg16_features(W, pred, tf32)
     feature = torch.stack([mean_l2_loss_on_batch(fp[l] - fc[l]) for l in VGG_CONTENT_LAYERS]).mean(0) * content_factor
     style = torch.stack([mean_l2_loss_on_batch(gram_matrix(fp[l]) - gram_matrix(fs[l]))
                          for l in VGG_STYLE_LAYERS]).mean(0) * style_factor
@@ -602,7 +629,7 @@ RMSPROP = dict(lr=1e-3, rho=0.9, eps=1e-7)      # tf.keras.optimizers.RMSprop() 
 
 
 def training_forward_backward(spec: TransferSpec, transfer_w, extractor: str, predictor_w, vgg_w, content, style, gt_content,
-                              dtype=torch.float64, moving=None, tap_grads=None, pred_grad=None):
+                              dtype=torch.float64, moving=None, tap_grads=None, pred_grad=None, vgg_tf32=False):
     """One forward/backward of the reference's training model with num_styles == 1:
     y_pred = transfer(content, predictor(style)) in training mode (BatchNorm uses batch statistics), loss vector from the
     VGG loss model, gradient of the batch SUM of the loss w.r.t. every trainable variable (VGG is frozen).
@@ -621,7 +648,7 @@ def training_forward_backward(spec: TransferSpec, transfer_w, extractor: str, pr
     y = _transfer_forward_t(spec, tw, torch.as_tensor(content).to(dtype), params, training=True, moving=moving, taps=taps)
     if taps is not None:
         taps["style_params"] = params
-    losses = style_loss_vgg(vgg_w, y, gt_content, style_t, dtype=dtype)
+    losses = style_loss_vgg(vgg_w, y, gt_content, style_t, dtype=dtype, tf32=vgg_tf32)
     total = losses["loss"].sum()
     names = [("t", k) for k, v in tw.items() if v.requires_grad] + [("p", k) for k, v in pw.items() if v.requires_grad]
     tensors = [tw[k] if w == "t" else pw[k] for w, k in names]

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librst_sm100.so")
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_TF32 = 2
 EXTRACTOR_NONE, EXTRACTOR_DUMMY, EXTRACTOR_MOBILE_NET = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 4
 
@@ -78,6 +79,7 @@ SIGNATURES = {
     "rst_loss_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, _i64p, C.c_int]),
     "rst_loss_commit": (C.c_int, [_vp]),
     "rst_loss_set_factors": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float]),
+    "rst_loss_set_math": (C.c_int, [_vp, C.c_int]),
     "rst_loss_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rst_loss_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "rst_train_create": (C.c_int, [C.POINTER(RstConfig), C.c_int, C.POINTER(_vp)]),
@@ -359,6 +361,10 @@ class NativeLoss:
             shape = (C.c_int64 * arr.ndim)(*arr.shape)
             self._check(self.lib.rst_loss_set_weight(self.handle, name.encode(), _ptr(arr), shape, arr.ndim))
         self._check(self.lib.rst_loss_commit(self.handle))
+
+    def set_math(self, precision: int):
+        """PRECISION_TF32 (default) or PRECISION_FP32 for the VGG16 convolutions; call before set_weights (commit)."""
+        self._check(self.lib.rst_loss_set_math(self.handle, int(precision)))
 
     def set_factors(self, content: float, style: float, tv: float):
         self._check(self.lib.rst_loss_set_factors(self.handle, content, style, tv))

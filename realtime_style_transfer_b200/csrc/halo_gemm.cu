@@ -48,6 +48,8 @@ constexpr int kMaxKsteps = 128;
 constexpr int MODE_RELU = 1;      // ReLU after the bias
 constexpr int MODE_POST = 2;      // then per-column affine (inference BatchNorm) and a second ReLU
 constexpr int MODE_F32 = 4;       // store fp32 instead of bf16
+constexpr int MODE_TF32 = 8;      // operands are fp32 (tf32) instead of bf16: K = 8 per MMA, same byte geometry; stores are
+                                  // rounded to tf32 so that the next layer's operand fetch (which truncates) sees exact values
 
 // epilogue warps per TMEM lane quadrant: one per 32-column chunk (the epilogue is issue-latency bound, more warps hide it)
 __host__ __device__ constexpr int halo_esplit(int n) { return n >= 128 ? 4 : n >= 64 ? 2 : 1; }
@@ -157,7 +159,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // The whole warp runs the (fully unrolled, compile-time scheduled) loop so that descriptor arithmetic stays in
         // the uniform datapath; only the tcgen05.mma / tcgen05.commit instructions themselves are issued by lane 0.
         {
-            const uint32_t idesc = make_idesc_bf16(128, N);
+            const uint32_t idesc = (MODE & MODE_TF32) ? make_idesc_tf32(128, N) : make_idesc_bf16(128, N);
             const uint64_t da_const = make_smem_desc(0, 16, sched_halo_h(SCH) * ROWB, SWZ);
             const uint64_t db_const = sched_b_units(SCH) ? make_smem_desc(0, 16, 256, SWIZZLE_32B) : make_smem_desc(0, 16, 1024, SWIZZLE_128B);
             const bool leader = elect_one();
@@ -187,7 +189,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH, ROWB, ks) >> 4));
                         const uint64_t db = db_const | (uint64_t)(sched_b_units(SCH) ? sB16 + sched_b_unit(SCH, ks) * 64
                                                                                     : b_base16 + (BRES ? (ks / 4) * (BBLK / 16) : 0) + (ks & 3) * 2);
-                        if (leader) mma_f16_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
+                        if (leader) {
+                            if (MODE & MODE_TF32) mma_tf32_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
+                            else mma_f16_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
+                        }
                         if (!BRES && (ks & 3) == 3) {
                             if (leader) mma_commit(&b_empty[bs]);
                             if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
@@ -274,6 +279,10 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     v[j] = x;
                 }
                 if (MODE & MODE_F32) {
+                    if (MODE & MODE_TF32) {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) v[j] = round_tf32(v[j]);
+                    }
                     if (valid) {
                         float4* o4;
                         if (EPI == EPI_QUAD3)
@@ -380,7 +389,9 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmemBudget = 227 * 1024;
 
-static bool sched_resident(const HaloGemmLaunch& l) { return !(l.sched == SCH_C3 && l.row_bytes == 128 && l.N == 128); }
+static bool sched_resident(const HaloGemmLaunch& l) {
+    return !(l.sched == SCH_C3 && l.row_bytes == 128 && l.N == 128) && !(l.mode & MODE_TF32);
+}
 
 bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err) {
     p->ksteps = sched_ksteps(l->sched, l->row_bytes);
@@ -449,6 +460,10 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
     RST_HALO_CASE(128, 128, EPI_CONVT2, 0, SCH_T2, true)                    // expand_0: 4 phases x 32 channels
     RST_HALO_CASE(64, 64, EPI_CONVT2, 0, SCH_T2, true)                      // expand_1: 4 phases x 16 channels
     RST_HALO_CASE(16, 128, EPI_QUAD3, MODE_F32, SCH_HEAD, true)             // expand_last: 4 pixels x 3 channels
+    RST_HALO_CASE(128, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)   // tf32 3x3 convs (VGG16 loss model)
+    RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)
+    RST_HALO_CASE(128, 128, EPI_NHWC, MODE_F32 | MODE_TF32, SCH_C3, false)               // ... and their input gradients
+    RST_HALO_CASE(64, 128, EPI_NHWC, MODE_F32 | MODE_TF32, SCH_C3, false)
 #undef RST_HALO_CASE
     return cudaErrorInvalidValue;
 }

@@ -107,7 +107,7 @@ struct HaloGemmParams {
 };
 
 constexpr int kHaloThreads = 352;    // warps: 0 A-TMA, 1 B-TMA, 2 MMA, 3..10 epilogue (two per TMEM lane quadrant)
-constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4;
+constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4, HALO_MODE_TF32 = 8;
 
 struct HaloGemmLaunch {
     int N = 128;            // GEMM N (output columns): 16, 32, 64 or 128
@@ -140,6 +140,29 @@ cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_hal
                               cudaStream_t s);
 // Packs B: f(kstep, n, e) -> weight of K-step `kstep`, output column n, K element e (0..15).
 void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out);
+
+// ---- tf32 3x3 convolution on fp32 NHWC tensors (conv_tf32.cu): the VGG16 loss model's layers and their input gradients ----
+// 3x3, stride 1, 'same'; Cin % 32 == 0, Cout % 64 == 0.  Operands are fp32 bit patterns consumed as tf32 by tcgen05
+// (kind::tf32, fp32 accumulation); weights are rounded to tf32 (nearest) once, outputs are stored rounded to tf32.
+struct Tf32Conv3x3 {
+    int ci = 0, co = 0, nb = 128, nblk = 0;
+    bool relu = false;
+    float* w_packed = nullptr;          // [nblk][n_groups * 9 blocks][nb rows][32 floats]
+    float* bias = nullptr;              // [co] or null
+    HaloGemmLaunch launch;
+    HaloGemmParams p;
+    std::vector<CUtensorMap> tmB;       // one weight map per block of nb output channels
+    struct BoundInput { const void* x; int B, H, W; CUtensorMap tm; };
+    std::vector<BoundInput> inputs;     // tensor maps of the input tensors seen so far
+    Tf32Conv3x3() = default;
+    Tf32Conv3x3(const Tf32Conv3x3&) = delete;
+    Tf32Conv3x3& operator=(const Tf32Conv3x3&) = delete;
+    ~Tf32Conv3x3();
+    // k: Keras kernel (3,3,ci_layer,co_layer).  input_gradient = false: y = [relu](conv(x, k) + bias), ci = ci_layer.
+    // input_gradient = true: y = d conv / d input applied to x = gradient w.r.t. the layer output (ci = co_layer, co = ci_layer).
+    bool setup(int ci_layer, int co_layer, const float* k, const float* bias_host, bool relu, bool input_gradient, std::string* err);
+    cudaError_t run(const float* x, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
+};
 
 // ---- bf16 elementwise companions ------------------------------------------------------------------
 cudaError_t launch_f32_to_bf16_pad(const float* x, __nv_bfloat16* y, long long pixels, int c_in, int c_out, cudaStream_t s);

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
             v = apply_act(v, p.act2);
             long long o = m * p.Co + co;
             if (p.residual) v += __ldg(p.residual + o);
+            if (p.out_tf32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
             p.y[o] = v;
         }
     }

@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "rst_internal.cuh"
+#include "halo_gemm.cuh"
+#include <memory>
 
 using namespace rst;
 
@@ -168,6 +170,10 @@ struct rst_loss {
     double* style_norm_dev = nullptr;
     int last_batch = 0;
     int64_t launches = 0;
+    // tf32 tensor-core convolutions for the 12 layers with >= 64 input channels (conv_tf32.cu), forward and input gradient
+    int math = RST_PRECISION_TF32;
+    int num_sms = 148;
+    std::unique_ptr<Tf32Conv3x3> fwd[13], bwd[13];
 };
 
 static thread_local std::string g_loss_err;
@@ -268,7 +274,32 @@ extern "C" int rst_loss_commit(rst_loss* c) {
             if (!d) LCUDA(c, cudaMalloc(&d, it->second.size() * sizeof(float)));
             LCUDA(c, cudaMemcpy(d, it->second.data(), it->second.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
+    for (int i = 0; i < 13; ++i) { c->fwd[i].reset(); c->bwd[i].reset(); }
+    if (c->math == RST_PRECISION_TF32) {
+        cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
+        std::string err;
+        for (int i = 1; i < 13; ++i) {
+            const std::vector<float>& k = c->host_w[kVgg[i].name + "/kernel"];
+            const std::vector<float>& b = c->host_w[kVgg[i].name + "/bias"];
+            c->fwd[i].reset(new Tf32Conv3x3());
+            c->bwd[i].reset(new Tf32Conv3x3());
+            if (!c->fwd[i]->setup(kVgg[i].ci, kVgg[i].co, k.data(), b.data(), true, false, &err) ||
+                !c->bwd[i]->setup(kVgg[i].ci, kVgg[i].co, k.data(), nullptr, false, true, &err))
+                return lfail(c, RST_ERR_CUDA, "rst_loss_commit: " + err);
+        }
+    }
     c->committed = true;
+    return RST_OK;
+}
+
+// RST_PRECISION_FP32: CUDA-core fp32 convolutions everywhere.  RST_PRECISION_TF32 (default): the 12 convolutions with >= 64 input
+// channels and their input gradients run on the tensor cores with tf32 operands and fp32 accumulation -- what TensorFlow does
+// with float32 convolutions on Ampere-and-later GPUs unless tf.config.experimental.enable_tensor_float_32_execution(False).
+extern "C" int rst_loss_set_math(rst_loss* c, int precision) {
+    if (!c) return RST_ERR_INVALID;
+    if (precision != RST_PRECISION_FP32 && precision != RST_PRECISION_TF32)
+        return lfail(c, RST_ERR_INVALID, "rst_loss_set_math: RST_PRECISION_FP32 or RST_PRECISION_TF32");
+    if (precision != c->math) { c->math = precision; c->committed = false; }
     return RST_OK;
 }
 
@@ -294,9 +325,17 @@ static int vgg_forward(rst_loss* c, const float* img, int batch, bool keep, cuda
     int flip = 0;
     for (int i = 0; i < 13; ++i) {
         float* y = keep ? c->act[i] : (flip ? c->sb : c->sa);
-        ConvF32 p = vgg_conv(c, i, cur, y, batch);
-        LCUDA(c, launch_conv_f32(p, s));
-        c->launches++;
+        if (c->fwd[i] && !getenv("RST_EXP_LOSS_FWD_FP32")) {
+            std::string err;
+            cudaError_t e = c->fwd[i]->run(cur, y, batch, c->lh[i], c->lw[i], c->num_sms, s, &err);
+            if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "tf32 conv " + kVgg[i].name + ": " + (err.empty() ? cudaGetErrorString(e) : err));
+            c->launches += c->fwd[i]->nblk;
+        } else {
+            ConvF32 p = vgg_conv(c, i, cur, y, batch);
+            p.out_tf32 = c->math == RST_PRECISION_TF32 ? 1 : 0;
+            LCUDA(c, launch_conv_f32(p, s));
+            c->launches++;
+        }
         int rc = on_tap(i, y);
         if (rc) return rc;
         cur = y;
@@ -405,6 +444,13 @@ extern "C" int rst_loss_backward(rst_loss* c, const float* d_pred, float* d_grad
             }
         }
         relu_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(g, c->act[i], n);
+        if (c->bwd[i] && !getenv("RST_EXP_LOSS_BWD_FP32")) {      // (env: experiment switch, see profiles/r01_03_experiments.md)
+            std::string err;
+            cudaError_t e = c->bwd[i]->run(g, gn, B, c->lh[i], c->lw[i], c->num_sms, s, &err);
+            if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "tf32 dgrad " + kVgg[i].name + ": " + (err.empty() ? cudaGetErrorString(e) : err));
+            std::swap(g, gn);
+            continue;
+        }
         // dgrad of the 3x3 SAME conv: a "transposed" pass over g with the same kernel, input/output channel roles swapped
         ConvF32 p;
         p.x = g; p.y = gn; p.w = c->dev_w[kVgg[i].name + "/kernel"];

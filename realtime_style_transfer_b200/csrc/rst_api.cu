@@ -5,6 +5,7 @@
 #include <tuple>
 
 #include "rst_ctx.h"
+#include "halo_gemm.cuh"
 
 using namespace rst;
 
@@ -1036,6 +1037,26 @@ extern "C" int rst_op_conv2d(const float* d_x, const float* d_kernel, const floa
         std::string err;
         int rc = op_conv2d_bf16(d_x, d_kernel, d_bias, d_y, batch, h, w, ci, co, kh, kw, stride, transposed, act, s, &err);
         if (rc) return op_fail(rc, err);
+        return RST_OK;
+    }
+    if (precision == RST_PRECISION_TF32) {
+        if (kh != 3 || kw != 3 || stride != 1 || ci % 32 || co % 64 || (act != ACT_RELU && act != ACT_NONE))
+            return op_fail(RST_ERR_UNSUPPORTED, "rst_op_conv2d(tf32): 3x3 stride-1 convs with Cin % 32 == 0, Cout % 64 == 0 only");
+        std::vector<float> hk((size_t)9 * ci * co), hb(co, 0.f);
+        OP_CUDA(cudaMemcpy(hk.data(), d_kernel, hk.size() * 4, cudaMemcpyDeviceToHost));
+        if (d_bias) OP_CUDA(cudaMemcpy(hb.data(), d_bias, co * 4, cudaMemcpyDeviceToHost));
+        Tf32Conv3x3 conv;
+        std::string err;
+        // a stride-1 'same' Conv2DTranspose with kernel (3,3,co,ci) is the input gradient of the conv layer co -> ci with that kernel
+        const bool ok = transposed ? conv.setup(co, ci, hk.data(), d_bias ? hb.data() : nullptr, act == ACT_RELU, true, &err)
+                                   : conv.setup(ci, co, hk.data(), d_bias ? hb.data() : nullptr, act == ACT_RELU, false, &err);
+        if (!ok) return op_fail(RST_ERR_CUDA, err);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = conv.run(d_x, d_y, batch, h, w, sms, s, &err);
+        if (e != cudaSuccess) return op_fail(RST_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
+        OP_CUDA(cudaStreamSynchronize(s));
         return RST_OK;
     }
     ConvF32 p;

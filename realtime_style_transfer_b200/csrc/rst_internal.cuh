@@ -44,6 +44,7 @@ struct ConvF32 {
     const float* post_shift = nullptr;
     int act2 = ACT_NONE;
     const float* residual = nullptr;
+    int out_tf32 = 0;                       // round the stored value to tf32 (it feeds a tf32 tensor-core conv, which truncates)
 };
 cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s);
 

@@ -229,5 +229,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::tf32, tf32 x tf32 -> fp32 (fp32 bit patterns in shared memory, the low 13 mantissa bits are ignored), K = 8 per MMA.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4)                    // D format: F32
+           | (2u << 7)                  // A format: TF32
+           | (2u << 10)                 // B format: TF32
+           | ((uint32_t)(N >> 3) << 17)
+           | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// round-to-nearest fp32 -> tf32 (kept in an fp32 container)
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 }  // namespace umma
 }  // namespace rst

@@ -76,6 +76,8 @@ class StyleLossModelVGG(StyleLossModelBase):
                 cin = co
         self._native = None
         self._dirty = True
+        # arithmetic of the VGG convolutions: tf32 tensor cores (TensorFlow's own default on Ampere and later) or fp32
+        self.math = _native.PRECISION_TF32
 
     @property
     def weights(self):
@@ -95,7 +97,9 @@ class StyleLossModelVGG(StyleLossModelBase):
                 self._native.close()
             self._native = _native.NativeLoss(self.input_shape[0], self.input_shape[1], batch)
             self._dirty = True
-        if self._dirty:
+        if self._dirty or getattr(self, "_native_math", None) != self.math:
+            self._native.set_math(self.math)
+            self._native_math = self.math
             self._native.set_weights(self._variables)
             self._native.set_factors(self.content_loss_factor, self.style_loss_factor, self.total_variation_loss_factor)
             self._dirty = False

@@ -58,7 +58,8 @@ class StyleTransferTrainingModel(NativeModel):
 
     def _versions(self):
         inf = self.inference_model
-        return (inf.transfer._version, inf.style_predictor._version, id(self.loss_model), getattr(self.loss_model, "_version", 0))
+        return (inf.transfer._version, inf.style_predictor._version, id(self.loss_model), getattr(self.loss_model, "_version", 0),
+                getattr(self.loss_model, "math", None))
 
     # -- variables live in the inference model's two sub-models ---------------------------------------------------
     def _all_variables(self):
@@ -126,6 +127,7 @@ class StyleTransferTrainingModel(NativeModel):
             # The RMSprop accumulators are kept, as tf.keras keeps its slots when variables are assigned.
             self._trainer.model.set_weights(self._all_variables(), commit=True)
             lm = self.loss_model
+            self._trainer.loss.set_math(getattr(lm, "math", _native.PRECISION_TF32))
             self._trainer.loss.set_weights(lm.weights)
             self._trainer.loss.set_factors(lm.content_loss_factor, lm.style_loss_factor, lm.total_variation_loss_factor)
             self._mirrored = self._versions()

@@ -90,6 +90,45 @@ def test_op_conv2d_fp32(cuda_device, b, h, w, ci, co, k, s, transposed):
         assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("b,h,w,ci,co,relu,transposed", [
+    (2, 16, 32, 64, 64, True, False),        # VGG block1_conv2
+    (1, 30, 60, 128, 256, True, False),      # two 128-column blocks, partial tiles (30 rows, 60 columns)
+    (1, 9, 21, 512, 512, True, False),       # 16 channel groups, four column blocks
+    (2, 12, 20, 64, 128, False, False),      # no activation
+    (2, 12, 20, 128, 64, False, True),       # input gradient of a 64 -> 128 layer (= stride-1 Conv2DTranspose)
+    (1, 15, 30, 512, 256, False, True),
+])
+def test_op_conv2d_tf32(cuda_device, b, h, w, ci, co, relu, transposed):
+    """tcgen05 kind::tf32 3x3 conv against (a) the same conv on tf32-rounded operands in fp64: only accumulation order differs;
+    (b) the exact fp32 conv: within tf32 operand rounding (2^-11 relative per operand)."""
+    rng = np.random.default_rng(ci + co + h)
+    x = rng.standard_normal((b, h, w, ci)).astype(np.float32)
+    kern = (rng.standard_normal((3, 3, co, ci) if transposed else (3, 3, ci, co)) * np.sqrt(2.0 / (9 * ci))).astype(np.float32)
+    bias = rng.standard_normal(co).astype(np.float32)
+
+    def tf32(a):                                  # round to nearest, ties away (cvt.rna.tf32.f32)
+        u = a.view(np.uint32).astype(np.uint64)
+        return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+    def conv(xx, kk):
+        f = O.conv2d_transpose_same if transposed else O.conv2d_same
+        y = f(torch.as_tensor(xx, dtype=torch.float64), torch.as_tensor(kk, dtype=torch.float64),
+              torch.as_tensor(bias, dtype=torch.float64), 1)
+        return (torch.relu(y) if relu else y).numpy()
+
+    exact, rounded = conv(x, kern), conv(tf32(x), tf32(kern))
+    d_y = torch.full(exact.shape, float("nan"), device=cuda_device)
+    d_x, d_k, d_b = dev(x, cuda_device), dev(kern, cuda_device), dev(bias, cuda_device)
+    _native.op_conv2d(d_x.data_ptr(), d_k.data_ptr(), d_b.data_ptr(), d_y.data_ptr(), b, h, w, ci, co, 3, 3, 1, transposed,
+                      _native.ACT_RELU if relu else _native.ACT_NONE, _native.PRECISION_TF32, stream())
+    got = d_y.cpu().numpy().astype(np.float64)
+    scale = np.abs(exact).max()
+    e_rounded, e_exact = np.abs(got - rounded).max() / scale, np.abs(got - exact).max() / scale
+    print(f"tf32 conv {ci}->{co}: vs tf32-rounded operands {e_rounded:.2e}, vs exact fp32 {e_exact:.2e}")
+    assert e_rounded < 1e-3        # the MMA truncates x (only the weights are pre-rounded) and the output is stored in tf32
+    assert e_exact < 2e-3
+
+
 def test_op_apply_style_weights_known_answer(cuda_device):
     """The reference's own known-answer test, run through the CUDA operator."""
     g = np.load(os.path.join(GOLDEN, "apply_style_weights_known_answer.npz"))

@@ -1,6 +1,16 @@
 """GPU parity of the training loss (VGG16 features, Gram style loss, content loss, total variation), forward and
 backward, against the oracle (oracle/rst_oracle.py, autograd for the gradient).  Bar (north_star): Gram-loss scalar
-within 1e-3 relative."""
+within 1e-3 relative.
+
+Two arithmetic modes (rst_loss_set_math):
+  * fp32 CUDA-core convolutions: losses and the gradient w.r.t. the prediction are checked tightly against the oracle;
+  * tf32 tensor-core convolutions (default; what TensorFlow does with float32 convolutions on Ampere and later): the loss
+    scalars stay within the 1e-3 bar of the EXACT oracle (measured 3e-4).  The gradient can only be checked for direction:
+    a randomly initialised VGG16 on random images is chaotic at this scale -- rounding ONE activation tensor to tf32 moves
+    the fp64 gradient by 8 % relative L2 (ReLU / max-pool routing flips), and the oracle's own tf32 restatement
+    (vgg16_features(tf32=True)) is no closer to the kernel than the exact model is (7 %), because a 1e-6 accumulation-order
+    difference flips a tf32 rounding now and then.  The tf32 kernels themselves (forward and input gradient) are checked
+    tightly at operator level in test_gpu_fp32.py::test_op_conv2d_tf32, and the backward pass logic is the fp32 one."""
 import numpy as np
 import pytest
 import torch
@@ -20,12 +30,18 @@ def _inputs(b, h, w, seed=0):
     return pred, content, style
 
 
+MATHS = [("fp32", _native.PRECISION_FP32), ("tf32", _native.PRECISION_TF32)]
+
+
+@pytest.mark.parametrize("math_name,math", MATHS)
 @pytest.mark.parametrize("b,h,w", [(2, 64, 96), (1, 128, 160)])
-def test_loss_forward_matches_oracle(cuda_device, b, h, w):
+def test_loss_forward_matches_oracle(cuda_device, b, h, w, math_name, math):
     vgg = O.init_vgg16_weights(seed=3)
     pred, content, style = _inputs(b, h, w)
-    ref = O.style_loss_vgg(vgg, pred, content, style)
+    exact = O.style_loss_vgg(vgg, pred, content, style, dtype=torch.float64)
+    ref = exact
     model = styleLoss.StyleLossModelVGG((h, w, 3))
+    model.math = math
     model.set_weights(vgg)
     compute_loss, m2 = styleLoss.make_style_loss_function(model, (h, w, 3), 1, with_depth_loss=False)
     assert m2 is model
@@ -34,13 +50,15 @@ def test_loss_forward_matches_oracle(cuda_device, b, h, w):
         r = ref[key].numpy()
         assert got[key].shape == (b,)
         rel = np.abs(got[key] - r).max() / max(np.abs(r).max(), 1e-12)
-        print(key, got[key], r, rel)
-        assert rel < 1e-3, key
+        rel_exact = np.abs(got[key] - exact[key].numpy()).max() / max(np.abs(r).max(), 1e-12)
+        print(math_name, key, got[key], r, rel, "vs exact", rel_exact)
+        assert rel_exact < (1e-5 if math_name == "fp32" else 1e-3), key     # north_star bar: 1e-3, either arithmetic
     with pytest.raises(AssertionError):
         styleLoss.make_style_loss_function(model, (h, w, 3), 2, with_depth_loss=False)
 
 
-def test_loss_backward_matches_autograd(cuda_device):
+@pytest.mark.parametrize("math_name,math", MATHS)
+def test_loss_backward_matches_autograd(cuda_device, math_name, math):
     b, h, w = 2, 64, 96
     vgg = O.init_vgg16_weights(seed=3)
     pred, content, style = _inputs(b, h, w, seed=1)
@@ -49,6 +67,7 @@ def test_loss_backward_matches_autograd(cuda_device):
     out["loss"].sum().backward()                  # Keras differentiates the (B,) loss vector = its batch sum
     ref_grad = p.grad.numpy()
     loss = _native.NativeLoss(h, w, b)
+    loss.set_math(math)
     loss.set_weights(vgg)
     d_pred = torch.tensor(pred).to(cuda_device)
     d_c = torch.tensor(content).to(cuda_device)
@@ -61,7 +80,11 @@ def test_loss_backward_matches_autograd(cuda_device):
     got = d_g.cpu().numpy()
     num = np.sqrt(((got - ref_grad) ** 2).sum())
     den = np.sqrt((ref_grad ** 2).sum())
-    print("grad rel l2", num / den, "max ref", np.abs(ref_grad).max())
-    assert num / den < 1e-3
+    cos = float((got * ref_grad).sum() / np.sqrt((got ** 2).sum() * (ref_grad ** 2).sum()))
+    print(math_name, "grad rel l2", num / den, "cosine", cos, "max ref", np.abs(ref_grad).max())
+    if math_name == "fp32":
+        assert num / den < 1e-3
+    else:
+        assert cos > 0.99 and num / den < 0.2
     assert np.abs(d_l.cpu().numpy()[:, 0] - out["loss"].detach().numpy()).max() / np.abs(out["loss"].detach().numpy()).max() < 1e-3
     loss.close()
