@@ -12,65 +12,98 @@ static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 //   convT: dW[ky,kx,co,ci] = sum_{n,i,j}  x[n,i,j,ci] * g[n, i*s + ky - pt, j*s + kx - pl, co]         (base = input grid)
 // One CTA = one filter tap x 32 input channels x 32 output channels x a slab of base pixels.
 // ---------------------------------------------------------------------------------------------------------------
+// TM x TN = input-channel x output-channel tile of one tap; 16 x 16 threads, each a (TM/16) x (TN/16) register tile.
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci_blocks, int pix_per_split) {
-    __shared__ float As[32][33];      // [pixel][ci]
-    __shared__ float Gs[32][33];      // [pixel][co]
-    const int tap = blockIdx.x / ci_blocks, ci0 = (blockIdx.x % ci_blocks) * 32, c0 = blockIdx.y * 32;
+    constexpr int RM = TM / 16, RN = TN / 16, PIX = 32;
+    __shared__ __align__(16) float As[PIX][TM + 4];      // [pixel][ci]
+    __shared__ __align__(16) float Gs[PIX][TN + 4];      // [pixel][co]
+    const int tap = blockIdx.x / ci_blocks, ci0 = (blockIdx.x % ci_blocks) * TM, c0 = blockIdx.y * TN;
     const int ky = tap / p.kw, kx = tap - ky * p.kw;
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     const long long p0 = (long long)blockIdx.z * pix_per_split;
     const long long p1 = min(NP, p0 + pix_per_split);
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-    const int ci = ci0 + tx, co = c0 + tx;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long pp = p0; pp < p1; pp += 32) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[RM][RN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int pl_ = ty + 8 * i;
-            const long long pix = pp + pl_;
-            float a = 0.f, g = 0.f;
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+    __shared__ long long xoff[PIX], goff[PIX];            // element offset of each pixel's channel 0 in x / g, -1 = zero
+    for (long long pp = p0; pp < p1; pp += PIX) {
+        if (threadIdx.x < PIX) {
+            const long long pix = pp + threadIdx.x;
+            long long xo = -1, go = -1;
             if (pix < p1) {
                 const int bx = (int)(pix % p.Wb);
                 const long long t = pix / p.Wb;
-                const int by = (int)(t % p.Hb);
-                const int n = (int)(t / p.Hb);
+                const int by = (int)(t % p.Hb), n = (int)(t / p.Hb);
                 int xy = by, xx = bx, gy_ = by, gx_ = bx;
                 if (!p.transposed) { xy = by * p.stride - p.pad_t + ky; xx = bx * p.stride - p.pad_l + kx; }
                 else { gy_ = by * p.stride + ky - p.pad_t; gx_ = bx * p.stride + kx - p.pad_l; }
-                if (ci < p.Ci && xy >= 0 && xy < p.Hx && xx >= 0 && xx < p.Wx)
-                    a = fmaf(__ldg(p.x + (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci + ci), p.in_scale, p.in_shift);
-                if (co < p.Co && gy_ >= 0 && gy_ < p.Hg && gx_ >= 0 && gx_ < p.Wg)
-                    g = __ldg(p.g + (((long long)n * p.Hg + gy_) * p.Wg + gx_) * p.Co + co);
+                if (xy >= 0 && xy < p.Hx && xx >= 0 && xx < p.Wx) xo = (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci;
+                if (gy_ >= 0 && gy_ < p.Hg && gx_ >= 0 && gx_ < p.Wg) go = (((long long)n * p.Hg + gy_) * p.Wg + gx_) * p.Co;
             }
-            As[pl_][tx] = a;
-            Gs[pl_][tx] = g;
+            xoff[threadIdx.x] = xo; goff[threadIdx.x] = go;
         }
         __syncthreads();
+        // cooperative loads: consecutive threads read consecutive channels of one pixel (coalesced NHWC reads)
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            const float gv = Gs[q][tx];
+        for (int e = threadIdx.x; e < PIX * TM; e += 256) {
+            const int q = e / TM, c = e % TM;
+            const long long xo = xoff[q];
+            As[q][c] = (xo >= 0 && ci0 + c < p.Ci) ? fmaf(__ldg(p.x + xo + ci0 + c), p.in_scale, p.in_shift) : 0.f;
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fmaf(As[q][ty + 8 * i], gv, acc[i]);
+        for (int e = threadIdx.x; e < PIX * TN; e += 256) {
+            const int q = e / TN, c = e % TN;
+            const long long go = goff[q];
+            Gs[q][c] = (go >= 0 && c0 + c < p.Co) ? __ldg(p.g + go + c0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int q = 0; q < PIX; ++q) {
+            float a[RM], g[RN];
+            if (RM == 4) { const float4 t = *reinterpret_cast<const float4*>(&As[q][ty * 4]); a[0] = t.x; a[1] = t.y; a[RM - 2] = t.z; a[RM - 1] = t.w; }
+            else { const float2 t = *reinterpret_cast<const float2*>(&As[q][ty * 2]); a[0] = t.x; a[1] = t.y; }
+            if (RN == 4) { const float4 t = *reinterpret_cast<const float4*>(&Gs[q][tx * 4]); g[0] = t.x; g[1] = t.y; g[RN - 2] = t.z; g[RN - 1] = t.w; }
+            else { const float2 t = *reinterpret_cast<const float2*>(&Gs[q][tx * 2]); g[0] = t.x; g[1] = t.y; }
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], g[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int cin = ci0 + ty + 8 * i;
-        if (cin < p.Ci && co < p.Co) {
-            const long long idx = !p.transposed ? ((long long)tap * p.Ci + cin) * p.Co + co : ((long long)tap * p.Co + co) * p.Ci + cin;
-            atomicAdd(p.dw + idx, acc[i]);
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+            const int cin = ci0 + ty * RM + i, co = c0 + tx * RN + j;
+            if (cin < p.Ci && co < p.Co) {
+                const long long idx = !p.transposed ? ((long long)tap * p.Ci + cin) * p.Co + co : ((long long)tap * p.Co + co) * p.Ci + cin;
+                atomicAdd(p.dw + idx, acc[i][j]);
+            }
         }
-    }
 }
 
 cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     if (NP == 0) return cudaSuccess;
-    const int ci_blocks = ceil_div(p.Ci, 32);
-    const int pix_per_split = 2048;
-    dim3 grid((unsigned)(p.kh * p.kw * ci_blocks), (unsigned)ceil_div(p.Co, 32), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
-    wgrad_f32_kernel<<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    const bool wide_m = p.Ci > 32, wide_n = p.Co > 32;
+    const int tm = wide_m ? 64 : 32, tn = wide_n ? 64 : 32;
+    const int ci_blocks = ceil_div(p.Ci, tm);
+    // enough pixel slabs to fill the GPU a few times over, but long enough to amortise the atomics
+    const long long tiles = (long long)p.kh * p.kw * ci_blocks * ceil_div(p.Co, tn);
+    long long splits = (148LL * 8 + tiles - 1) / tiles;
+    int pix_per_split = (int)((NP + splits - 1) / splits);
+    pix_per_split = (pix_per_split + 31) / 32 * 32;
+    if (pix_per_split < 512) pix_per_split = 512;
+    dim3 grid((unsigned)(p.kh * p.kw * ci_blocks), (unsigned)ceil_div(p.Co, tn), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
+    if (wide_m && wide_n) wgrad_f32_kernel<64, 64><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    else if (wide_m) wgrad_f32_kernel<64, 32><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    else if (wide_n) wgrad_f32_kernel<32, 64><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    else wgrad_f32_kernel<32, 32><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
     return cudaGetLastError();
 }
 
