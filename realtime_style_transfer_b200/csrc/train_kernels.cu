@@ -13,13 +13,17 @@ static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 // One CTA = one filter tap x 32 input channels x 32 output channels x a slab of base pixels.
 // ---------------------------------------------------------------------------------------------------------------
 // TM x TN = input-channel x output-channel tile of one tap; 16 x 16 threads, each a (TM/16) x (TN/16) register tile.
-template <int TM, int TN>
+// ROWMODE (stride-1 Conv2D): the M dimension of a CTA is a block of (kx, ci) pairs of ONE filter row ky -- for a fixed output
+// pixel these kw*Ci inputs are contiguous in NHWC memory, so thin layers (17 input channels, 81 taps) fill the tile.
+template <int TM, int TN, bool ROWMODE>
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci_blocks, int pix_per_split) {
     constexpr int RM = TM / 16, RN = TN / 16, PIX = 32;
-    __shared__ __align__(16) float As[PIX][TM + 4];      // [pixel][ci]
+    __shared__ __align__(16) float As[PIX][TM + 4];      // [pixel][ci]  (ROWMODE: [pixel][kx*Ci + ci])
     __shared__ __align__(16) float Gs[PIX][TN + 4];      // [pixel][co]
+    __shared__ int xcol[PIX];                             // ROWMODE: input column of kx = 0
     const int tap = blockIdx.x / ci_blocks, ci0 = (blockIdx.x % ci_blocks) * TM, c0 = blockIdx.y * TN;
-    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+    const int ky = ROWMODE ? tap : tap / p.kw, kx = ROWMODE ? 0 : tap - ky * p.kw;
+    const int row_len = p.kw * p.Ci;                      // ROWMODE: M extent
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     const long long p0 = (long long)blockIdx.z * pix_per_split;
     const long long p1 = min(NP, p0 + pix_per_split);
@@ -41,7 +45,11 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
                 int xy = by, xx = bx, gy_ = by, gx_ = bx;
                 if (!p.transposed) { xy = by * p.stride - p.pad_t + ky; xx = bx * p.stride - p.pad_l + kx; }
                 else { gy_ = by * p.stride + ky - p.pad_t; gx_ = bx * p.stride + kx - p.pad_l; }
-                if (xy >= 0 && xy < p.Hx && xx >= 0 && xx < p.Wx) xo = (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci;
+                if (ROWMODE) {
+                    // offset of (row, column of kx = 0, channel 0); the column may lie left of the image, elements are checked
+                    if (xy >= 0 && xy < p.Hx) xo = (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci + (1LL << 40);
+                    xcol[threadIdx.x] = xx;
+                } else if (xy >= 0 && xy < p.Hx && xx >= 0 && xx < p.Wx) xo = (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci;
                 if (gy_ >= 0 && gy_ < p.Hg && gx_ >= 0 && gx_ < p.Wg) go = (((long long)n * p.Hg + gy_) * p.Wg + gx_) * p.Co;
             }
             xoff[threadIdx.x] = xo; goff[threadIdx.x] = go;
@@ -52,6 +60,11 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
         for (int e = threadIdx.x; e < PIX * TM; e += 256) {
             const int q = e / TM, c = e % TM;
             const long long xo = xoff[q];
+            if (ROWMODE) {
+                const int m = ci0 + c, col = xcol[q] + m / p.Ci;          // m / Ci is loop-invariant per thread (256 % TM == 0)
+                As[q][c] = (xo >= 0 && m < row_len && col >= 0 && col < p.Wx)
+                               ? fmaf(__ldg(p.x + (xo - (1LL << 40)) + m), p.in_scale, p.in_shift) : 0.f;
+            } else
             As[q][c] = (xo >= 0 && ci0 + c < p.Ci) ? fmaf(__ldg(p.x + xo + ci0 + c), p.in_scale, p.in_shift) : 0.f;
         }
 #pragma unroll
@@ -80,7 +93,9 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
 #pragma unroll
         for (int j = 0; j < RN; ++j) {
             const int cin = ci0 + ty * RM + i, co = c0 + tx * RN + j;
-            if (cin < p.Ci && co < p.Co) {
+            if (ROWMODE) {
+                if (cin < row_len && co < p.Co) atomicAdd(p.dw + ((long long)ky * row_len + cin) * p.Co + co, acc[i][j]);
+            } else if (cin < p.Ci && co < p.Co) {
                 const long long idx = !p.transposed ? ((long long)tap * p.Ci + cin) * p.Co + co : ((long long)tap * p.Co + co) * p.Ci + cin;
                 atomicAdd(p.dw + idx, acc[i][j]);
             }
@@ -90,20 +105,29 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
 cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     if (NP == 0) return cudaSuccess;
-    const bool wide_m = p.Ci > 32, wide_n = p.Co > 32;
+    const bool rowmode = !p.transposed && p.stride == 1;
+    const int m_extent = rowmode ? p.kw * p.Ci : p.Ci;
+    const bool wide_m = m_extent > 32, wide_n = p.Co > 32;
     const int tm = wide_m ? 64 : 32, tn = wide_n ? 64 : 32;
-    const int ci_blocks = ceil_div(p.Ci, tm);
+    const int ci_blocks = ceil_div(m_extent, tm);
+    const int groups = rowmode ? p.kh : p.kh * p.kw;
     // enough pixel slabs to fill the GPU a few times over, but long enough to amortise the atomics
-    const long long tiles = (long long)p.kh * p.kw * ci_blocks * ceil_div(p.Co, tn);
+    const long long tiles = (long long)groups * ci_blocks * ceil_div(p.Co, tn);
     long long splits = (148LL * 8 + tiles - 1) / tiles;
     int pix_per_split = (int)((NP + splits - 1) / splits);
     pix_per_split = (pix_per_split + 31) / 32 * 32;
     if (pix_per_split < 512) pix_per_split = 512;
-    dim3 grid((unsigned)(p.kh * p.kw * ci_blocks), (unsigned)ceil_div(p.Co, tn), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
-    if (wide_m && wide_n) wgrad_f32_kernel<64, 64><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
-    else if (wide_m) wgrad_f32_kernel<64, 32><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
-    else if (wide_n) wgrad_f32_kernel<32, 64><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
-    else wgrad_f32_kernel<32, 32><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    dim3 grid((unsigned)(groups * ci_blocks), (unsigned)ceil_div(p.Co, tn), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
+#define RST_WGRAD(TM_, TN_)                                                                                              \
+    do {                                                                                                                  \
+        if (rowmode) wgrad_f32_kernel<TM_, TN_, true><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                 \
+        else wgrad_f32_kernel<TM_, TN_, false><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                        \
+    } while (0)
+    if (wide_m && wide_n) RST_WGRAD(64, 64);
+    else if (wide_m) RST_WGRAD(64, 32);
+    else if (wide_n) RST_WGRAD(32, 64);
+    else RST_WGRAD(32, 32);
+#undef RST_WGRAD
     return cudaGetLastError();
 }
 
