@@ -13,17 +13,19 @@ static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 // One CTA = one filter tap x 32 input channels x 32 output channels x a slab of base pixels.
 // ---------------------------------------------------------------------------------------------------------------
 // TM x TN = input-channel x output-channel tile of one tap; 16 x 16 threads, each a (TM/16) x (TN/16) register tile.
-// ROWMODE (stride-1 Conv2D): the M dimension of a CTA is a block of (kx, ci) pairs of ONE filter row ky -- for a fixed output
+// RMODE 1 (stride-1 Conv2D): the M dimension of a CTA is a block of (kx, ci) pairs of ONE filter row ky -- for a fixed output
 // pixel these kw*Ci inputs are contiguous in NHWC memory, so thin layers (17 input channels, 81 taps) fill the tile.
-template <int TM, int TN, bool ROWMODE>
+// RMODE 2 (stride-1 Conv2DTranspose): the same on the gradient side, N = block of (kx, co) pairs (16 -> 3 head: 27 columns).
+template <int TM, int TN, int RMODE>
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci_blocks, int pix_per_split) {
     constexpr int RM = TM / 16, RN = TN / 16, PIX = 32;
     __shared__ __align__(16) float As[PIX][TM + 4];      // [pixel][ci]  (ROWMODE: [pixel][kx*Ci + ci])
     __shared__ __align__(16) float Gs[PIX][TN + 4];      // [pixel][co]
-    __shared__ int xcol[PIX];                             // ROWMODE: input column of kx = 0
+    constexpr bool ROWMODE = RMODE == 1, GROW = RMODE == 2;
+    __shared__ int xcol[PIX];                             // ROWMODE / GROW: column of kx = 0 in x / g
     const int tap = blockIdx.x / ci_blocks, ci0 = (blockIdx.x % ci_blocks) * TM, c0 = blockIdx.y * TN;
-    const int ky = ROWMODE ? tap : tap / p.kw, kx = ROWMODE ? 0 : tap - ky * p.kw;
-    const int row_len = p.kw * p.Ci;                      // ROWMODE: M extent
+    const int ky = (ROWMODE || GROW) ? tap : tap / p.kw, kx = (ROWMODE || GROW) ? 0 : tap - ky * p.kw;
+    const int row_len = p.kw * (GROW ? p.Co : p.Ci);      // ROWMODE: M extent, GROW: N extent
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     const long long p0 = (long long)blockIdx.z * pix_per_split;
     const long long p1 = min(NP, p0 + pix_per_split);
@@ -50,6 +52,10 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
                     if (xy >= 0 && xy < p.Hx) xo = (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci + (1LL << 40);
                     xcol[threadIdx.x] = xx;
                 } else if (xy >= 0 && xy < p.Hx && xx >= 0 && xx < p.Wx) xo = (((long long)n * p.Hx + xy) * p.Wx + xx) * p.Ci;
+                if (GROW) {
+                    if (gy_ >= 0 && gy_ < p.Hg) go = (((long long)n * p.Hg + gy_) * p.Wg + gx_) * p.Co + (1LL << 40);
+                    xcol[threadIdx.x] = gx_;
+                } else
                 if (gy_ >= 0 && gy_ < p.Hg && gx_ >= 0 && gx_ < p.Wg) go = (((long long)n * p.Hg + gy_) * p.Wg + gx_) * p.Co;
             }
             xoff[threadIdx.x] = xo; goff[threadIdx.x] = go;
@@ -71,6 +77,10 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
         for (int e = threadIdx.x; e < PIX * TN; e += 256) {
             const int q = e / TN, c = e % TN;
             const long long go = goff[q];
+            if (GROW) {
+                const int nn = c0 + c, col = xcol[q] + nn / p.Co;
+                Gs[q][c] = (go >= 0 && nn < row_len && col >= 0 && col < p.Wg) ? __ldg(p.g + (go - (1LL << 40)) + nn) : 0.f;
+            } else
             Gs[q][c] = (go >= 0 && c0 + c < p.Co) ? __ldg(p.g + go + c0 + c) : 0.f;
         }
         __syncthreads();
@@ -95,6 +105,8 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
             const int cin = ci0 + ty * RM + i, co = c0 + tx * RN + j;
             if (ROWMODE) {
                 if (cin < row_len && co < p.Co) atomicAdd(p.dw + ((long long)ky * row_len + cin) * p.Co + co, acc[i][j]);
+            } else if (GROW) {
+                if (cin < p.Ci && co < row_len) atomicAdd(p.dw + ((long long)ky * row_len + co) * p.Ci + cin, acc[i][j]);
             } else if (cin < p.Ci && co < p.Co) {
                 const long long idx = !p.transposed ? ((long long)tap * p.Ci + cin) * p.Co + co : ((long long)tap * p.Co + co) * p.Ci + cin;
                 atomicAdd(p.dw + idx, acc[i][j]);
@@ -105,23 +117,24 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
 cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     if (NP == 0) return cudaSuccess;
-    const bool rowmode = !p.transposed && p.stride == 1;
-    const int m_extent = rowmode ? p.kw * p.Ci : p.Ci;
-    const bool wide_m = m_extent > 32, wide_n = p.Co > 32;
+    const int rmode = p.stride != 1 ? 0 : (p.transposed ? 2 : 1);
+    const int m_extent = rmode == 1 ? p.kw * p.Ci : p.Ci, n_extent = rmode == 2 ? p.kw * p.Co : p.Co;
+    const bool wide_m = m_extent > 32, wide_n = n_extent > 32;
     const int tm = wide_m ? 64 : 32, tn = wide_n ? 64 : 32;
     const int ci_blocks = ceil_div(m_extent, tm);
-    const int groups = rowmode ? p.kh : p.kh * p.kw;
+    const int groups = rmode ? p.kh : p.kh * p.kw;
     // enough pixel slabs to fill the GPU a few times over, but long enough to amortise the atomics
-    const long long tiles = (long long)groups * ci_blocks * ceil_div(p.Co, tn);
+    const long long tiles = (long long)groups * ci_blocks * ceil_div(n_extent, tn);
     long long splits = (148LL * 8 + tiles - 1) / tiles;
     int pix_per_split = (int)((NP + splits - 1) / splits);
     pix_per_split = (pix_per_split + 31) / 32 * 32;
     if (pix_per_split < 512) pix_per_split = 512;
-    dim3 grid((unsigned)(groups * ci_blocks), (unsigned)ceil_div(p.Co, tn), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
+    dim3 grid((unsigned)(groups * ci_blocks), (unsigned)ceil_div(n_extent, tn), (unsigned)((NP + pix_per_split - 1) / pix_per_split));
 #define RST_WGRAD(TM_, TN_)                                                                                              \
     do {                                                                                                                  \
-        if (rowmode) wgrad_f32_kernel<TM_, TN_, true><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                 \
-        else wgrad_f32_kernel<TM_, TN_, false><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                        \
+        if (rmode == 1) wgrad_f32_kernel<TM_, TN_, 1><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                 \
+        else if (rmode == 2) wgrad_f32_kernel<TM_, TN_, 2><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);            \
+        else wgrad_f32_kernel<TM_, TN_, 0><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                            \
     } while (0)
     if (wide_m && wide_n) RST_WGRAD(64, 64);
     else if (wide_m) RST_WGRAD(64, 32);
