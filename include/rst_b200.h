@@ -177,6 +177,11 @@ int rst_train_destroy(rst_trainer* trainer);
 const char* rst_train_last_error(const rst_trainer* trainer);
 /* The trainer's model / loss contexts: set variables with rst_set_weight + rst_commit_weights and rst_loss_set_weight +
  * rst_loss_commit before the first step.  The model context also serves rst_transfer_forward / rst_predict_style. */
+/* Arithmetic of the step.  RST_PRECISION_FP32 (default): fp32 transfer network and predictor; the loss model keeps its own
+ * setting (rst_loss_set_math, tf32 by default).  RST_PRECISION_TF32: additionally runs the 3x3 convolutions of the residual
+ * trunk (forward and input gradient) on the tensor cores with tf32 operands -- TensorFlow's behaviour for float32 models on
+ * Ampere and later -- and sets the loss model to tf32.  Call before rst_commit_weights / rst_loss_commit. */
+int rst_train_set_math(rst_trainer* trainer, int precision);
 rst_ctx* rst_train_model(rst_trainer* trainer);
 rst_loss* rst_train_loss(rst_trainer* trainer);
 /* One forward + backward of Model.train_step: y_pred = model(x, training=True) [BatchNorm on batch statistics,

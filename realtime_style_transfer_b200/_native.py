@@ -85,6 +85,7 @@ SIGNATURES = {
     "rst_train_create": (C.c_int, [C.POINTER(RstConfig), C.c_int, C.POINTER(_vp)]),
     "rst_train_destroy": (C.c_int, [_vp]),
     "rst_train_last_error": (C.c_char_p, [_vp]),
+    "rst_train_set_math": (C.c_int, [_vp, C.c_int]),
     "rst_train_model": (_vp, [_vp]),
     "rst_train_loss": (_vp, [_vp]),
     "rst_train_forward_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
@@ -415,6 +416,10 @@ class NativeTrainer:
             self.close()
         except Exception:
             pass
+
+    def set_math(self, precision: int):
+        """PRECISION_TF32: tf32 tensor cores for the residual trunk and the loss model; call before the weights are set."""
+        self._check(self.lib.rst_train_set_math(self.handle, int(precision)))
 
     def forward_backward(self, d_content: int, d_style: int, d_gt_content: int, d_gt_style: int, d_losses: int, batch: int):
         self._check(self.lib.rst_train_forward_backward(self.handle, _vp(d_content), _vp(d_style), _vp(d_gt_content),

@@ -7,22 +7,34 @@
 
 namespace rst {
 
-static float to_tf32(float x) {                      // round to nearest, ties away from zero (cvt.rna.tf32.f32)
-    uint32_t u;
-    std::memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;
-    u &= 0xffffe000u;
-    std::memcpy(&x, &u, 4);
-    return x;
-}
-
 Tf32Conv3x3::~Tf32Conv3x3() {
     if (w_packed) cudaFree(w_packed);
     if (bias) cudaFree(bias);
 }
 
-bool Tf32Conv3x3::setup(int ci_layer, int co_layer, const float* k, const float* bias_host, bool relu_, bool input_gradient,
-                        std::string* err) {
+// packed[j][blk][n][r]: K-step ks = 4*blk + r/8, element e = r%8 -> channel group g = ks/36, tap = (ks%36)/4,
+// input channel g*32 + ((ks%36)%4)*8 + e; output channel j*nb + n.  Rounded to tf32 (nearest).
+__global__ void tf32_pack_weights_kernel(const float* __restrict__ k, float* __restrict__ out, int ci_layer, int co_layer,
+                                         int input_gradient, int nb, int blocks, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int r = (int)(idx % 32);
+    long long t = idx / 32;
+    const int n = (int)(t % nb);
+    t /= nb;
+    const int blk = (int)(t % blocks), j = (int)(t / blocks);
+    const int ks = blk * 4 + r / 8, e = r % 8;
+    const int g = ks / 36, l = ks % 36, tap = l / 4;
+    const int cin = g * 32 + (l % 4) * 8 + e, cout = j * nb + n;
+    const float w = !input_gradient ? k[((size_t)tap * ci_layer + cin) * co_layer + cout]
+                                    : k[((size_t)(8 - tap) * ci_layer + cout) * co_layer + cin];
+    uint32_t rr;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(w));
+    out[idx] = __uint_as_float(rr);
+}
+
+bool Tf32Conv3x3::setup_shape(int ci_layer_, int co_layer_, bool relu_, bool input_gradient_, std::string* err) {
+    ci_layer = ci_layer_; co_layer = co_layer_; input_gradient = input_gradient_;
     ci = input_gradient ? co_layer : ci_layer;
     co = input_gradient ? ci_layer : co_layer;
     relu = relu_;
@@ -32,27 +44,11 @@ bool Tf32Conv3x3::setup(int ci_layer, int co_layer, const float* k, const float*
     }
     nb = co % 128 == 0 ? 128 : 64;
     nblk = co / nb;
-    const int n_groups = ci / 32, ksteps = 36, total_ksteps = n_groups * ksteps, blocks = total_ksteps / 4;
-    std::vector<float> packed((size_t)nblk * blocks * nb * 32, 0.f);
-    for (int j = 0; j < nblk; ++j)
-        for (int ks = 0; ks < total_ksteps; ++ks) {
-            const int g = ks / ksteps, l = ks % ksteps, tap = l / 4;
-            for (int n = 0; n < nb; ++n)
-                for (int e = 0; e < 8; ++e) {
-                    const int cin = g * 32 + (l % 4) * 8 + e, cout = j * nb + n;
-                    const float w = !input_gradient ? k[((size_t)tap * ci_layer + cin) * co_layer + cout]
-                                                    : k[((size_t)(8 - tap) * ci_layer + cout) * co_layer + cin];
-                    packed[(((size_t)j * blocks + ks / 4) * nb + n) * 32 + (ks % 4) * 8 + e] = to_tf32(w);
-                }
-        }
+    const int n_groups = ci / 32, blocks = n_groups * 9;
     if (w_packed) { cudaFree(w_packed); w_packed = nullptr; }
     if (bias) { cudaFree(bias); bias = nullptr; }
-    cudaError_t e = cudaMalloc(&w_packed, packed.size() * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpy(w_packed, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && bias_host) {
-        e = cudaMalloc(&bias, co * sizeof(float));
-        if (e == cudaSuccess) e = cudaMemcpy(bias, bias_host, co * sizeof(float), cudaMemcpyHostToDevice);
-    }
+    ext_bias = nullptr;
+    cudaError_t e = cudaMalloc(&w_packed, (size_t)nblk * blocks * nb * 32 * sizeof(float));
     if (e != cudaSuccess) {
         if (err) *err = std::string("tf32 conv: ") + cudaGetErrorString(e);
         return false;
@@ -68,6 +64,36 @@ bool Tf32Conv3x3::setup(int ci_layer, int co_layer, const float* k, const float*
     for (int j = 0; j < nblk; ++j)
         if (!encode_weight_map(&tmB[j], w_packed + (size_t)j * blocks * nb * 32, blocks, nb, err)) return false;
     inputs.clear();
+    return true;
+}
+
+cudaError_t Tf32Conv3x3::repack(const float* d_kernel, const float* d_bias, cudaStream_t s) {
+    const int blocks = (ci / 32) * 9;
+    const long long total = (long long)nblk * blocks * nb * 32;
+    tf32_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_kernel, w_packed, ci_layer, co_layer,
+                                                                            input_gradient ? 1 : 0, nb, blocks, total);
+    ext_bias = d_bias;
+    return cudaGetLastError();
+}
+
+bool Tf32Conv3x3::setup(int ci_layer_, int co_layer_, const float* k, const float* bias_host, bool relu_, bool input_gradient_,
+                        std::string* err) {
+    if (!setup_shape(ci_layer_, co_layer_, relu_, input_gradient_, err)) return false;
+    float* d_k = nullptr;
+    const size_t kelems = (size_t)9 * ci_layer_ * co_layer_;
+    cudaError_t e = cudaMalloc(&d_k, kelems * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_k, k, kelems * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && bias_host) {
+        e = cudaMalloc(&bias, co * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(bias, bias_host, co * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = repack(d_k, bias, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (d_k) cudaFree(d_k);
+    if (e != cudaSuccess) {
+        if (err) *err = std::string("tf32 conv: ") + cudaGetErrorString(e);
+        return false;
+    }
     return true;
 }
 
@@ -90,7 +116,7 @@ cudaError_t Tf32Conv3x3::run(const float* x, float* y, int B, int H, int W, int 
     q.y_f32 = 1; q.stats = nullptr;
     for (int j = 0; j < nblk; ++j) {
         q.y = y + (size_t)j * nb;
-        q.bias = bias ? bias + (size_t)j * nb : nullptr;
+        q.bias = ext_bias ? ext_bias + (size_t)j * nb : nullptr;
         cudaError_t e = launch_halo_gemm(launch, *tmA, tmB[j], q, num_sms, s);
         if (e != cudaSuccess) return e;
     }

@@ -148,7 +148,10 @@ struct Tf32Conv3x3 {
     int ci = 0, co = 0, nb = 128, nblk = 0;
     bool relu = false;
     float* w_packed = nullptr;          // [nblk][n_groups * 9 blocks][nb rows][32 floats]
-    float* bias = nullptr;              // [co] or null
+    float* bias = nullptr;              // [co] or null (owned copy made by setup)
+    const float* ext_bias = nullptr;    // or a caller-owned device vector (set by repack)
+    int ci_layer = 0, co_layer = 0;
+    bool input_gradient = false;
     HaloGemmLaunch launch;
     HaloGemmParams p;
     std::vector<CUtensorMap> tmB;       // one weight map per block of nb output channels
@@ -161,6 +164,10 @@ struct Tf32Conv3x3 {
     // k: Keras kernel (3,3,ci_layer,co_layer).  input_gradient = false: y = [relu](conv(x, k) + bias), ci = ci_layer.
     // input_gradient = true: y = d conv / d input applied to x = gradient w.r.t. the layer output (ci = co_layer, co = ci_layer).
     bool setup(int ci_layer, int co_layer, const float* k, const float* bias_host, bool relu, bool input_gradient, std::string* err);
+    // Same without weights: allocate and plan only; repack() then (re)builds the packed tf32 weights from a DEVICE kernel
+    // tensor (3,3,ci_layer,co_layer), e.g. once per training step after the optimizer moved the variables.
+    bool setup_shape(int ci_layer, int co_layer, bool relu, bool input_gradient, std::string* err);
+    cudaError_t repack(const float* d_kernel, const float* d_bias, cudaStream_t s);
     cudaError_t run(const float* x, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
 };
 

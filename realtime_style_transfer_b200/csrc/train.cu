@@ -12,6 +12,8 @@
 
 #include "rst_ctx.h"
 #include "train_kernels.cuh"
+#include "halo_gemm.cuh"
+#include <memory>
 
 using namespace rst;
 
@@ -54,7 +56,25 @@ struct rst_trainer {
     Tensor* pred = nullptr;
     Tensor* style_params = nullptr;
     int rc = RST_OK;                      // sticky error of the op being recorded
+    // optional tf32 tensor-core path for the 3x3 stride-1 convolutions of the transfer network (Cin % 32 == 0, Cout % 64 == 0:
+    // the residual trunk), forward and input gradient; weights are re-packed from the live variables every step
+    int math = RST_PRECISION_FP32;
+    int num_sms = 148;
+    std::map<std::string, std::unique_ptr<Tf32Conv3x3>> tf32_fwd, tf32_bwd;
 };
+
+static Tf32Conv3x3* tf32_conv(rst_trainer* t, std::map<std::string, std::unique_ptr<Tf32Conv3x3>>& cache, const std::string& name,
+                              int ci, int co, bool relu, bool input_gradient) {
+    auto it = cache.find(name);
+    if (it != cache.end()) return it->second.get();
+    std::unique_ptr<Tf32Conv3x3> c(new Tf32Conv3x3());
+    std::string err;
+    if (!c->setup_shape(ci, co, relu, input_gradient, &err)) {
+        if (t->rc == RST_OK) t->rc = RST_ERR_CUDA, t->err = "training tf32 conv " + name + ": " + err;
+        return nullptr;
+    }
+    return (cache[name] = std::move(c)).get();
+}
 
 static thread_local std::string g_train_create_error;
 
@@ -158,8 +178,19 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
     if (!cs.transposed) { p.w_ci = co; p.w_co = 1; } else { p.w_ci = 1; p.w_co = ci; }
     p.in_scale = cs.in_scale; p.in_shift = cs.in_shift;
     p.act1 = cs.act;
-    OPCUDA(t, launch_conv_f32(p, t->s));
-    t->m->launches += 1;
+    const bool tensor_core = t->math == RST_PRECISION_TF32 && !cs.transposed && cs.k == 3 && cs.stride == 1 && ci % 32 == 0 &&
+                             co % 64 == 0 && (cs.act == ACT_RELU || cs.act == ACT_NONE) && cs.in_scale == 1.f && cs.in_shift == 0.f;
+    Tf32Conv3x3* fwd = tensor_core ? tf32_conv(t, t->tf32_fwd, kname, ci, co, cs.act == ACT_RELU, false) : nullptr;
+    if (fwd) {
+        std::string err;
+        OPCUDA(t, fwd->repack(vk->w, vb ? vb->w : nullptr, t->s));
+        OPCUDA(t, fwd->run(x->d, y->d, x->B, x->H, x->W, t->num_sms, t->s, &err));
+        t->m->launches += 1 + fwd->nblk;
+    } else {
+        OPCUDA(t, launch_conv_f32(p, t->s));
+        t->m->launches += 1;
+    }
+    float* dgrad_tmp = (tensor_core && x->needs_grad) ? falloc(t, x->n()) : nullptr;
     double* st = dalloc(t, (long long)x->B * co * 2);
     double* st2 = dalloc(t, (long long)co * 2);
     const ConvSpec spec = cs;
@@ -176,7 +207,16 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
         TCUDA(t, launch_wgrad_f32(wg, t->s));
         t->m->launches += 2;
         if (vb) { int rc = bias_grad(t, y->g, y->B, y->P(), co, vb->g, st, st2); if (rc) return rc; }
-        if (x->needs_grad) {
+        Tf32Conv3x3* bwd = (tensor_core && x->needs_grad) ? tf32_conv(t, t->tf32_bwd, kname, ci, co, false, true) : nullptr;
+        if (bwd) {
+            std::string err;
+            float* dst = x->g_init ? dgrad_tmp : x->g;
+            TCUDA(t, bwd->repack(vk->w, nullptr, t->s));
+            TCUDA(t, bwd->run(y->g, dst, x->B, x->H, x->W, t->num_sms, t->s, &err));
+            if (x->g_init) TCUDA(t, launch_add_inplace(x->g, dgrad_tmp, x->n(), t->s));
+            t->m->launches += 2 + bwd->nblk;
+            x->g_init = true;
+        } else if (x->needs_grad) {
             ConvF32 q;     // input gradient: the adjoint map with the channel roles of the same kernel swapped
             q.x = y->g; q.y = x->g; q.w = vk->w;
             q.B = x->B; q.Hi = ho; q.Wi = wo; q.Ci = co; q.Ho = x->H; q.Wo = x->W; q.Co = ci;
@@ -473,6 +513,7 @@ extern "C" int rst_train_create(const rst_config* cfg, int device, rst_trainer**
     rc = rst_loss_create(cfg->out_h, cfg->out_w, cfg->max_batch, device, &t->loss);
     if (rc != RST_OK) { g_train_create_error = rst_loss_last_error(nullptr); rst_train_destroy(t); return rc; }
     cudaSetDevice(device);
+    cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, device);
     // one arena for every variable: trainable ones first, so that gradients / RMSprop slots are flat arrays of the same layout
     auto padded = [](int64_t n) { return (n + 63) / 64 * 64; };
     auto trainable = [](const std::string& n) {
@@ -501,6 +542,16 @@ extern "C" int rst_train_create(const rst_config* cfg, int device, rst_trainer**
     }
     *out = t;
     return RST_OK;
+}
+
+// RST_PRECISION_FP32 (default) or RST_PRECISION_TF32: tensor-core tf32 arithmetic for the loss model (rst_loss_set_math) AND for
+// the 3x3 convolutions of the transfer network's residual trunk, forward and input gradient (weight gradients stay fp32).
+extern "C" int rst_train_set_math(rst_trainer* t, int precision) {
+    if (!t) return RST_ERR_INVALID;
+    if (precision != RST_PRECISION_FP32 && precision != RST_PRECISION_TF32)
+        return tfail(t, RST_ERR_INVALID, "rst_train_set_math: RST_PRECISION_FP32 or RST_PRECISION_TF32");
+    t->math = precision;
+    return rst_loss_set_math(t->loss, precision);
 }
 
 extern "C" rst_ctx* rst_train_model(rst_trainer* t) { return t ? t->m : nullptr; }

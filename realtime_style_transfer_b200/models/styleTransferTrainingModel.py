@@ -55,11 +55,14 @@ class StyleTransferTrainingModel(NativeModel):
         self._host_stale = False
         self._grad_tensor = None
         self._mirrored = None       # variable versions of the sub-models the trainer's device copy corresponds to
+        # _native.PRECISION_TF32 runs the residual trunk's convolutions and the loss model on the tensor cores with tf32
+        # operands (TensorFlow's behaviour for float32 models on Ampere and later); the default keeps the networks in fp32
+        self.math = _native.PRECISION_FP32
 
     def _versions(self):
         inf = self.inference_model
         return (inf.transfer._version, inf.style_predictor._version, id(self.loss_model), getattr(self.loss_model, "_version", 0),
-                getattr(self.loss_model, "math", None))
+                getattr(self.loss_model, "math", None), self.math)
 
     # -- variables live in the inference model's two sub-models ---------------------------------------------------
     def _all_variables(self):
@@ -127,7 +130,10 @@ class StyleTransferTrainingModel(NativeModel):
             # The RMSprop accumulators are kept, as tf.keras keeps its slots when variables are assigned.
             self._trainer.model.set_weights(self._all_variables(), commit=True)
             lm = self.loss_model
-            self._trainer.loss.set_math(getattr(lm, "math", _native.PRECISION_TF32))
+            if self.math == _native.PRECISION_TF32:
+                self._trainer.set_math(_native.PRECISION_TF32)
+            else:
+                self._trainer.loss.set_math(getattr(lm, "math", _native.PRECISION_TF32))
             self._trainer.loss.set_weights(lm.weights)
             self._trainer.loss.set_factors(lm.content_loss_factor, lm.style_loss_factor, lm.total_variation_loss_factor)
             self._mirrored = self._versions()

@@ -267,3 +267,41 @@ def test_data_parallel_two_gpus(cuda_device):
                          capture_output=True, text=True, timeout=600, cwd=root)
     print(out.stdout[-2000:], out.stderr[-2000:])
     assert out.returncode == 0 and "DP_TRAIN_OK 2" in out.stdout
+
+
+def test_training_step_tf32_trunk(cuda_device):
+    """rst_train_set_math(TF32): the residual trunk's 3x3 convolutions (forward and input gradient) and the loss model run on
+    the tensor cores with tf32 operands.  Bars against the EXACT fp64 model: prediction 5e-3, losses 2e-3 (the 1e-3 bar of the
+    loss model plus the tf32 prediction), whole-gradient cosine 0.98 (see tests/test_gpu_loss.py for why not tighter); the
+    optimisation still makes progress."""
+    batch, filters = 2, 64
+    spec = O.TransferSpec(IN_SHAPE, OUT_SHAPE, RES_Y, filters, 1)
+    tw = O.init_transfer_weights(spec, seed=11, trained_like=True)
+    pw = O.init_predictor_weights("DUMMY", spec.num_style_parameters, seed=12)
+    vgg = O.init_vgg16_weights(seed=3)
+    rng = np.random.default_rng(3)
+    content = rng.uniform(0, 1, (batch,) + IN_SHAPE).astype(np.float32)
+    style = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+    gt = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+    ref_losses, ref_grads, ref_pred = O.training_forward_backward(spec, tw, "DUMMY", pw, vgg, content, style, gt)
+    tr = _native.NativeTrainer(in_shape=IN_SHAPE, out_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=filters,
+                               max_batch=batch, extractor=_native.EXTRACTOR_DUMMY, style_shape=OUT_SHAPE[:2])
+    tr.set_math(_native.PRECISION_TF32)
+    tr.model.set_weights({**tw, **pw})
+    tr.loss.set_weights(vgg)
+    losses = _step(tr, cuda_device, content, style, gt)
+    launches_tf32 = tr.lib.rst_last_launch_count(tr.model.handle)
+    err = np.abs(tr.read_prediction(batch) - ref_pred.numpy()).max()
+    rel = np.abs(losses[:, 0] - ref_losses["loss"].numpy()).max() / np.abs(ref_losses["loss"].numpy()).max()
+    flat_got = np.concatenate([tr.read_gradient(n, tuple(g.shape)).ravel() for n, g in ref_grads.items()])
+    flat_ref = np.concatenate([g.numpy().ravel() for g in ref_grads.values()])
+    cos = float((flat_got * flat_ref).sum() / np.sqrt((flat_got ** 2).sum() * (flat_ref ** 2).sum()))
+    print("tf32 trunk: prediction max abs err", err, "loss rel", rel, "gradient cosine", cos, "launches", launches_tf32)
+    assert err < 5e-3 and rel < 2e-3 and cos > 0.98
+    history = [float(losses[:, 0].sum())]
+    for _ in range(6):
+        tr.apply_gradients()
+        history.append(float(_step(tr, cuda_device, content, style, gt)[:, 0].sum()))
+    print(history)
+    assert history[-1] < history[0]
+    tr.close()
