@@ -307,9 +307,9 @@ def main():
                     "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16_tflops"],
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                    # (profiles/r01_ncu_full_halo_gemm2_raw_subset.csv: 60.2 MB read + 10.7..13.8 MB written); algorithmic
+                    # (profiles/r01_ncu_full_final_raw_subset.csv: 61.3 MB read + 19.5..21.4 MB written); algorithmic
                     # in+out is 118 MB, most of the output stays in the 126 MB L2 for the norm pass that follows
-                    "traffic": 72.4e6, "peak_source": pk["source"] + ", burst figure (kernel timed alone between events)",
+                    "traffic": 81.8e6, "peak_source": pk["source"] + ", burst figure (kernel timed alone between events)",
                     "avg_launch_ms": g_ms / g_n, "launches": g_n, "share_of_step": shares.get("conv3x3_umma")}
         whole = {"achieved_tflops": fps * GFLOP_PER_FRAME / 1e3 / world, "peak": pk["bf16_tflops_sustained"],
                  "frac_of_sustained_bf16": fps * GFLOP_PER_FRAME / 1e3 / world / pk["bf16_tflops_sustained"]}
