@@ -607,7 +607,7 @@ cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long
 
 // One thread per (pixel, 8-element slot group of the packed row).
 __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C,
-                                       int n_real, int row_elems, long long total_slots) {
+                                       int n_real, int row_elems, int pair_window, long long total_slots) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_slots) return;
     const int slots = row_elems / 8;
@@ -627,7 +627,8 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
         } else {
             const int g = (e - real_elems) / 16, t = (e - real_elems) % 16;   // virtual group g, horizontal tap t
             const int ch = n_real + g;
-            if (ch < C && t < 9) {
+            const int taps = pair_window ? ((px & 1) ? 0 : 10) : 9;
+            if (ch < C && t < taps) {
                 const int sx = px + t - 4;
                 if (sx >= 0 && sx < W) val = xp[(long long)(t - 4) * C + ch];
             }
@@ -643,7 +644,7 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
 // Fast path for the G-buffer layouts (16 real channels + NV windowed ones, W % 64 == 0): one warp per 64-pixel row segment.
 // The segment plus a 4-pixel halo on each side is 72*C floats = 18*C aligned float4 (coalesced loads) staged in the warp's
 // own shared-memory slice; each lane then assembles two packed pixels (stride-C reads are bank-conflict free for C = 17).
-template <int NV>
+template <int NV, bool PAIRW>
 __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
                                                              long long total_segments) {
     constexpr int C = 16 + NV, ROW = NV <= 1 ? 32 : 64, NF4 = 18 * C;
@@ -682,6 +683,12 @@ __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __rest
 #pragma unroll
             for (int t = 0; t < 9; ++t) v[t] = sf[(pl + t) * C + 16 + g];        // channel 16+g at x + t - 4
             v[9] = 0.f;
+            if (PAIRW) {                              // window shared by the pixel pair: 10 values in the even pixel, none in the odd
+                const float keep = (pl & 1) ? 0.f : 1.f;                         // branch-free: lanes alternate even / odd pixels
+                v[9] = sf[min(pl + 9, 71) * C + 16 + g];                         // even pl <= 62 stays inside the 72-pixel slice
+#pragma unroll
+                for (int t = 0; t < 10; ++t) v[t] *= keep;
+            }
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
@@ -715,20 +722,22 @@ __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __rest
 }
 
 cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
-                                   cudaStream_t s) {
+                                   int pair_window, cudaStream_t s) {
     long long total = (long long)B * H * W * (row_elems / 8);
     if (total == 0) return cudaSuccess;
     const int nv = C - 16;
+    if (pair_window && (nv != 1 || n_real != 16 || (W & 1))) return cudaErrorInvalidValue;
     if (n_real == 16 && (nv == 1 || nv == 2) && W % 64 == 0 && row_elems == (nv <= 1 ? 32 : 64) &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         const long long segments = (long long)B * H * (W / 64);
         const unsigned blocks = (unsigned)((segments + 7) / 8);
         const size_t smem = (size_t)8 * 18 * C * sizeof(float4);
-        if (nv == 1) pack_stem_rows_kernel<1><<<blocks, 256, smem, s>>>(x, y, W, segments);
-        else pack_stem_rows_kernel<2><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        if (nv == 1 && pair_window) pack_stem_rows_kernel<1, true><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        else if (nv == 1) pack_stem_rows_kernel<1, false><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        else pack_stem_rows_kernel<2, false><<<blocks, 256, smem, s>>>(x, y, W, segments);
         return cudaGetLastError();
     }
-    pack_stem_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, total);
+    pack_stem_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, pair_window, total);
     return cudaGetLastError();
 }
 

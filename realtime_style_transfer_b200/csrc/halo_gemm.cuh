@@ -45,17 +45,19 @@ enum HaloEpi : int {
 //          N = 2 x 32 output columns, 10 window pixels per row tap.  The block-Toeplitz weight matrix is never
 //          materialised: B is stored as 32-row "units" [0, W(ky,8), ..., W(ky,0), 0] per row tap and every K-step reads
 //          TWO ADJACENT units through a shifted SWIZZLE_32B descriptor (the halo trick applied to the weights).
+//          The 17th channel is stored ONCE per pair, as the 10-wide window x0-4 .. x0+5 in the even pixel's spare slots:
+//          one K-step per row tap serves both pixels (units [Wa, Wb] = the 9 taps at slot offsets 0 and 1): 90 + 9 K-steps.
 enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM2 = 4, SCH_STEM = 10 };
 __host__ __device__ constexpr bool sched_b_units(int sch) { return sch == SCH_STEM2; }
-constexpr int kStem2Units = 9 * 11 + 9 * 3;          // 126 units of 32 rows x 32 bytes
+constexpr int kStem2Units = 9 * 11 + 9 * 2 + 2;      // 99 real + 18 window units + 2 zero units (padding K-step)
 constexpr int kStem2Boxes = (kStem2Units * 32 + 255) / 256;   // TMA boxes of 256 rows (8 KB)
 // unit index (1 KB each) where K-step ks of SCH_STEM2 starts reading its 64 B rows
 __host__ __device__ constexpr int sched_b_unit(int sch, int ks) {
-    return sch != SCH_STEM2 ? 0 : ks < 90 ? (ks / 10) * 11 + (9 - ks % 10) : 99 + ((ks - 90) / 2) * 3 + (1 - (ks - 90) % 2);
+    return sch != SCH_STEM2 ? 0 : ks < 90 ? (ks / 10) * 11 + (9 - ks % 10) : 99 + (ks - 90) * 2;
 }
 __host__ __device__ constexpr int sched_real_ksteps(int sch, int rowb) {
     return sch == SCH_C3 ? 9 * (rowb / 32) : sch == SCH_T2 ? 4 * (rowb / 32) : sch == SCH_HEAD ? 108
-           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 108
+           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 99
            : 81 * ((sch - SCH_STEM) / 4) + 9 * ((sch - SCH_STEM) % 4);
 }
 __host__ __device__ constexpr int sched_ksteps(int sch, int rowb) { return (sched_real_ksteps(sch, rowb) + 3) / 4 * 4; }
@@ -71,8 +73,8 @@ __host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
     if (sch == SCH_HEAD) { const int dy = ks / 12, kx = ks % 12; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
     if (sch == SCH_STEM2) {
         if (ks < 90) { const int ky = ks / 10, kxp = ks % 10; return ((kxp / 2) * 16 + ky) * 128 + (kxp % 2) * 64; }
-        const int ky = (ks - 90) / 2, j = (ks - 90) % 2;
-        return (2 * 16 + ky) * 128 + j * 64 + 32;
+        const int ky = ks - 90;
+        return (2 * 16 + ky) * 128 + 32;                 // window slots of the pair's even pixel
     }
     if (sch == SCH_S2D) {
         // per row tap: kper slices at w2+0 (column taps 0,1) then kper/2 slices at w2+1 (column tap 2)
@@ -177,8 +179,10 @@ cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long
 
 // Stem input packing: fp32 NHWC (C channels) -> bf16 rows of `row_elems`: [n_real real channels, zero padded to
 // 16 when n_real > 0][one 16-slot group per remaining channel c: x[y, x-4 .. x+4, c] then 7 zeros].
+// pair_window (SCH_STEM2, one windowed channel, even W): the group of an EVEN pixel holds x[y, x-4 .. x+5, c] (10 values, shared
+// by the pixel pair), the group of an odd pixel is zero.
 cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
-                                   cudaStream_t s);
+                                   int pair_window, cudaStream_t s);
 
 // instance-norm apply: y = act(bias + (x-mean)*inv*scale) [+ residual]; x bf16 or fp32, y bf16 or fp32, C % vec == 0
 struct CinApplyV {

@@ -171,8 +171,12 @@ static void setup_stem2(HaloConv* c, const float* k, const float* bias, const fl
             for (int o = 0; o < co; ++o)
                 for (int e = 0; e < 16; ++e) put(ky * 11 + s, o, e, k[((size_t)(ky * 9 + kx) * C + e) * co + o]);
         }
-        for (int o = 0; o < co; ++o)                         // windowed 17th channel: element e = column tap
-            for (int e = 0; e < 9; ++e) put(99 + ky * 3 + 1, o, e, k[((size_t)(ky * 9 + e) * C + 16) * co + o]);
+        for (int o = 0; o < co; ++o)                         // windowed 17th channel: window slot e holds column x0 - 4 + e
+            for (int e = 0; e < 9; ++e) {
+                const float w = k[((size_t)(ky * 9 + e) * C + 16) * co + o];
+                put(99 + ky * 2, o, e, w);                   // even pixel x0: tap kx = e
+                put(99 + ky * 2 + 1, o, e + 1, w);           // odd pixel x0 + 1: tap kx = e at slot e + 1
+            }
     }
     col_bias->resize(64); col_scale->resize(64); col_shift->resize(64);
     for (int n = 0; n < 64; ++n) {
@@ -429,7 +433,7 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
     {
         LaunchScope ls(c, s, "pack_input");
         RST_CUDA(c, launch_pack_stem_input(d_content, st->s_in, batch, g.in_h, g.in_w, g.in_c, st->stem_layout.n_real,
-                                           st->stem_layout.row_elems, s));
+                                           st->stem_layout.row_elems, st->stem.launch.sched == SCH_STEM2 ? 1 : 0, s));
     }
     {
         LaunchScope ls(c, s, "stem_umma");
@@ -562,7 +566,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
     if (e == cudaSuccess && !y_f32) e = cudaMalloc(&yb, pout * co * 2);
     int rc = RST_OK;
     if (e == cudaSuccess) {
-        if (kind == STEM) e = launch_pack_stem_input(d_x, xb, batch, h, w, ci, SL.n_real, SL.row_elems, s);
+        if (kind == STEM) e = launch_pack_stem_input(d_x, xb, batch, h, w, ci, SL.n_real, SL.row_elems, stem_pairs ? 1 : 0, s);
         else e = launch_f32_to_bf16_pad(d_x, xb, pin, ci, in_c_dev, s);
     }
     if (e == cudaSuccess) {
