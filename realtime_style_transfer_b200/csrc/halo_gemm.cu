@@ -700,24 +700,27 @@ __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __rest
 #pragma unroll
         for (int j = 8 + 8 * NV; j < ROW / 2; ++j) w[half][j] = 0u;
     }
-    // transpose through the (now consumed) staging slice so that the warp writes the 64 packed pixels as one contiguous,
-    // fully coalesced run; the vector index is XOR-swizzled by the pixel to keep the shared-memory stores conflict-free
-    __syncwarp();
+    // transpose through the (now consumed) staging slice so that the warp writes its packed pixels as contiguous, fully
+    // coalesced runs: all 64 pixels at once when they fit in the slice (17 channels: 4 KB of 4.8 KB), else 32 at a time
+    // (18 channels: 2 x 4 KB of 5.1 KB); the vector index is XOR-swizzled by the pixel to keep the stores conflict-free
     uint4* so = reinterpret_cast<uint4*>(s4);
+    constexpr int PASSES = 64 * V <= NF4 ? 1 : 2, PPP = 64 / PASSES;       // pixels per pass
+    auto slot = [](int pl, int j) { return pl * V + (j ^ ((pl >> (V == 4 ? 1 : 0)) & (V - 1))); };
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int pl = lane + 32 * half;
+    for (int pass = 0; pass < PASSES; ++pass) {
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < V; ++j)
-            so[pl * V + (j ^ ((pl >> (V == 4 ? 1 : 0)) & (V - 1)))] =
-                make_uint4(w[half][4 * j], w[half][4 * j + 1], w[half][4 * j + 2], w[half][4 * j + 3]);
-    }
-    __syncwarp();
-    uint4* out = reinterpret_cast<uint4*>(y + pix0 * ROW);
+        for (int half = 0; half < 2; ++half) {
+            if (PASSES == 2 && half != pass) continue;
+            const int pl = PASSES == 2 ? lane : lane + 32 * half;
 #pragma unroll
-    for (int k = lane; k < 64 * V; k += 32) {
-        const int pl = k / V, j = k % V;
-        out[k] = so[pl * V + (j ^ ((pl >> (V == 4 ? 1 : 0)) & (V - 1)))];
+            for (int j = 0; j < V; ++j)
+                so[slot(pl, j)] = make_uint4(w[half][4 * j], w[half][4 * j + 1], w[half][4 * j + 2], w[half][4 * j + 3]);
+        }
+        __syncwarp();
+        uint4* out = reinterpret_cast<uint4*>(y + (pix0 + PPP * pass) * ROW);
+#pragma unroll
+        for (int k = lane; k < PPP * V; k += 32) out[k] = so[slot(k / V, k % V)];
     }
 }
 

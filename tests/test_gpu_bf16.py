@@ -131,6 +131,26 @@ def test_transfer_bf16_full_resolution(cuda_device):
     assert out.min() >= 0 and out.max() <= 1
 
 
+def test_transfer_bf16_full_resolution_dual_style(cuda_device):
+    """rst-960-120-128-18 (BASELINE.json configs[2]): 18-channel G-buffer, two predicted style-parameter sets blended per pixel
+    by the weight map and its mips (styleTransfer.py:36-44, :297-303), batch 1, bf16 vs the fp32 oracle."""
+    cfg = ShapeConfig.from_spec("rst-960-120-128-18")
+    cfg2 = ShapeConfig(num_styles=2, num_channels=18)
+    spec = O.TransferSpec(cfg2.input_shape["content"], cfg2.output_shape, 120, 128, 2)
+    assert cfg.input_shape["content"] == cfg2.input_shape["content"] == (480, 960, 18)
+    weights = O.init_transfer_weights(spec, seed=4)
+    content = O.synthetic_content(1, 480, 960, cfg2.channels, seed=5)
+    params = np.random.default_rng(6).uniform(0.3, 1.2, (1, 2, spec.num_style_parameters)).astype(np.float32)
+    sw = O.synthetic_style_weights(1, 480, 960)
+    ref = O.transfer_forward(spec, weights, content, params, sw).numpy()
+    out, _, launches = run_bf16(cfg2.input_shape["content"], cfg2.output_shape, 120, 128, 2, weights, content, params, sw)
+    err = np.abs(out - ref)
+    print(f"bf16 full-res dual style: rel_l2={rel_l2(out, ref):.4e} max_abs={err.max():.4e} p99.9={np.quantile(err, 0.999):.4e} "
+          f"launches={launches}")
+    assert rel_l2(out, ref) <= BF16_REL_TOL
+    assert np.quantile(err, 0.99) <= 2e-2 and np.quantile(err, 0.999) <= 5e-2
+
+
 def test_bf16_frames_independent_and_deterministic(cuda_device):
     shape_in, shape_out = (64, 128, 17), (64, 128, 3)
     spec = O.TransferSpec(shape_in, shape_out, 16, 128, 1)
