@@ -112,6 +112,22 @@ def test_transfer_bf16_small(cuda_device, styles, trained_like):
     assert np.quantile(err, 0.99) <= 2e-2 and np.quantile(err, 0.999) <= 5e-2
 
 
+@pytest.mark.parametrize("channels,filters", [(17, 64), (3, 128), (18, 64)])
+def test_transfer_bf16_other_geometries(cuda_device, channels, filters):
+    """64-filter bottleneck (1-CTA trunk kernels, N = 64 variants) and the 3- / 18-channel stems inside a whole network."""
+    shape_in, shape_out = (64, 128, channels), (64, 128, 3)
+    spec = O.TransferSpec(shape_in, shape_out, 16, filters, 1)
+    weights = O.init_transfer_weights(spec, seed=7)
+    content = O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=channels).channels, seed=3, unit_depth=True)
+    params = np.random.default_rng(4).uniform(0.3, 1.2, (2, 1, spec.num_style_parameters)).astype(np.float32)
+    ref = O.transfer_forward(spec, weights, content, params).numpy()
+    out, _, launches = run_bf16(shape_in, shape_out, 16, filters, 1, weights, content, params)
+    err = np.abs(out - ref)
+    print(f"bf16 C={channels} F={filters}: rel_l2={rel_l2(out, ref):.4e} max_abs={err.max():.4e}")
+    assert rel_l2(out, ref) <= BF16_REL_TOL
+    assert np.quantile(err, 0.99) <= 2e-2 and np.quantile(err, 0.999) <= 5e-2
+
+
 def test_transfer_bf16_full_resolution(cuda_device):
     """rst-960-120-128-17 geometry (BASELINE.json configs[1]) at batch 2, bf16 vs the fp32 oracle."""
     cfg = ShapeConfig.from_spec("rst-960-120-128-17")
