@@ -140,6 +140,11 @@ bool encode_weight_unit_map(CUtensorMap* out, const void* base, int rows, std::s
 size_t halo_gemm2_smem_bytes(int n_groups);
 cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
                               cudaStream_t s);
+// 2-CTA variant of the pair-pixel stem (halo_stem2cta.cu): tmB_units must cover kStem2Boxes * 256 + 32 rows (the peer CTA's
+// copy of the unit array starts one unit later)
+size_t halo_stem2cta_smem_bytes();
+cudaError_t launch_halo_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p, int num_sms,
+                                 cudaStream_t s);
 // Packs B: f(kstep, n, e) -> weight of K-step `kstep`, output column n, K element e (0..15).
 void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out);
 

@@ -21,6 +21,7 @@ struct HaloConv {
     HaloGemmLaunch launch;
     HaloGemmParams p;
     CUtensorMap tmA, tmB, tmB_half;
+    bool stem_2cta = false;        // SCH_STEM2: cta_group::2 kernel (halo_stem2cta.cu)
     bool two_cta = false;          // 128->128 3x3 convs: cta_group::2 kernel with resident weights
     __nv_bfloat16* w_packed = nullptr;
     float* col_bias = nullptr;     // [N] bias expanded to GEMM columns
@@ -61,7 +62,9 @@ struct HaloConv {
             if (!encode_s2d_map(&tmA, x, B, 2 * H, 2 * WRU, in_C / 2, err)) return false;
         } else if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
         if (sched_b_units(launch.sched)) {
-            if (!encode_weight_unit_map(&tmB, w_packed, kStem2Boxes * 256, err)) return false;
+            if (!encode_weight_unit_map(&tmB, w_packed, (kStem2Boxes + 1) * 256, err)) return false;
+            const char* env2 = getenv("RST_STEM_2CTA");
+            stem_2cta = !(env2 && env2[0] == '0') && launch.mode == (HALO_MODE_RELU | HALO_MODE_POST);
         } else if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
         const char* env = getenv("RST_TRUNK_2CTA");
         two_cta = launch.sched == SCH_C3 && launch.N == 128 && launch.row_bytes == 128 && launch.epi == EPI_NHWC &&
@@ -77,6 +80,7 @@ struct HaloConv {
         if (getenv("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiments only (wrong results)
         if (getenv("RST_EXP_NOSTORE")) q.H = 0;
         if (two_cta && !y_f32) return launch_halo_gemm2(tmA, tmB_half, q, num_sms, s);
+        if (stem_2cta && !y_f32 && !q.stats) return launch_halo_stem2cta(tmA, tmB, q, num_sms, s);
         return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
     }
 };
@@ -163,7 +167,7 @@ static void setup_stem2(HaloConv* c, const float* k, const float* bias, const fl
     c->in_C = 64; c->p.n_groups = 1;
     use_sched(c, SCH_STEM2);
     c->p.out_C = 64; c->p.stats_c = 64;
-    packed->assign((size_t)kStem2Boxes * 256 * 16, __float2bfloat16(0.f));
+    packed->assign((size_t)(kStem2Boxes + 1) * 256 * 16, __float2bfloat16(0.f));   // + one zero box: the 2-CTA peer reads one unit further
     auto put = [&](int unit, int row, int e, float w) { (*packed)[((size_t)unit * 32 + row) * 16 + e] = __float2bfloat16(w); };
     for (int ky = 0; ky < 9; ++ky) {
         for (int s = 1; s <= 9; ++s) {                       // unit s of the sequence holds column tap kx = 9 - s
