@@ -78,7 +78,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nbslots = BRES ? blocks_per_tile : p.n_bstages;
     uint8_t* sA = smem;
     uint8_t* sB = sA + p.n_astages * a_stage_bytes;
-    uint8_t* tail = sB + (sched_b_units(SCH) ? kStem2Boxes * 8192 : nbslots * BBLK);
+    uint8_t* tail = sB + (sched_b_units(SCH) ? sched_b_boxes(SCH) * 8192 : nbslots * BBLK);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 4;
     uint64_t* b_full = a_empty + 4;
@@ -128,7 +128,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     mbar_expect_tx(&a_full[stage], halo_bytes);
                     if (SCH == SCH_S2D) tma_load_5d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], 0, h0, 0, w0, n);
-                    else tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 + p.ox, n);
+                    else tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 * p.a_w_mul + p.ox, n);
                     if (++stage == (uint32_t)p.n_astages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -137,8 +137,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= B producer ===========================================================
         if (lane == 0 && tile_begin < tile_end) {
             if (sched_b_units(SCH)) {
-                mbar_expect_tx(&b_full[0], kStem2Boxes * 8192);
-                for (int kb = 0; kb < kStem2Boxes; ++kb) tma_load_2d(sB + kb * 8192, &tmB, &b_full[0], 0, kb * 256);
+                mbar_expect_tx(&b_full[0], sched_b_boxes(SCH) * 8192);
+                for (int kb = 0; kb < sched_b_boxes(SCH); ++kb) tma_load_2d(sB + kb * 8192, &tmB, &b_full[0], 0, kb * 256);
             } else if (BRES) {
                 mbar_expect_tx(&b_full[0], blocks_per_tile * BBLK);
                 for (int kb = 0; kb < blocks_per_tile; ++kb) tma_load_2d(sB + kb * BBLK, &tmB, &b_full[0], 0, kb * N);
@@ -160,7 +160,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // the uniform datapath; only the tcgen05.mma / tcgen05.commit instructions themselves are issued by lane 0.
         {
             const uint32_t idesc = (MODE & MODE_TF32) ? make_idesc_tf32(128, N) : make_idesc_bf16(128, N);
-            const uint64_t da_const = make_smem_desc(0, 16, sched_halo_h(SCH) * ROWB, SWZ);
+            const uint64_t da_const = make_smem_desc(0, 16, sched_a_unit_stride(SCH) * sched_halo_h(SCH) * ROWB, SWZ);
             const uint64_t db_const = sched_b_units(SCH) ? make_smem_desc(0, 16, 256, SWIZZLE_32B) : make_smem_desc(0, 16, 1024, SWIZZLE_128B);
             const bool leader = elect_one();
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
@@ -187,7 +187,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             b_base16 = sB16 + bs * (BBLK / 16);
                         }
                         const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH, ROWB, ks) >> 4));
-                        const uint64_t db = db_const | (uint64_t)(sched_b_units(SCH) ? sB16 + sched_b_unit(SCH, ks) * 64
+                        const uint64_t db = db_const | (uint64_t)(sched_b_units(SCH) ? sB16 + sched_b_off16(SCH, ks)
                                                                                     : b_base16 + (BRES ? (ks / 4) * (BBLK / 16) : 0) + (ks & 3) * 2);
                         if (leader) {
                             if (MODE & MODE_TF32) mma_tf32_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
@@ -233,6 +233,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     bool on = lane < CW;
                     if (EPI == EPI_CONVT2) ch = col % p.stats_c;
                     if (EPI == EPI_QUAD3) { ch = col % 3; on = on && col < 12; }
+                    if (EPI == EPI_OCT3) { ch = col % 4; on = on && ch < 3; }
                     if (on) {
                         double* dst = p.stats + ((size_t)cur_n * p.stats_c + ch) * 2;
                         atomicAdd(dst, (double)s1);
@@ -283,7 +284,15 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < CW; ++j) v[j] = round_tf32(v[j]);
                     }
-                    if (valid) {
+                    if (valid && EPI == EPI_OCT3) {
+                        // 8 pixels x 3 channels = 24 contiguous floats; column j*4 + 3 is padding
+                        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (((size_t)n * p.out_H + gh) * p.out_W + 8 * gw) * 3);
+                        float w24[24];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { w24[3 * j] = v[4 * j]; w24[3 * j + 1] = v[4 * j + 1]; w24[3 * j + 2] = v[4 * j + 2]; }
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) o4[j] = make_float4(w24[4 * j], w24[4 * j + 1], w24[4 * j + 2], w24[4 * j + 3]);
+                    } else if (valid) {
                         float4* o4;
                         if (EPI == EPI_QUAD3)
                             o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (((size_t)n * p.out_H + gh) * p.out_W + 4 * gw) * 3);
@@ -404,7 +413,7 @@ bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err) {
     p->b_resident = sched_resident(*l) ? 1 : 0;
     int b_bytes;
     if (sched_b_units(l->sched)) {
-        b_bytes = kStem2Boxes * 8192;
+        b_bytes = sched_b_boxes(l->sched) * 8192;
     } else if (p->b_resident) {
         b_bytes = blocks * bblk;
     } else {
@@ -460,6 +469,7 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
     RST_HALO_CASE(128, 128, EPI_CONVT2, 0, SCH_T2, true)                    // expand_0: 4 phases x 32 channels
     RST_HALO_CASE(64, 64, EPI_CONVT2, 0, SCH_T2, true)                      // expand_1: 4 phases x 16 channels
     RST_HALO_CASE(16, 128, EPI_QUAD3, MODE_F32, SCH_HEAD, true)             // expand_last: 4 pixels x 3 channels
+    RST_HALO_CASE(32, 128, EPI_OCT3, MODE_F32, SCH_HEAD8, true)             // expand_last: 8 pixels x 3 (+1) channels
     RST_HALO_CASE(128, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)   // tf32 3x3 convs (VGG16 loss model)
     RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)
     RST_HALO_CASE(128, 128, EPI_NHWC, MODE_F32 | MODE_TF32, SCH_C3, false)               // ... and their input gradients

@@ -33,11 +33,18 @@ enum HaloEpi : int {
     EPI_NHWC = 0,     // out[n, gh, gw, col]                       (conv)
     EPI_CONVT2 = 1,   // col = phase*Cq + c -> out[n, 2gh+a, 2gw+b, c] (stride-2 transposed conv as 4 phases)
     EPI_QUAD3 = 2,    // col = j*3 + c (j<4) -> out[n, gh, 4gw+j, c]   (3-channel head, 4 pixels per row unit)
+    EPI_OCT3 = 3,     // col = j*4 + c (j<8, c<3) -> out[n, gh, 8gw+j, c]  (3-channel head, 8 pixels per GEMM row)
 };
 
 // ---- K-step schedules: compile-time A-operand offsets so that the MMA issue loop is fully unrolled ----------------
 // SCH_C3: 3x3 taps x (row_bytes/32) channel slices, halo 10x18.     SCH_T2: 2x2 taps (stride-2 transposed conv), halo 9x17.
 // SCH_HEAD: 9 rows x 12 window pixels over 4-pixel row units, halo 16x18.
+// SCH_HEAD8: the same 9x9 transposed conv with EIGHT pixels per GEMM row = two adjacent 4-pixel row units (the A descriptor's
+//          8-row-group stride is doubled): 9 rows x 16 window pixels, N = 8 x (3 + 1 pad) columns, halo 16x35.  A third fewer
+//          K-steps per pixel at the same ~41 cycles per MMA.  B is a block-Toeplitz matrix over 4-row weight units (one per
+//          column tap); K-step s reads 8 consecutive units starting at 15 - s from the sequence [7 zeros, U0..U8, 7 zeros].
+//          A SWIZZLE_32B atom is 8 rows = TWO units, so the sequence is stored twice per row tap, the second copy shifted
+//          by one unit, and odd starts read the shifted copy: every descriptor start stays atom-aligned.
 // SCH_STEM + 4*REAL + NV: 9x9 taps over the 16 real channels (REAL) plus 9 row taps per windowed channel group (NV).
 // SCH_S2D: 3x3 stride-2 conv over the space-to-depth view (h2, row parity, w2, [col parity x channels]) of the input:
 //          row taps ky -> (h2 + ky/2, parity ky%2); column taps kx -> (w2 + kx/2, parity kx%2) = channel slice of the row.
@@ -47,30 +54,44 @@ enum HaloEpi : int {
 //          TWO ADJACENT units through a shifted SWIZZLE_32B descriptor (the halo trick applied to the weights).
 //          The 17th channel is stored ONCE per pair, as the 10-wide window x0-4 .. x0+5 in the even pixel's spare slots:
 //          one K-step per row tap serves both pixels (units [Wa, Wb] = the 9 taps at slot offsets 0 and 1): 90 + 9 K-steps.
-enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM2 = 4, SCH_STEM = 10 };
-__host__ __device__ constexpr bool sched_b_units(int sch) { return sch == SCH_STEM2; }
+enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM2 = 4, SCH_HEAD8 = 5, SCH_STEM = 10 };
+__host__ __device__ constexpr bool sched_b_units(int sch) { return sch == SCH_STEM2 || sch == SCH_HEAD8; }
 constexpr int kStem2Units = 9 * 11 + 9 * 2 + 2;      // 99 real + 18 window units + 2 zero units (padding K-step)
 constexpr int kStem2Boxes = (kStem2Units * 32 + 255) / 256;   // TMA boxes of 256 rows (8 KB)
 // unit index (1 KB each) where K-step ks of SCH_STEM2 starts reading its 64 B rows
 __host__ __device__ constexpr int sched_b_unit(int sch, int ks) {
     return sch != SCH_STEM2 ? 0 : ks < 90 ? (ks / 10) * 11 + (9 - ks % 10) : 99 + (ks - 90) * 2;
 }
+// SCH_HEAD8: 9 row taps x 2 copies x 24 units of 4 rows x 32 B (128 B)
+constexpr int kHead8SeqUnits = 24;
+constexpr int kHead8Rows = 9 * 2 * kHead8SeqUnits * 4;                 // 1728 rows of 32 B
+constexpr int kHead8Boxes = (kHead8Rows + 255) / 256;                  // 7 TMA boxes of 256 rows
+// B start of K-step ks in 16-byte units relative to the start of the resident weights
+__host__ __device__ constexpr int sched_b_off16(int sch, int ks) {
+    if (sch == SCH_STEM2) return sched_b_unit(sch, ks) * 64;
+    if (sch == SCH_HEAD8) { const int dy = ks / 16, m0 = 15 - ks % 16, par = m0 & 1; return ((dy * 2 + par) * kHead8SeqUnits + m0 - par) * 8; }
+    return 0;
+}
+__host__ __device__ constexpr int sched_b_boxes(int sch) { return sch == SCH_STEM2 ? kStem2Boxes : sch == SCH_HEAD8 ? kHead8Boxes : 0; }
+// GEMM rows advance by this many row units along W (SCH_HEAD8: an 8-pixel row = two 4-pixel units)
+__host__ __device__ constexpr int sched_a_unit_stride(int sch) { return sch == SCH_HEAD8 ? 2 : 1; }
 __host__ __device__ constexpr int sched_real_ksteps(int sch, int rowb) {
     return sch == SCH_C3 ? 9 * (rowb / 32) : sch == SCH_T2 ? 4 * (rowb / 32) : sch == SCH_HEAD ? 108
-           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 99
+           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 99 : sch == SCH_HEAD8 ? 144
            : 81 * ((sch - SCH_STEM) / 4) + 9 * ((sch - SCH_STEM) % 4);
 }
 __host__ __device__ constexpr int sched_ksteps(int sch, int rowb) { return (sched_real_ksteps(sch, rowb) + 3) / 4 * 4; }
 __host__ __device__ constexpr int sched_halo_h(int sch) { return sch == SCH_C3 ? 10 : sch == SCH_T2 ? 9 : sch == SCH_S2D ? 18 : 16; }
-__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : sch == SCH_STEM2 ? 20 : 24; }
+__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : sch == SCH_STEM2 ? 20 : sch == SCH_HEAD8 ? 35 : 24; }
 __host__ __device__ constexpr int sched_oy(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : -4; }
-__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD ? -1 : sch == SCH_STEM2 ? -2 : -4; }
+__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD || sch == SCH_HEAD8 ? -1 : sch == SCH_STEM2 ? -2 : -4; }
 // byte offset of K-step ks into the halo patch
 __host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
     if (ks >= sched_real_ksteps(sch, rowb)) return 0;
     if (sch == SCH_C3) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 3) * 10 + tap / 3) * rowb + (ks % kper) * 32; }
     if (sch == SCH_T2) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 2) * 9 + tap / 2) * rowb + (ks % kper) * 32; }
     if (sch == SCH_HEAD) { const int dy = ks / 12, kx = ks % 12; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
+    if (sch == SCH_HEAD8) { const int dy = ks / 16, kx = ks % 16; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
     if (sch == SCH_STEM2) {
         if (ks < 90) { const int ky = ks / 10, kxp = ks % 10; return ((kxp / 2) * 16 + ky) * 128 + (kxp % 2) * 64; }
         const int ky = ks - 90;
@@ -93,6 +114,7 @@ struct HaloGemmParams {
     int B = 0, H = 0, WRU = 0, tiles_h = 0, tiles_w = 0;
     // A halo
     int oy = 0, ox = 0;              // halo origin relative to the tile origin (rows, RUs)
+    int a_w_mul = 1;                 // TMA W coordinate = tile column * a_w_mul + ox (SCH_HEAD8: GEMM rows span two row units)
     int halo_h = 10, halo_w = 18;    // box extent (rows, RUs)
     int n_groups = 1;                // halo loads per tile; group g loads channel coordinate g * row_elems
     int ksteps = 0;                  // K-steps per group, multiple of 4

@@ -60,8 +60,11 @@ struct HaloConv {
         p.tiles_h = ceil_div(H, 8); p.tiles_w = ceil_div(WRU, 16);
         if (launch.sched == SCH_S2D) {
             if (!encode_s2d_map(&tmA, x, B, 2 * H, 2 * WRU, in_C / 2, err)) return false;
-        } else if (!encode_halo_map(&tmA, x, B, H, WRU, in_C, launch.row_bytes / 2, p.halo_h, p.halo_w, err)) return false;
-        if (sched_b_units(launch.sched)) {
+        } else if (!encode_halo_map(&tmA, x, B, H, WRU * sched_a_unit_stride(launch.sched), in_C, launch.row_bytes / 2,
+                                    sched_halo_h(launch.sched), sched_halo_w(launch.sched), err)) return false;
+        if (launch.sched == SCH_HEAD8) {
+            if (!encode_weight_unit_map(&tmB, w_packed, kHead8Boxes * 256, err)) return false;
+        } else if (sched_b_units(launch.sched)) {
             if (!encode_weight_unit_map(&tmB, w_packed, (kStem2Boxes + 1) * 256, err)) return false;
             const char* env2 = getenv("RST_STEM_2CTA");
             stem_2cta = !(env2 && env2[0] == '0') && launch.mode == (HALO_MODE_RELU | HALO_MODE_POST);
@@ -87,6 +90,7 @@ struct HaloConv {
 
 static void use_sched(HaloConv* c, int sch) {
     c->launch.sched = sch;
+    c->p.a_w_mul = sched_a_unit_stride(sch);
     c->p.ksteps = sched_ksteps(sch, c->launch.row_bytes);
     c->p.halo_h = sched_halo_h(sch); c->p.halo_w = sched_halo_w(sch);
     c->p.oy = sched_oy(sch); c->p.ox = sched_ox(sch);
@@ -264,6 +268,31 @@ static void setup_head(HaloConv* c, const float* k, const float* bias, std::vect
     for (int n = 0; n < 12; ++n) (*col_bias)[n] = bias[n % 3];
 }
 
+// The same layer with 8 pixels per GEMM row (SCH_HEAD8, needs W % 8 == 0): block-Toeplitz weight units, see halo_gemm.cuh.
+static void setup_head8(HaloConv* c, const float* k, const float* bias, std::vector<__nv_bfloat16>* packed,
+                        std::vector<float>* col_bias) {
+    c->launch.N = 32; c->launch.row_bytes = 128; c->launch.epi = EPI_OCT3;
+    c->in_C = 64; c->p.n_groups = 1;
+    use_sched(c, SCH_HEAD8);
+    c->launch.mode = HALO_MODE_F32;
+    c->p.out_C = 3; c->p.stats_c = 3;
+    packed->assign((size_t)kHead8Boxes * 256 * 16, __float2bfloat16(0.f));
+    for (int dy = 0; dy < 9; ++dy) {
+        const int ky = 8 - dy;
+        for (int par = 0; par < 2; ++par)
+            for (int m = 0; m < kHead8SeqUnits; ++m) {
+                const int kx = m + par - 7;                  // copy `par` holds the sequence shifted by one unit
+                if (kx < 0 || kx > 8) continue;
+                for (int o = 0; o < 3; ++o)
+                    for (int e = 0; e < 16; ++e)
+                        (*packed)[((((size_t)dy * 2 + par) * kHead8SeqUnits + m) * 4 + o) * 16 + e] =
+                            __float2bfloat16(k[((size_t)(ky * 9 + kx) * 3 + o) * 16 + e]);
+            }
+    }
+    col_bias->assign(32, 0.f);
+    for (int n = 0; n < 32; ++n) if (n % 4 < 3) (*col_bias)[n] = bias[n % 4];
+}
+
 // ------------------------------------------------------------------------------------------------
 struct Bf16State {
     int num_sms = 148;
@@ -396,11 +425,13 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, st->e1.upload(packed, cb, nullptr, nullptr));
         st->e1.p.out_H = L1.ho; st->e1.p.out_W = L1.wo;
         if (!st->e1.bind_input(st->ze0, B, L1.hi, L1.wi, &err)) return fail(c, RST_ERR_CUDA, err);
-        setup_head(&st->head, c->find_weight(L2.name + "/conv/kernel")->host.data(),
+        const char* env8 = getenv("RST_HEAD8");
+        const bool head8 = L2.wi % 8 == 0 && !(env8 && env8[0] == '0');
+        (head8 ? setup_head8 : setup_head)(&st->head, c->find_weight(L2.name + "/conv/kernel")->host.data(),
                    c->find_weight(L2.name + "/conv/bias")->host.data(), &packed, &cb);
         RST_CUDA(c, st->head.upload(packed, cb, nullptr, nullptr));
         st->head.p.out_H = L2.ho; st->head.p.out_W = L2.wo;
-        if (!st->head.bind_input(st->ze1, B, L2.hi, L2.wi / 4, &err)) return fail(c, RST_ERR_CUDA, err);
+        if (!st->head.bind_input(st->ze1, B, L2.hi, L2.wi / (head8 ? 8 : 4), &err)) return fail(c, RST_ERR_CUDA, err);
     }
     return RST_OK;
 }
@@ -559,8 +590,10 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
         setup_convt2(&hc, ci, co, hk.data(), hb.data(), &packed, &cb);
         oh = 2 * h; ow = 2 * w;
     } else {
-        setup_head(&hc, hk.data(), hb.data(), &packed, &cb);
-        wru = w / 4; y_f32 = true;
+        const char* env8 = getenv("RST_HEAD8");
+        const bool head8 = w % 8 == 0 && !(env8 && env8[0] == '0');
+        (head8 ? setup_head8 : setup_head)(&hc, hk.data(), hb.data(), &packed, &cb);
+        wru = w / (head8 ? 8 : 4); y_f32 = true;
     }
     e = (kind == STEM || kind == S2) ? hc.upload(packed, cb, &cs, &csh) : hc.upload(packed, cb, nullptr, nullptr);
     const long long pin = (long long)batch * h * w, pout = (long long)batch * oh * ow;
