@@ -15,7 +15,7 @@ Tf32Conv3x3::~Tf32Conv3x3() {
 // packed[j][blk][n][r]: K-step ks = 4*blk + r/8, element e = r%8 -> channel group g = ks/36, tap = (ks%36)/4,
 // input channel g*32 + ((ks%36)%4)*8 + e; output channel j*nb + n.  Rounded to tf32 (nearest).
 __global__ void tf32_pack_weights_kernel(const float* __restrict__ k, float* __restrict__ out, int ci_layer, int co_layer,
-                                         int input_gradient, int nb, int blocks, long long total) {
+                                         int input_gradient, int nb, int blocks, int ci_real, long long total) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int r = (int)(idx % 32);
@@ -25,17 +25,36 @@ __global__ void tf32_pack_weights_kernel(const float* __restrict__ k, float* __r
     const int blk = (int)(t % blocks), j = (int)(t / blocks);
     const int ks = blk * 4 + r / 8, e = r % 8;
     const int g = ks / 36, l = ks % 36, tap = l / 4;
-    const int cin = g * 32 + (l % 4) * 8 + e, cout = j * nb + n;
+    const int cin_eff = g * 32 + (l % 4) * 8 + e, cout = j * nb + n;
+    const int part = cin_eff / ci_real, cin = cin_eff - part * ci_real;       // split convs: parts [w_hi | w_hi | w_lo]
     const float w = !input_gradient ? k[((size_t)tap * ci_layer + cin) * co_layer + cout]
                                     : k[((size_t)(8 - tap) * ci_layer + cout) * co_layer + cin];
     uint32_t rr;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(w));
-    out[idx] = __uint_as_float(rr);
+    float v = __uint_as_float(rr);
+    if (part == 2) { asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(w - v)); v = __uint_as_float(rr); }
+    out[idx] = v;
 }
 
-bool Tf32Conv3x3::setup_shape(int ci_layer_, int co_layer_, bool relu_, bool input_gradient_, std::string* err) {
-    ci_layer = ci_layer_; co_layer = co_layer_; input_gradient = input_gradient_;
-    ci = input_gradient ? co_layer : ci_layer;
+// x (P, c) -> [tf32(x) | tf32(x - tf32(x)) | tf32(x)] (P, 3c)
+__global__ void tf32_split_expand_kernel(const float* __restrict__ x, float* __restrict__ out, int c, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long pix = i / c;
+    const int ch = (int)(i - pix * c);
+    const float v = x[i];
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    const float hi = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - hi));
+    const float lo = __uint_as_float(r);
+    float* o = out + pix * 3 * c + ch;
+    o[0] = hi; o[c] = lo; o[2 * c] = hi;
+}
+
+bool Tf32Conv3x3::setup_shape(int ci_layer_, int co_layer_, bool relu_, bool input_gradient_, std::string* err, bool split_) {
+    ci_layer = ci_layer_; co_layer = co_layer_; input_gradient = input_gradient_; split = split_;
+    ci = (input_gradient ? co_layer : ci_layer) * (split ? 3 : 1);
     co = input_gradient ? ci_layer : co_layer;
     relu = relu_;
     if (ci % 32 != 0 || co % 64 != 0) {
@@ -71,7 +90,7 @@ cudaError_t Tf32Conv3x3::repack(const float* d_kernel, const float* d_bias, cuda
     const int blocks = (ci / 32) * 9;
     const long long total = (long long)nblk * blocks * nb * 32;
     tf32_pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_kernel, w_packed, ci_layer, co_layer,
-                                                                            input_gradient ? 1 : 0, nb, blocks, total);
+                                                                            input_gradient ? 1 : 0, nb, blocks, split ? ci / 3 : ci, total);
     ext_bias = d_bias;
     return cudaGetLastError();
 }
@@ -114,6 +133,7 @@ cudaError_t Tf32Conv3x3::run(const float* x, float* y, int B, int H, int W, int 
     q.tiles_h = ceil_div(H, 8); q.tiles_w = ceil_div(W, 16);
     q.out_H = H; q.out_W = W; q.out_C = co;
     q.y_f32 = 1; q.stats = nullptr;
+    q.store_exact = split ? 1 : 0;
     for (int j = 0; j < nblk; ++j) {
         q.y = y + (size_t)j * nb;
         q.bias = ext_bias ? ext_bias + (size_t)j * nb : nullptr;
@@ -121,6 +141,18 @@ cudaError_t Tf32Conv3x3::run(const float* x, float* y, int B, int H, int W, int 
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+cudaError_t Tf32Conv3x3::run_split(const float* x, float* scratch, float* y, int B, int H, int W, int num_sms, cudaStream_t s,
+                                   std::string* err) {
+    if (!split) return run(x, y, B, H, W, num_sms, s, err);
+    const int c = ci / 3;
+    const long long total = (long long)B * H * W * c;
+    if (total == 0) return cudaSuccess;
+    tf32_split_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, scratch, c, total);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return run(scratch, y, B, H, W, num_sms, s, err);
 }
 
 }  // namespace rst

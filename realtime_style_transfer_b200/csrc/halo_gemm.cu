@@ -280,7 +280,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     v[j] = x;
                 }
                 if (MODE & MODE_F32) {
-                    if (MODE & MODE_TF32) {
+                    if ((MODE & MODE_TF32) && !p.store_exact) {
 #pragma unroll
                         for (int j = 0; j < CW; ++j) v[j] = round_tf32(v[j]);
                     }

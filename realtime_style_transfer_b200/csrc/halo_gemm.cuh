@@ -128,6 +128,7 @@ struct HaloGemmParams {
     const float* post_shift = nullptr;
     double* stats = nullptr;             // (B, stats_c, 2) [sum, sumsq] or null
     int stats_c = 0;
+    int store_exact = 0;                 // MODE_TF32: store the fp32 accumulator as is (split-tf32 convs) instead of rounding to tf32
 };
 
 constexpr int kHaloThreads = 352;    // warps: 0 A-TMA, 1 B-TMA, 2 MMA, 3..10 epilogue (two per TMEM lane quadrant)
@@ -195,7 +196,13 @@ struct Tf32Conv3x3 {
     bool setup(int ci_layer, int co_layer, const float* k, const float* bias_host, bool relu, bool input_gradient, std::string* err);
     // Same without weights: allocate and plan only; repack() then (re)builds the packed tf32 weights from a DEVICE kernel
     // tensor (3,3,ci_layer,co_layer), e.g. once per training step after the optimizer moved the variables.
-    bool setup_shape(int ci_layer, int co_layer, bool relu, bool input_gradient, std::string* err);
+    // split = true: error-compensated "3 x tf32" arithmetic with fp32-level accuracy: x = x_hi + x_lo, w = w_hi + w_lo (each part
+    // on the tf32 grid), y = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in fp32 -- realised as ONE conv over 3*ci channels
+    // [x_hi | x_lo | x_hi] with weights [w_hi | w_hi | w_lo]; run() then needs a scratch tensor of 3x the input size.
+    bool setup_shape(int ci_layer, int co_layer, bool relu, bool input_gradient, std::string* err, bool split = false);
+    bool split = false;
+    size_t scratch_floats(int B, int H, int W) const { return split ? (size_t)B * H * W * ci : 0; }
+    cudaError_t run_split(const float* x, float* scratch, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
     cudaError_t repack(const float* d_kernel, const float* d_bias, cudaStream_t s);
     cudaError_t run(const float* x, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
 };

@@ -59,17 +59,18 @@ struct rst_trainer {
     // optional tf32 tensor-core path for the 3x3 stride-1 convolutions of the transfer network (Cin % 32 == 0, Cout % 64 == 0:
     // the residual trunk), forward and input gradient; weights are re-packed from the live variables every step
     int math = RST_PRECISION_FP32;
+    int split_tf32 = 1;                   // fp32 math: 1 = split-tf32 tensor-core convs for the trunk, 0 = CUDA-core fp32 (RST_TRAIN_SPLIT_TF32=0)
     int num_sms = 148;
     std::map<std::string, std::unique_ptr<Tf32Conv3x3>> tf32_fwd, tf32_bwd;
 };
 
 static Tf32Conv3x3* tf32_conv(rst_trainer* t, std::map<std::string, std::unique_ptr<Tf32Conv3x3>>& cache, const std::string& name,
-                              int ci, int co, bool relu, bool input_gradient) {
+                              int ci, int co, bool relu, bool input_gradient, bool split) {
     auto it = cache.find(name);
-    if (it != cache.end()) return it->second.get();
+    if (it != cache.end() && it->second->split == split) return it->second.get();
     std::unique_ptr<Tf32Conv3x3> c(new Tf32Conv3x3());
     std::string err;
-    if (!c->setup_shape(ci, co, relu, input_gradient, &err)) {
+    if (!c->setup_shape(ci, co, relu, input_gradient, &err, split)) {
         if (t->rc == RST_OK) t->rc = RST_ERR_CUDA, t->err = "training tf32 conv " + name + ": " + err;
         return nullptr;
     }
@@ -178,19 +179,25 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
     if (!cs.transposed) { p.w_ci = co; p.w_co = 1; } else { p.w_ci = 1; p.w_co = ci; }
     p.in_scale = cs.in_scale; p.in_shift = cs.in_shift;
     p.act1 = cs.act;
-    const bool tensor_core = t->math == RST_PRECISION_TF32 && !cs.transposed && cs.k == 3 && cs.stride == 1 && ci % 32 == 0 &&
-                             co % 64 == 0 && (cs.act == ACT_RELU || cs.act == ACT_NONE) && cs.in_scale == 1.f && cs.in_shift == 0.f;
-    Tf32Conv3x3* fwd = tensor_core ? tf32_conv(t, t->tf32_fwd, kname, ci, co, cs.act == ACT_RELU, false) : nullptr;
+    // 3x3 stride-1 convs with Cin % 32 == 0, Cout % 64 == 0 (the residual trunk) run on the tensor cores: plain tf32 operands
+    // under RST_PRECISION_TF32, error-compensated split tf32 (fp32-level accuracy) otherwise
+    const bool tensor_core = t->split_tf32 >= 0 && !cs.transposed && cs.k == 3 && cs.stride == 1 && ci % 32 == 0 && co % 64 == 0 &&
+                             (cs.act == ACT_RELU || cs.act == ACT_NONE) && cs.in_scale == 1.f && cs.in_shift == 0.f &&
+                             (t->math == RST_PRECISION_TF32 || t->split_tf32 == 1);
+    const bool split = tensor_core && t->math != RST_PRECISION_TF32;
+    Tf32Conv3x3* fwd = tensor_core ? tf32_conv(t, t->tf32_fwd, kname, ci, co, cs.act == ACT_RELU, false, split) : nullptr;
     if (fwd) {
         std::string err;
+        float* scratch = split ? falloc(t, (long long)fwd->scratch_floats(x->B, x->H, x->W)) : nullptr;
         OPCUDA(t, fwd->repack(vk->w, vb ? vb->w : nullptr, t->s));
-        OPCUDA(t, fwd->run(x->d, y->d, x->B, x->H, x->W, t->num_sms, t->s, &err));
-        t->m->launches += 1 + fwd->nblk;
+        OPCUDA(t, fwd->run_split(x->d, scratch, y->d, x->B, x->H, x->W, t->num_sms, t->s, &err));
+        t->m->launches += 1 + fwd->nblk + (split ? 1 : 0);
     } else {
         OPCUDA(t, launch_conv_f32(p, t->s));
         t->m->launches += 1;
     }
     float* dgrad_tmp = (tensor_core && x->needs_grad) ? falloc(t, x->n()) : nullptr;
+    float* dgrad_scratch = (split && x->needs_grad) ? falloc(t, 3LL * y->n()) : nullptr;
     double* st = dalloc(t, (long long)x->B * co * 2);
     double* st2 = dalloc(t, (long long)co * 2);
     const ConvSpec spec = cs;
@@ -207,12 +214,12 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
         TCUDA(t, launch_wgrad_f32(wg, t->s));
         t->m->launches += 2;
         if (vb) { int rc = bias_grad(t, y->g, y->B, y->P(), co, vb->g, st, st2); if (rc) return rc; }
-        Tf32Conv3x3* bwd = (tensor_core && x->needs_grad) ? tf32_conv(t, t->tf32_bwd, kname, ci, co, false, true) : nullptr;
+        Tf32Conv3x3* bwd = (tensor_core && x->needs_grad) ? tf32_conv(t, t->tf32_bwd, kname, ci, co, false, true, split) : nullptr;
         if (bwd) {
             std::string err;
             float* dst = x->g_init ? dgrad_tmp : x->g;
             TCUDA(t, bwd->repack(vk->w, nullptr, t->s));
-            TCUDA(t, bwd->run(y->g, dst, x->B, x->H, x->W, t->num_sms, t->s, &err));
+            TCUDA(t, bwd->run_split(y->g, dgrad_scratch, dst, x->B, x->H, x->W, t->num_sms, t->s, &err));
             if (x->g_init) TCUDA(t, launch_add_inplace(x->g, dgrad_tmp, x->n(), t->s));
             t->m->launches += 2 + bwd->nblk;
             x->g_init = true;
@@ -514,6 +521,7 @@ extern "C" int rst_train_create(const rst_config* cfg, int device, rst_trainer**
     if (rc != RST_OK) { g_train_create_error = rst_loss_last_error(nullptr); rst_train_destroy(t); return rc; }
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* env = getenv("RST_TRAIN_SPLIT_TF32")) t->split_tf32 = env[0] == '0' ? 0 : 1;
     // one arena for every variable: trainable ones first, so that gradients / RMSprop slots are flat arrays of the same layout
     auto padded = [](int64_t n) { return (n + 63) / 64 * 64; };
     auto trainable = [](const std::string& n) {

@@ -305,3 +305,40 @@ def test_training_step_tf32_trunk(cuda_device):
     print(history)
     assert history[-1] < history[0]
     tr.close()
+
+
+def test_training_step_split_tf32_trunk_keeps_fp32_accuracy(cuda_device):
+    """Default (fp32) math with a 64-filter trunk: the residual trunk's convolutions run on the tensor cores as
+    error-compensated split tf32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation).  The fp32 bars must hold: prediction
+    1e-4 and the network's backward pass within VJP_TOL of fp64 autograd for the same upstream gradient."""
+    batch, filters = 2, 64
+    spec = O.TransferSpec(IN_SHAPE, OUT_SHAPE, RES_Y, filters, 1)
+    tw = O.init_transfer_weights(spec, seed=21, trained_like=True)
+    pw = O.init_predictor_weights("DUMMY", spec.num_style_parameters, seed=22)
+    vgg = O.init_vgg16_weights(seed=3)
+    rng = np.random.default_rng(13)
+    content = rng.uniform(0, 1, (batch,) + IN_SHAPE).astype(np.float32)
+    style = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+    gt = rng.uniform(0, 1, (batch,) + OUT_SHAPE).astype(np.float32)
+    tr = _native.NativeTrainer(in_shape=IN_SHAPE, out_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=filters,
+                               max_batch=batch, extractor=_native.EXTRACTOR_DUMMY, style_shape=OUT_SHAPE[:2])
+    tr.model.set_weights({**tw, **pw})
+    tr.loss.set_weights(vgg)
+    _step(tr, cuda_device, content, style, gt)
+    y_nat = tr.debug_read("expand_last/out").reshape((batch,) + OUT_SHAPE).astype(np.float64)
+    g_nat = tr.debug_read("expand_last/out", want_grad=True).reshape(y_nat.shape) / (y_nat * (1 - y_nat))
+    _, vjp_grads, ref_pred = O.training_forward_backward(spec, tw, "DUMMY", pw, vgg, content, style, gt, pred_grad=g_nat)
+    _, vjp32, _ = O.training_forward_backward(spec, tw, "DUMMY", pw, vgg, content, style, gt, pred_grad=g_nat, dtype=torch.float32)
+    err = np.abs(tr.read_prediction(batch) - ref_pred.numpy()).max()
+    print("split-tf32 trunk: prediction max abs err", err)
+    assert err < 1e-4
+    worst = 0.0
+    for name, g in vjp_grads.items():
+        ref = g.numpy()
+        norm = np.sqrt((ref ** 2).sum())
+        rel = np.sqrt(((tr.read_gradient(name, tuple(g.shape)) - ref) ** 2).sum()) / max(norm, 1e-300)
+        rel32 = np.sqrt(((vjp32[name].double().numpy() - ref) ** 2).sum()) / max(norm, 1e-300)
+        worst = max(worst, rel if rel32 < 1 else 0.0)
+        assert rel < VJP_TOL or rel <= 4 * rel32, (name, rel, rel32)
+    print("split-tf32 trunk: worst vjp rel l2", worst)
+    tr.close()
