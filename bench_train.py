@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--filters", type=int, default=128)
     ap.add_argument("--math", default="default", choices=["default", "fp32", "tf32"],
-                    help="default: fp32 transfer net + tf32 loss model; fp32: everything fp32; tf32: trunk convs and loss model in tf32")
+                    help="default = fp32: split-tf32 tensor-core convs (fp32-level accuracy); tf32: plain tf32 operands")
     args = ap.parse_args()
     rank, world, local = rdist.env_rank()
     dev = torch.device("cuda", local)
@@ -49,8 +49,6 @@ def main():
                                device=local)
     if args.math == "tf32":
         tr.set_math(_native.PRECISION_TF32)
-    elif args.math == "fp32":
-        tr.loss.set_math(_native.PRECISION_FP32)
     tr.model.set_weights(weights)
     vgg = {}
     cin = 3
@@ -96,7 +94,7 @@ def main():
         print(json.dumps({
             "metric": "training_samples_per_second", "value": b * world / (dt / args.steps), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "dtype": {"default": "f32 (loss model tf32)", "fp32": "f32", "tf32": "tf32"}[args.math], "data": "synthetic",
+            "scaling": "weak", "dtype": {"default": "f32 (split tf32 on tensor cores)", "fp32": "f32 (split tf32 on tensor cores)", "tf32": "tf32"}[args.math], "data": "synthetic",
             "config": {"workload": f"train-{w}-{h // 4}-{f}-17 B={b}/GPU, {args.extractor} predictor, VGG16 loss, RMSprop"},
             "approx_tflops_per_gpu": flop_per_sample * b / (dt / args.steps) / 1e12,
             "loss": float(losses[:, 0].mean().item()),

@@ -34,8 +34,11 @@ enum rst_status {
 enum rst_precision {
     RST_PRECISION_FP32 = 0,  /* CUDA-core fp32 path, bar: max abs err <= 1e-4 vs the oracle */
     RST_PRECISION_BF16 = 1,  /* tcgen05 bf16 path (fp32 accumulate), bar: <= 2e-2 relative */
-    RST_PRECISION_TF32 = 2   /* tcgen05 tf32 operands on fp32 tensors (what TensorFlow itself does with fp32 convolutions on
-                              * Ampere and later GPUs); operator level and the VGG16 loss model only, see rst_loss_set_math */
+    RST_PRECISION_TF32 = 2,  /* tcgen05 tf32 operands on fp32 tensors (what TensorFlow itself does with fp32 convolutions on
+                              * Ampere and later GPUs); operator level, the loss model and the training step only, see
+                              * rst_loss_set_math / rst_train_set_math */
+    RST_PRECISION_TF32X3 = 3 /* rst_op_conv2d only: error-compensated split tf32 (the arithmetic behind RST_PRECISION_FP32 in
+                              * rst_loss_set_math / rst_train_set_math), for operator-level parity tests */
 };
 
 enum rst_extractor {         /* stylePrediction.StyleFeatureExtractor, stylePrediction.py:19-22 */
@@ -155,9 +158,10 @@ int rst_loss_set_weight(rst_loss* loss, const char* name, const float* h_data, c
 int rst_loss_commit(rst_loss* loss);
 /* content / style / total-variation factors (defaults 1e4, 1e-3, 1e-1: styleLoss.py:101-104) */
 int rst_loss_set_factors(rst_loss* loss, float content, float style, float tv);
-/* Arithmetic of the VGG16 convolutions with >= 64 input channels and of their input gradients: RST_PRECISION_TF32 (default:
- * tf32 operands on the tensor cores, fp32 accumulation -- TensorFlow's own default for float32 convolutions on Ampere and
- * later) or RST_PRECISION_FP32 (CUDA-core fp32).  Takes effect at the next rst_loss_commit. */
+/* Arithmetic of the VGG16 convolutions with >= 64 input channels and of their input gradients (both on the tensor cores).
+ * RST_PRECISION_FP32 (default): error-compensated split tf32, x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation =
+ * fp32-level accuracy.  RST_PRECISION_TF32: plain tf32 operands -- TensorFlow's own default for float32 convolutions on Ampere
+ * and later -- a third of the tensor work, loss scalars still within 1e-3.  Takes effect at the next rst_loss_commit. */
 int rst_loss_set_math(rst_loss* loss, int precision);
 /* compute_loss(y_pred, y_true) (styleLoss.py:363-367): d_losses (B,4) = [loss, feature_loss, style_loss,
  * total_variation_loss], each a per-sample value like the reference's (B,) vectors. */
@@ -177,10 +181,11 @@ int rst_train_destroy(rst_trainer* trainer);
 const char* rst_train_last_error(const rst_trainer* trainer);
 /* The trainer's model / loss contexts: set variables with rst_set_weight + rst_commit_weights and rst_loss_set_weight +
  * rst_loss_commit before the first step.  The model context also serves rst_transfer_forward / rst_predict_style. */
-/* Arithmetic of the step.  RST_PRECISION_FP32 (default): fp32 transfer network and predictor; the loss model keeps its own
- * setting (rst_loss_set_math, tf32 by default).  RST_PRECISION_TF32: additionally runs the 3x3 convolutions of the residual
- * trunk (forward and input gradient) on the tensor cores with tf32 operands -- TensorFlow's behaviour for float32 models on
- * Ampere and later -- and sets the loss model to tf32.  Call before rst_commit_weights / rst_loss_commit. */
+/* Arithmetic of the step's tensor-core convolutions (the residual trunk of the transfer network, forward and input gradient,
+ * and the loss model): RST_PRECISION_FP32 (default) = error-compensated split tf32 with fp32-level accuracy;
+ * RST_PRECISION_TF32 = plain tf32 operands (TensorFlow's behaviour for float32 models on Ampere and later).  Everything else
+ * (predictor, 9x9 / strided / transposed layers, weight gradients, normalisation) is fp32 either way.
+ * Call before rst_commit_weights / rst_loss_commit. */
 int rst_train_set_math(rst_trainer* trainer, int precision);
 rst_ctx* rst_train_model(rst_trainer* trainer);
 rst_loss* rst_train_loss(rst_trainer* trainer);

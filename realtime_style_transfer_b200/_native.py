@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librst_sm100.so")
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_TF32 = 2
+PRECISION_TF32X3 = 3
 EXTRACTOR_NONE, EXTRACTOR_DUMMY, EXTRACTOR_MOBILE_NET = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 4
 
@@ -364,7 +365,8 @@ class NativeLoss:
         self._check(self.lib.rst_loss_commit(self.handle))
 
     def set_math(self, precision: int):
-        """PRECISION_TF32 (default) or PRECISION_FP32 for the VGG16 convolutions; call before set_weights (commit)."""
+        """PRECISION_FP32 (default: split tf32, fp32-level accuracy) or PRECISION_TF32 (plain tf32) for the VGG16 convolutions;
+        call before set_weights (commit)."""
         self._check(self.lib.rst_loss_set_math(self.handle, int(precision)))
 
     def set_factors(self, content: float, style: float, tv: float):

@@ -96,8 +96,8 @@ cudaError_t Tf32Conv3x3::repack(const float* d_kernel, const float* d_bias, cuda
 }
 
 bool Tf32Conv3x3::setup(int ci_layer_, int co_layer_, const float* k, const float* bias_host, bool relu_, bool input_gradient_,
-                        std::string* err) {
-    if (!setup_shape(ci_layer_, co_layer_, relu_, input_gradient_, err)) return false;
+                        std::string* err, bool split_) {
+    if (!setup_shape(ci_layer_, co_layer_, relu_, input_gradient_, err, split_)) return false;
     float* d_k = nullptr;
     const size_t kelems = (size_t)9 * ci_layer_ * co_layer_;
     cudaError_t e = cudaMalloc(&d_k, kelems * sizeof(float));

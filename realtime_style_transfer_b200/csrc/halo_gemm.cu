@@ -170,11 +170,23 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t sA16 = __shfl_sync(0xffffffffu, smem_u32(sA) >> 4, 0);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t a_stage16 = (uint32_t)a_stage_bytes >> 4;
+            // CHUNK (tf32 kernels): every channel group accumulates into a FRESH accumulator stage and the epilogue warps add the
+            // partial sums in registers.  The tensor core truncates (rounds toward zero) at every accumulate step: measured
+            // ~2^-25 relative per MMA, i.e. 4e-5 after the 1728 MMAs of a split-tf32 512-channel layer -- a bias that
+            // compounds over VGG16's 13 layers.  Chains of 36 MMAs plus round-to-nearest fp32 adds outside remove it.
+            constexpr bool CHUNK = (MODE & MODE_TF32) != 0;
             for (int t = tile_begin; t < tile_end; ++t) {
-                mbar_wait(&acc_empty[cs], cph ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_u + cs * N;
+                if (!CHUNK) {
+                    mbar_wait(&acc_empty[cs], cph ^ 1);
+                    tc_fence_after();
+                }
+                uint32_t tmem_d = tmem_u + cs * N;
                 for (int g = 0; g < p.n_groups; ++g) {
+                    if (CHUNK) {
+                        mbar_wait(&acc_empty[cs], cph ^ 1);
+                        tc_fence_after();
+                        tmem_d = tmem_u + cs * N;
+                    }
                     mbar_wait(&a_full[as], aph);
                     tc_fence_after();
                     const uint32_t a_base16 = sA16 + as * a_stage16;
@@ -190,7 +202,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint64_t db = db_const | (uint64_t)(sched_b_units(SCH) ? sB16 + sched_b_off16(SCH, ks)
                                                                                     : b_base16 + (BRES ? (ks / 4) * (BBLK / 16) : 0) + (ks & 3) * 2);
                         if (leader) {
-                            if (MODE & MODE_TF32) mma_tf32_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
+                            if (MODE & MODE_TF32) mma_tf32_ss(tmem_d, da, db, idesc, ks == 0 ? 0u : 1u);
                             else mma_f16_ss(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
                         }
                         if (!BRES && (ks & 3) == 3) {
@@ -200,9 +212,15 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     if (leader) mma_commit(&a_empty[as]);
                     if (++as == (uint32_t)p.n_astages) { as = 0; aph ^= 1; }
+                    if (CHUNK) {
+                        if (leader) mma_commit(&acc_full[cs]);
+                        if (++cs == 2) { cs = 0; cph ^= 1; }
+                    }
                 }
-                if (leader) mma_commit(&acc_full[cs]);
-                if (++cs == 2) { cs = 0; cph ^= 1; }
+                if (!CHUNK) {
+                    if (leader) mma_commit(&acc_full[cs]);
+                    if (++cs == 2) { cs = 0; cph ^= 1; }
+                }
             }
         }
     } else if (warp < 3 + 4 * ESPLIT) {
@@ -371,6 +389,34 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr int CPW = NCH / ESPLIT;        // chunks per warp: 1 or 2
             static_assert(CPW == 1 || CPW == 2, "epilogue warp handles one or two chunks");
             float va[32], vb[32];
+            if constexpr ((MODE & MODE_TF32) != 0) {
+                // partial sums of all channel groups but the last: read, release the stage, add (fp32, round to nearest)
+                float part[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) part[j] = 0.f;
+                for (int g = 0; g + 1 < p.n_groups; ++g) {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cs * N + c_begin * 32, va);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[cs]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) part[j] += va[j];
+                    if (++cs == 2) { cs = 0; cph ^= 1; }
+                    mbar_wait(&acc_full[cs], cph);
+                    tc_fence_after();
+                }
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cs * N + c_begin * 32, va);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[cs]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) va[j] += part[j];
+                process(va, c_begin);
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+                continue;
+            }
             if (CW == 32) tmem_ld_32x32(taddr + c_begin * 32, va);
             else {
                 tmem_ld_32x16(taddr + c_begin * 16, va);

@@ -193,7 +193,8 @@ struct Tf32Conv3x3 {
     ~Tf32Conv3x3();
     // k: Keras kernel (3,3,ci_layer,co_layer).  input_gradient = false: y = [relu](conv(x, k) + bias), ci = ci_layer.
     // input_gradient = true: y = d conv / d input applied to x = gradient w.r.t. the layer output (ci = co_layer, co = ci_layer).
-    bool setup(int ci_layer, int co_layer, const float* k, const float* bias_host, bool relu, bool input_gradient, std::string* err);
+    bool setup(int ci_layer, int co_layer, const float* k, const float* bias_host, bool relu, bool input_gradient, std::string* err,
+               bool split = false);
     // Same without weights: allocate and plan only; repack() then (re)builds the packed tf32 weights from a DEVICE kernel
     // tensor (3,3,ci_layer,co_layer), e.g. once per training step after the optimizer moved the variables.
     // split = true: error-compensated "3 x tf32" arithmetic with fp32-level accuracy: x = x_hi + x_lo, w = w_hi + w_lo (each part

@@ -171,7 +171,9 @@ struct rst_loss {
     int last_batch = 0;
     int64_t launches = 0;
     // tf32 tensor-core convolutions for the 12 layers with >= 64 input channels (conv_tf32.cu), forward and input gradient
-    int math = RST_PRECISION_TF32;
+    int math = RST_PRECISION_FP32;       // FP32: split tf32 on the tensor cores (fp32-level accuracy); TF32: plain tf32 operands
+    float* split_scratch = nullptr;      // [x_hi | x_lo | x_hi] expansion of the largest conv input
+    size_t split_scratch_floats = 0;
     int num_sms = 148;
     std::unique_ptr<Tf32Conv3x3> fwd[13], bwd[13];
 };
@@ -191,6 +193,7 @@ extern "C" int rst_loss_destroy(rst_loss* c) {
     for (int i = 0; i < 4; ++i) { if (c->gram_style[i]) cudaFree(c->gram_style[i]); if (c->gram_pred[i]) cudaFree(c->gram_pred[i]); }
     if (c->red) cudaFree(c->red);
     if (c->style_norm_dev) cudaFree(c->style_norm_dev);
+    if (c->split_scratch) cudaFree(c->split_scratch);
     delete c;
     return RST_OK;
 }
@@ -275,26 +278,39 @@ extern "C" int rst_loss_commit(rst_loss* c) {
             LCUDA(c, cudaMemcpy(d, it->second.data(), it->second.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
     for (int i = 0; i < 13; ++i) { c->fwd[i].reset(); c->bwd[i].reset(); }
-    if (c->math == RST_PRECISION_TF32) {
+    const bool cuda_core_only = c->math == RST_PRECISION_FP32 && getenv("RST_LOSS_CUDA_CORE") != nullptr;
+    if (!cuda_core_only) {
+        const bool split = c->math == RST_PRECISION_FP32;
         cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
         std::string err;
+        size_t need = 0;
         for (int i = 1; i < 13; ++i) {
             const std::vector<float>& k = c->host_w[kVgg[i].name + "/kernel"];
             const std::vector<float>& b = c->host_w[kVgg[i].name + "/bias"];
             c->fwd[i].reset(new Tf32Conv3x3());
             c->bwd[i].reset(new Tf32Conv3x3());
-            if (!c->fwd[i]->setup(kVgg[i].ci, kVgg[i].co, k.data(), b.data(), true, false, &err) ||
-                !c->bwd[i]->setup(kVgg[i].ci, kVgg[i].co, k.data(), nullptr, false, true, &err))
+            if (!c->fwd[i]->setup(kVgg[i].ci, kVgg[i].co, k.data(), b.data(), true, false, &err, split) ||
+                !c->bwd[i]->setup(kVgg[i].ci, kVgg[i].co, k.data(), nullptr, false, true, &err, split))
                 return lfail(c, RST_ERR_CUDA, "rst_loss_commit: " + err);
+            need = std::max(need, c->fwd[i]->scratch_floats(c->max_batch, c->lh[i], c->lw[i]));
+            need = std::max(need, c->bwd[i]->scratch_floats(c->max_batch, c->lh[i], c->lw[i]));
+        }
+        if (need > c->split_scratch_floats) {
+            if (c->split_scratch) cudaFree(c->split_scratch);
+            c->split_scratch = nullptr; c->split_scratch_floats = 0;
+            LCUDA(c, cudaMalloc(&c->split_scratch, need * sizeof(float)));
+            c->split_scratch_floats = need;
         }
     }
     c->committed = true;
     return RST_OK;
 }
 
-// RST_PRECISION_FP32: CUDA-core fp32 convolutions everywhere.  RST_PRECISION_TF32 (default): the 12 convolutions with >= 64 input
-// channels and their input gradients run on the tensor cores with tf32 operands and fp32 accumulation -- what TensorFlow does
-// with float32 convolutions on Ampere-and-later GPUs unless tf.config.experimental.enable_tensor_float_32_execution(False).
+// The 12 convolutions with >= 64 input channels and their input gradients run on the tensor cores.  RST_PRECISION_FP32 (default):
+// error-compensated split tf32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation) = fp32-level accuracy.
+// RST_PRECISION_TF32: plain tf32 operands -- what TensorFlow does with float32 convolutions on Ampere-and-later GPUs unless
+// tf.config.experimental.enable_tensor_float_32_execution(False); ~3x less tensor work, losses still within 1e-3.
+// (Environment RST_LOSS_CUDA_CORE=1 with FP32 math: CUDA-core fp32 convolutions everywhere, the slow cross-check.)
 extern "C" int rst_loss_set_math(rst_loss* c, int precision) {
     if (!c) return RST_ERR_INVALID;
     if (precision != RST_PRECISION_FP32 && precision != RST_PRECISION_TF32)
@@ -327,7 +343,7 @@ static int vgg_forward(rst_loss* c, const float* img, int batch, bool keep, cuda
         float* y = keep ? c->act[i] : (flip ? c->sb : c->sa);
         if (c->fwd[i] && !getenv("RST_EXP_LOSS_FWD_FP32")) {
             std::string err;
-            cudaError_t e = c->fwd[i]->run(cur, y, batch, c->lh[i], c->lw[i], c->num_sms, s, &err);
+            cudaError_t e = c->fwd[i]->run_split(cur, c->split_scratch, y, batch, c->lh[i], c->lw[i], c->num_sms, s, &err);
             if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "tf32 conv " + kVgg[i].name + ": " + (err.empty() ? cudaGetErrorString(e) : err));
             c->launches += c->fwd[i]->nblk;
         } else {
@@ -446,7 +462,7 @@ extern "C" int rst_loss_backward(rst_loss* c, const float* d_pred, float* d_grad
         relu_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(g, c->act[i], n);
         if (c->bwd[i] && !getenv("RST_EXP_LOSS_BWD_FP32")) {      // (env: experiment switch, see profiles/r01_03_experiments.md)
             std::string err;
-            cudaError_t e = c->bwd[i]->run(g, gn, B, c->lh[i], c->lw[i], c->num_sms, s, &err);
+            cudaError_t e = c->bwd[i]->run_split(g, c->split_scratch, gn, B, c->lh[i], c->lw[i], c->num_sms, s, &err);
             if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "tf32 dgrad " + kVgg[i].name + ": " + (err.empty() ? cudaGetErrorString(e) : err));
             std::swap(g, gn);
             continue;

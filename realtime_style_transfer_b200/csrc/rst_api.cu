@@ -1039,7 +1039,8 @@ extern "C" int rst_op_conv2d(const float* d_x, const float* d_kernel, const floa
         if (rc) return op_fail(rc, err);
         return RST_OK;
     }
-    if (precision == RST_PRECISION_TF32) {
+    if (precision == RST_PRECISION_TF32 || precision == RST_PRECISION_TF32X3) {
+        const bool split = precision == RST_PRECISION_TF32X3;
         if (kh != 3 || kw != 3 || stride != 1 || ci % 32 || co % 64 || (act != ACT_RELU && act != ACT_NONE))
             return op_fail(RST_ERR_UNSUPPORTED, "rst_op_conv2d(tf32): 3x3 stride-1 convs with Cin % 32 == 0, Cout % 64 == 0 only");
         std::vector<float> hk((size_t)9 * ci * co), hb(co, 0.f);
@@ -1048,15 +1049,18 @@ extern "C" int rst_op_conv2d(const float* d_x, const float* d_kernel, const floa
         Tf32Conv3x3 conv;
         std::string err;
         // a stride-1 'same' Conv2DTranspose with kernel (3,3,co,ci) is the input gradient of the conv layer co -> ci with that kernel
-        const bool ok = transposed ? conv.setup(co, ci, hk.data(), d_bias ? hb.data() : nullptr, act == ACT_RELU, true, &err)
-                                   : conv.setup(ci, co, hk.data(), d_bias ? hb.data() : nullptr, act == ACT_RELU, false, &err);
+        const bool ok = transposed ? conv.setup(co, ci, hk.data(), d_bias ? hb.data() : nullptr, act == ACT_RELU, true, &err, split)
+                                   : conv.setup(ci, co, hk.data(), d_bias ? hb.data() : nullptr, act == ACT_RELU, false, &err, split);
         if (!ok) return op_fail(RST_ERR_CUDA, err);
+        float* scratch = nullptr;
+        if (split) OP_CUDA(cudaMalloc(&scratch, conv.scratch_floats(batch, h, w) * sizeof(float)));
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = conv.run(d_x, d_y, batch, h, w, sms, s, &err);
+        cudaError_t e = conv.run_split(d_x, scratch, d_y, batch, h, w, sms, s, &err);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (scratch) cudaFree(scratch);
         if (e != cudaSuccess) return op_fail(RST_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
-        OP_CUDA(cudaStreamSynchronize(s));
         return RST_OK;
     }
     ConvF32 p;

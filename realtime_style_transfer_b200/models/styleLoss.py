@@ -76,8 +76,9 @@ class StyleLossModelVGG(StyleLossModelBase):
                 cin = co
         self._native = None
         self._dirty = True
-        # arithmetic of the VGG convolutions: tf32 tensor cores (TensorFlow's own default on Ampere and later) or fp32
-        self.math = _native.PRECISION_TF32
+        # arithmetic of the VGG convolutions on the tensor cores: PRECISION_FP32 = split tf32 (fp32-level accuracy, default),
+        # PRECISION_TF32 = plain tf32 operands (TensorFlow's own default on Ampere and later; faster, losses within 1e-3)
+        self.math = _native.PRECISION_FP32
 
     @property
     def weights(self):

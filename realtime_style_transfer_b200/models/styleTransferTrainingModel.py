@@ -55,8 +55,8 @@ class StyleTransferTrainingModel(NativeModel):
         self._host_stale = False
         self._grad_tensor = None
         self._mirrored = None       # variable versions of the sub-models the trainer's device copy corresponds to
-        # _native.PRECISION_TF32 runs the residual trunk's convolutions and the loss model on the tensor cores with tf32
-        # operands (TensorFlow's behaviour for float32 models on Ampere and later); the default keeps the networks in fp32
+        # the tensor-core convolutions (residual trunk, loss model) use error-compensated split tf32 = fp32-level accuracy;
+        # _native.PRECISION_TF32 switches them to plain tf32 operands (TensorFlow's behaviour on Ampere and later, faster)
         self.math = _native.PRECISION_FP32
 
     def _versions(self):
@@ -133,7 +133,7 @@ class StyleTransferTrainingModel(NativeModel):
             if self.math == _native.PRECISION_TF32:
                 self._trainer.set_math(_native.PRECISION_TF32)
             else:
-                self._trainer.loss.set_math(getattr(lm, "math", _native.PRECISION_TF32))
+                self._trainer.loss.set_math(getattr(lm, "math", _native.PRECISION_FP32))
             self._trainer.loss.set_weights(lm.weights)
             self._trainer.loss.set_factors(lm.content_loss_factor, lm.style_loss_factor, lm.total_variation_loss_factor)
             self._mirrored = self._versions()

@@ -129,6 +129,33 @@ def test_op_conv2d_tf32(cuda_device, b, h, w, ci, co, relu, transposed):
     assert e_exact < 2e-3
 
 
+@pytest.mark.parametrize("b,h,w,ci,co,relu,transposed", [
+    (2, 16, 32, 64, 64, True, False),
+    (1, 30, 60, 128, 256, True, False),
+    (1, 9, 21, 512, 512, True, False),
+    (2, 12, 20, 128, 64, False, True),
+    (1, 15, 30, 512, 256, False, True),
+])
+def test_op_conv2d_split_tf32(cuda_device, b, h, w, ci, co, relu, transposed):
+    """Error-compensated split tf32 (three tensor-core products per fp32 product) with per-channel-group accumulation chains
+    summed in fp32 by the epilogue: fp32-level accuracy (7e-7 measured).  With ONE long chain in the tensor core the same
+    kernel is 10-60x less accurate (1e-5 .. 4.4e-5, growing with the number of MMAs): the accumulate step truncates."""
+    rng = np.random.default_rng(ci + co + h + 1)
+    x = rng.standard_normal((b, h, w, ci)).astype(np.float32)
+    kern = (rng.standard_normal((3, 3, co, ci) if transposed else (3, 3, ci, co)) * np.sqrt(2.0 / (9 * ci))).astype(np.float32)
+    bias = rng.standard_normal(co).astype(np.float32)
+    f = O.conv2d_transpose_same if transposed else O.conv2d_same
+    ref = f(torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(kern, dtype=torch.float64), torch.as_tensor(bias, dtype=torch.float64), 1)
+    ref = (torch.relu(ref) if relu else ref).numpy()
+    d_y = torch.full(ref.shape, float("nan"), device=cuda_device)
+    d_x, d_k, d_b = dev(x, cuda_device), dev(kern, cuda_device), dev(bias, cuda_device)
+    _native.op_conv2d(d_x.data_ptr(), d_k.data_ptr(), d_b.data_ptr(), d_y.data_ptr(), b, h, w, ci, co, 3, 3, 1, transposed,
+                      _native.ACT_RELU if relu else _native.ACT_NONE, _native.PRECISION_TF32X3, stream())
+    err = np.abs(d_y.cpu().numpy() - ref).max() / np.abs(ref).max()
+    print(f"split tf32 conv {ci}->{co}: max err relative to max |y| {err:.2e}")
+    assert err < 5e-6
+
+
 def test_op_apply_style_weights_known_answer(cuda_device):
     """The reference's own known-answer test, run through the CUDA operator."""
     g = np.load(os.path.join(GOLDEN, "apply_style_weights_known_answer.npz"))

@@ -33,7 +33,7 @@ def _setup(extractor_name, batch, seed=0):
     return spec, tw, pw, vgg, content, style, gt
 
 
-def _trainer(extractor, batch, tw, pw, vgg, math=_native.PRECISION_TF32):
+def _trainer(extractor, batch, tw, pw, vgg, math=_native.PRECISION_FP32):
     tr = _native.NativeTrainer(in_shape=IN_SHAPE, out_shape=OUT_SHAPE, bottleneck_res_y=RES_Y, bottleneck_num_filters=FILTERS,
                                max_batch=batch, extractor=extractor, style_shape=OUT_SHAPE[:2])
     tr.model.set_weights({**tw, **pw})
