@@ -12,21 +12,26 @@ import numpy as np
 from . import exr
 
 
+_RGB = ("R", "G", "B")
+
+
+def _planes_of(image: "exr.ExrImage", count: int) -> np.ndarray:
+    """(H, W, count) from one EXR: RGB order for colour planes, the red channel for scalar planes (Unreal writes scalars
+    into R), file order otherwise."""
+    if count == 3:
+        names = _RGB
+    elif count == 1:
+        names = _RGB[:1]
+    else:
+        names = tuple(image.channels())
+    return np.stack([image.channel(n) for n in names], axis=-1)
+
+
 def load_unreal_hdr_screenshot(base_png_filepath, expected_channels):
-    base_png_filepath = Path(base_png_filepath)
-    channel_list = []
-    for channel_name, num_channels in expected_channels:
-        channel_path = base_png_filepath.parent / f"{base_png_filepath.stem}_{channel_name}.exr"
-        exr_data = exr.load(channel_path)
-        if num_channels == 3:
-            image_tensor = np.stack([exr_data.channel('R'), exr_data.channel('G'), exr_data.channel('B')], axis=-1)
-        elif num_channels == 1:
-            image_tensor = np.expand_dims(exr_data.channel('R'), axis=-1)
-        else:
-            image_tensor = np.stack([channel for _, channel in exr_data.channels().items()], axis=-1)
-        channel_list.append(image_tensor)
-    all_channels = np.concatenate(channel_list, axis=-1).astype(np.float32, copy=False)
-    return all_channels, base_png_filepath
+    """Returns ((H, W, sum of plane widths) float32, the png path), planes concatenated in ``expected_channels`` order."""
+    png = Path(base_png_filepath)
+    stack = [_planes_of(exr.load(png.with_name(f"{png.stem}_{name}.exr")), width) for name, width in expected_channels]
+    return np.concatenate(stack, axis=-1).astype(np.float32, copy=False), png
 
 
 def iter_unreal_hdr_screenshots(content_image_dir, expected_channels, batch: int = 1):
