@@ -610,6 +610,21 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
             ctx->launches = g.launches;
             return RST_OK;
         }
+    // capture only when this exact set of buffers comes back: callers that pass fresh device tensors on every call would
+    // otherwise pay a capture + instantiate per call
+    {
+        bool seen = false;
+        for (auto& g : ctx->graph_candidates)
+            seen = seen || (g.batch == batch && g.content == d_content && g.params == d_style_params && g.weights == d_style_weights &&
+                            g.out == d_out);
+        if (!seen) {
+            rst_ctx::GraphEntry k;
+            k.batch = batch; k.content = d_content; k.params = d_style_params; k.weights = d_style_weights; k.out = d_out;
+            if (ctx->graph_candidates.size() >= 16) ctx->graph_candidates.erase(ctx->graph_candidates.begin());
+            ctx->graph_candidates.push_back(k);
+            return run();
+        }
+    }
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
         return run();

@@ -101,6 +101,7 @@ struct rst_ctx {
         cudaGraphExec_t exec = nullptr; int64_t launches = 0;
     };
     std::vector<GraphEntry> graphs;
+    std::vector<GraphEntry> graph_candidates;   // buffer sets seen once (captured when they come back)
     bool use_graphs = true;
 
     // ---- debug / accounting ----
