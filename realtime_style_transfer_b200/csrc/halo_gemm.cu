@@ -41,7 +41,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
 }
 
 constexpr int kTailBytes = 6400;    // barriers (256) + per-column bias/scale/shift (3*N*4) + per-warp stats (4*2*N*4)
-constexpr int kMaxKsteps = 128;
 
 // MODE bits: what the epilogue does besides "+ bias" (compile-time so that the epilogue stays small: an epilogue
 // that does not fit the instruction cache is fetch-bound, see profiles/r01_01_icache.md)
@@ -257,8 +256,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         atomicAdd(dst, (double)s1);
                         atomicAdd(dst + 1, (double)s2);
                     }
-                    return;
-                }
+                } else {
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; ++c) {
                     const int col = c * CW + lane;
@@ -274,6 +272,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         my_sum[col] = 0.f; my_sq[col] = 0.f;
                     }
+                }
                 }
             }
         };

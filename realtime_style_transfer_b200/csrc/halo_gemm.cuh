@@ -131,7 +131,6 @@ struct HaloGemmParams {
     int store_exact = 0;                 // MODE_TF32: store the fp32 accumulator as is (split-tf32 convs) instead of rounding to tf32
 };
 
-constexpr int kHaloThreads = 352;    // warps: 0 A-TMA, 1 B-TMA, 2 MMA, 3..10 epilogue (two per TMEM lane quadrant)
 constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4, HALO_MODE_TF32 = 8;
 
 struct HaloGemmLaunch {

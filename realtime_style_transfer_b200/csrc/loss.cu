@@ -140,10 +140,6 @@ __global__ void finalize_losses_kernel(const double* __restrict__ feat, const do
     out[n * 4 + 2] = (float)s;
     out[n * 4 + 3] = (float)t;
 }
-__global__ void add_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] += b[i];
-}
 
 inline unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 

@@ -313,7 +313,6 @@ struct Bf16State {
             if (q) cudaFree(q);
     }
 };
-struct TrainState {};
 
 int bf16_create(rst_ctx* c) {
     const rst_config& g = c->cfg;
