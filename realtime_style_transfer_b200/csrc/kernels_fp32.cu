@@ -220,11 +220,22 @@ __global__ void moments_f32_kernel(const float* __restrict__ x, double* __restri
         const int g = threadIdx.x / C;
         double s = 0.0, q = 0.0;
         if (g < G) {
-            for (int pp = p0 + g; pp < p1; pp += G) {
+            // four independent loads and accumulator pairs in flight (one dependent fp64 chain per load is latency bound)
+            double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
+            int pp = p0 + g;
+            for (; pp + 3 * G < p1; pp += 4 * G) {
+                const float f0 = __ldg(xb + (long long)pp * C + c), f1 = __ldg(xb + (long long)(pp + G) * C + c);
+                const float f2 = __ldg(xb + (long long)(pp + 2 * G) * C + c), f3 = __ldg(xb + (long long)(pp + 3 * G) * C + c);
+                const double v0 = f0, v1 = f1, v2 = f2, v3 = f3;
+                s += v0; q += v0 * v0; s1 += v1; q1 += v1 * v1; s2 += v2; q2 += v2 * v2; s3 += v3; q3 += v3 * v3;
+            }
+            for (; pp < p1; pp += G) {
                 double v = (double)__ldg(xb + (long long)pp * C + c);
                 s += v;
                 q += v * v;
             }
+            s += s1 + s2 + s3;
+            q += q1 + q2 + q3;
         }
         sm[threadIdx.x] = s;
         sm[blockDim.x + threadIdx.x] = q;
@@ -254,7 +265,9 @@ __global__ void moments_f32_kernel(const float* __restrict__ x, double* __restri
 cudaError_t launch_moments_f32(const float* x, double* stats, int B, int P, int C, cudaStream_t s) {
     if (B == 0 || P == 0) return cudaSuccess;
     int threads = C <= 256 ? C * (256 / C) : 256;
+    // enough CTAs to fill the GPU (8 x 148) even for one small tensor, long enough runs to amortise the atomics
     int pix_per_block = 2048;
+    while (pix_per_block > 256 && (long long)ceil_div(P, pix_per_block) * B < 148 * 8) pix_per_block /= 2;
     dim3 grid((unsigned)ceil_div(P, pix_per_block), (unsigned)B);
     moments_f32_kernel<<<grid, threads, 2 * threads * sizeof(double), s>>>(x, stats, P, C, pix_per_block);
     return cudaGetLastError();
