@@ -488,10 +488,68 @@ __global__ void gram_f32_kernel(const float* __restrict__ x, float* __restrict__
         if (c < C && d < C) atomicAdd(&g[((long long)b * C + c) * C + d], acc[i] * invP);
     }
 }
+// C % 64 == 0 (the VGG16 taps): 64 x 64 tile of G per CTA, 4 x 4 register tile per thread, 128-bit shared-memory reads
+__global__ void __launch_bounds__(256) gram64_f32_kernel(const float* __restrict__ x, float* __restrict__ g, int P, int C,
+                                                         int pix_per_split, float invP) {
+    __shared__ __align__(16) float Fc[32][68];
+    __shared__ __align__(16) float Fd[32][68];
+    const int c0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+    const int splits = ceil_div(P, pix_per_split);
+    const int b = blockIdx.z / splits, sp = blockIdx.z % splits;
+    const int p0 = sp * pix_per_split, p1 = min(P, p0 + pix_per_split);
+    const float* xb = x + (long long)b * P * C;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int pp = p0; pp < p1; pp += 32) {
+        // 32 pixels x 64 channels per operand = 512 float4: two per thread and operand, coalesced along the channels
+#pragma unroll
+        for (int e = threadIdx.x; e < 512; e += 256) {
+            const int r = e >> 4, c4 = (e & 15) * 4, pix = pp + r;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d = a;
+            if (pix < p1) {
+                a = __ldg(reinterpret_cast<const float4*>(xb + (long long)pix * C + c0 + c4));
+                d = __ldg(reinterpret_cast<const float4*>(xb + (long long)pix * C + d0 + c4));
+            }
+            *reinterpret_cast<float4*>(&Fc[r][c4]) = a;
+            *reinterpret_cast<float4*>(&Fd[r][c4]) = d;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&Fc[r][ty * 4]);
+            const float4 d = *reinterpret_cast<const float4*>(&Fd[r][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], dv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            atomicAdd(&g[((long long)b * C + c0 + ty * 4 + i) * C + d0 + tx * 4 + j], acc[i][j] * invP);
+}
+
 cudaError_t launch_gram_f32(const float* x, float* g, int B, int P, int C, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(g, 0, (size_t)B * C * C * sizeof(float), s);
     if (e != cudaSuccess) return e;
+    if (C % 64 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int tiles = (C / 64) * (C / 64);
+        int pix_per_split = 4096;
+        while (pix_per_split > 256 && (long long)ceil_div(P, pix_per_split) * B * tiles < 148 * 4) pix_per_split /= 2;
+        const int splits = ceil_div(P, pix_per_split);
+        dim3 grid((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)(B * splits));
+        gram64_f32_kernel<<<grid, 256, 0, s>>>(x, g, P, C, pix_per_split, 1.f / (float)P);
+        return cudaGetLastError();
+    }
     int pix_per_split = 4096;
     int splits = ceil_div(P, pix_per_split);
     dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(C, 32), (unsigned)(B * splits));

@@ -269,12 +269,21 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ g, const float*
         double s1 = 0.0, s2 = 0.0;
         if (gi < G) {
             const float m = mean ? mean[per_sample ? n * C + c : c] : 0.f, iv = inv ? inv[per_sample ? n * C + c : c] : 1.f;
-            for (int pp = p0 + gi; pp < p1; pp += G) {
+            double t1 = 0.0, t2 = 0.0;
+            int pp = p0 + gi;
+            for (; pp + G < p1; pp += 2 * G) {                      // two independent load pairs / accumulator chains in flight
+                const float ga = g[base + (long long)pp * C + c], gb = g[base + (long long)(pp + G) * C + c];
+                const float xa = (x[base + (long long)pp * C + c] - m) * iv, xb = (x[base + (long long)(pp + G) * C + c] - m) * iv;
+                s1 += ga; s2 += (double)ga * xa;
+                t1 += gb; t2 += (double)gb * xb;
+            }
+            for (; pp < p1; pp += G) {
                 const float gv = g[base + (long long)pp * C + c];
                 const float xh = (x[base + (long long)pp * C + c] - m) * iv;
                 s1 += gv;
                 s2 += (double)gv * xh;
             }
+            s1 += t1; s2 += t2;
         }
         sm[threadIdx.x] = s1;
         sm[T + threadIdx.x] = s2;

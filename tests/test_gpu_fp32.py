@@ -186,10 +186,13 @@ def test_op_cin(cuda_device, styles):
     assert np.abs(d_y.cpu().numpy() - ref.numpy()).max() < 2e-5
 
 
-def test_op_gram(cuda_device):
-    x = np.random.default_rng(0).standard_normal((2, 24, 40, 64)).astype(np.float32)
+@pytest.mark.parametrize("shape", [(2, 24, 40, 64), (1, 30, 61, 128), (2, 9, 11, 24)])
+def test_op_gram(cuda_device, shape):
+    """64-multiple channel counts take the register-tiled kernel, others the generic one; ragged pixel counts."""
+    x = np.random.default_rng(0).standard_normal(shape).astype(np.float32)
     ref = O.gram_matrix(torch.as_tensor(x, dtype=torch.float64)).numpy()
     got = styleLoss.gram_matrix(x)
+    assert got.shape == ref.shape
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
 
 
