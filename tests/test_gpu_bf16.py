@@ -184,6 +184,45 @@ def test_bf16_frames_independent_and_deterministic(cuda_device):
     ctx.close()
 
 
+def test_graph_replay_matches_eager_and_follows_new_inputs(cuda_device):
+    """rst_transfer_forward on device buffers: the first call with a buffer set runs eagerly, the second captures a CUDA graph,
+    later calls replay it.  Replays must read the CURRENT contents of the buffers (not the contents at capture time) and agree
+    with the eager result; a weight commit drops the graphs."""
+    shape_in, shape_out = (64, 128, 17), (64, 128, 3)
+    spec = O.TransferSpec(shape_in, shape_out, 16, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    ctx = _native.NativeContext(in_shape=shape_in, out_shape=shape_out, bottleneck_res_y=16, bottleneck_num_filters=128,
+                                num_styles=1, max_batch=2, precision=_native.PRECISION_BF16)
+    ctx.set_weights(weights)
+    rng = np.random.default_rng(8)
+    params = rng.uniform(0.3, 1.0, (2, 1, spec.num_style_parameters)).astype(np.float32)
+    frames = [O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=17).channels, seed=s, unit_depth=True) for s in (1, 2, 3, 4)]
+    d_content = torch.empty((2,) + shape_in, device=cuda_device)
+    d_params = torch.as_tensor(params).to(cuda_device)
+    d_out = torch.empty((2,) + shape_out, device=cuda_device)
+    stream = torch.cuda.Stream(cuda_device)
+    outs = []
+    with torch.cuda.stream(stream):
+        for f in frames:                                    # same device buffers, new contents: eager, capture, replay, replay
+            d_content.copy_(torch.as_tensor(f))
+            ctx.transfer_forward_device(d_content.data_ptr(), d_params.data_ptr(), None, d_out.data_ptr(), 2, stream.cuda_stream)
+            stream.synchronize()
+            outs.append(d_out.cpu().numpy().copy())
+    for f, got in zip(frames, outs):
+        ref = ctx.transfer_forward_host(f, params)          # separate staging buffers: its own (eager / captured) path
+        assert np.abs(got - ref).max() < 5e-3               # statistics use atomics: order may differ, values agree to rounding
+    assert not np.allclose(outs[2], outs[3])
+    # new weights: graphs captured with the old operands must not be replayed
+    weights2 = O.init_transfer_weights(spec, seed=2)
+    ctx.set_weights(weights2)
+    with torch.cuda.stream(stream):
+        ctx.transfer_forward_device(d_content.data_ptr(), d_params.data_ptr(), None, d_out.data_ptr(), 2, stream.cuda_stream)
+        stream.synchronize()
+    ref2 = O.transfer_forward(spec, weights2, frames[3], params).numpy()
+    assert rel_l2(d_out.cpu().numpy(), ref2) <= BF16_REL_TOL
+    ctx.close()
+
+
 def test_mixed_precision_policy_selects_tensor_core_path(cuda_device):
     mixed_precision.set_global_policy("mixed_bfloat16")
     try:
