@@ -338,7 +338,7 @@ def main():
             "dominant_group": dominant[0],
             "checksum": checksum,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # the CPU arm is timed at N=1 only (its host cores are shared at N>1)
             line["cpu_baseline"] = cpu_baseline_sample(cfg)
         print(json.dumps(line))
     ctx.close()
