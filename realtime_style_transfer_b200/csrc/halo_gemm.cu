@@ -504,6 +504,7 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
     RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU, SCH_C3, true)
     RST_HALO_CASE(64, 64, EPI_NHWC, MODE_RELU, SCH_C3, true)
     RST_HALO_CASE(64, 128, EPI_NHWC, STEM_MODE, SCH_STEM2, true)            // 9x9 stem, 17 channels, two pixels per GEMM row
+    RST_HALO_CASE(64, 128, EPI_NHWC, STEM_MODE, SCH_STEM2B, true)           // 9x9 stem, 18 channels, two pixels per GEMM row
     RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 1, true)      // 9x9 stem, 17 channels: 16 real + 1 windowed
     RST_HALO_CASE(32, 64, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 0, true)      // 5..16 channels
     RST_HALO_CASE(32, 128, EPI_NHWC, STEM_MODE, SCH_STEM + 4 + 2, true)     // 18 channels
@@ -696,6 +697,84 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
     reinterpret_cast<uint4*>(y)[i] = o;
 }
+// 18-channel pair layout (SCH_STEM2B), any even W: one thread per (pixel pair, 8-element group of the 64-element pair row).
+__global__ void pack_stem_pairs18_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W, long long total_groups) {
+    constexpr int C = 18;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_groups) return;
+    const int grp = (int)(i & 7);
+    const long long pair = i >> 3;
+    const int pw = W / 2;
+    const int x0 = (int)(pair % pw) * 2;
+    const float* xp = x + ((pair / pw) * W + x0) * C;                 // the even pixel
+    float v[8];
+    if (grp < 4) {                                                     // real channels of pixel grp / 2
+        const float* q = xp + (grp >> 1) * C + (grp & 1) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = q[j];
+    } else {                                                           // window slots t = 8 * (grp & 1) + j of channel 16 + (grp - 4) / 2
+        const int ch = 16 + ((grp - 4) >> 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = (grp & 1) * 8 + j, sx = x0 + t - 4;
+            v[j] = (t < 10 && sx >= 0 && sx < W) ? xp[(long long)(t - 4) * C + ch] : 0.f;
+        }
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+}
+// Fast variant (W % 64 == 0): one warp per 64-pixel row segment staged in shared memory as in pack_stem_rows_kernel below;
+// each lane assembles ONE pixel pair (128 B), the warp writes its 4 KB of packed pairs as contiguous, coalesced runs.
+__global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
+                                                                    long long total_segments) {
+    constexpr int C = 18, NF4 = 18 * C;                                // 72 pixels x 18 floats
+    extern __shared__ float4 pack_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (seg >= total_segments) return;
+    const int segs_per_row = W / 64;
+    const int sx = (int)(seg % segs_per_row);
+    const long long pix0 = (seg / segs_per_row) * W + sx * 64;
+    float4* s4 = pack_smem + warp * NF4;
+    const float4* g4 = reinterpret_cast<const float4*>(x + (pix0 - 4) * C);
+    const bool left_oob = sx == 0, right_oob = sx == segs_per_row - 1;
+#pragma unroll
+    for (int i = lane; i < NF4; i += 32) {
+        const bool oob = (left_oob && i < C) || (right_oob && i >= 17 * C);
+        s4[i] = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(g4 + i);
+    }
+    __syncwarp();
+    const float* sf = reinterpret_cast<const float*>(s4);
+    const float* px = sf + (4 + 2 * lane) * C;                         // the lane's even pixel; its window starts 4 pixels earlier
+    uint32_t w[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 b = __floats2bfloat162_rn(px[h * C + 2 * j], px[h * C + 2 * j + 1]);
+            w[h * 8 + j] = *reinterpret_cast<uint32_t*>(&b);
+        }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            __nv_bfloat162 b = __floats2bfloat162_rn(px[(2 * j - 4) * C + 16 + g], px[(2 * j - 3) * C + 16 + g]);
+            w[16 + 8 * g + j] = *reinterpret_cast<uint32_t*>(&b);
+        }
+#pragma unroll
+        for (int j = 5; j < 8; ++j) w[16 + 8 * g + j] = 0u;
+    }
+    uint4* so = reinterpret_cast<uint4*>(s4);                          // 32 pairs x 8 vectors = 256 of the slice's 324 float4
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) so[lane * 8 + (j ^ (lane & 7))] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    __syncwarp();
+    uint4* out = reinterpret_cast<uint4*>(y + pix0 * 32);
+#pragma unroll
+    for (int k = lane; k < 256; k += 32) out[k] = so[(k & ~7) + ((k & 7) ^ ((k >> 3) & 7))];
+}
 // Fast path for the G-buffer layouts (16 real channels + NV windowed ones, W % 64 == 0): one warp per 64-pixel row segment.
 // The segment plus a 4-pixel halo on each side is 72*C floats = 18*C aligned float4 (coalesced loads) staged in the warp's
 // own shared-memory slice; each lane then assembles two packed pixels (stride-C reads are bank-conflict free for C = 17).
@@ -784,7 +863,17 @@ cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int 
     long long total = (long long)B * H * W * (row_elems / 8);
     if (total == 0) return cudaSuccess;
     const int nv = C - 16;
-    if (pair_window && (nv != 1 || n_real != 16 || (W & 1))) return cudaErrorInvalidValue;
+    if (pair_window && ((nv != 1 && nv != 2) || n_real != 16 || (W & 1))) return cudaErrorInvalidValue;
+    if (pair_window && nv == 2) {
+        if (row_elems != 32) return cudaErrorInvalidValue;
+        if (W % 64 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            const long long segments = (long long)B * H * (W / 64);
+            pack_stem_pair_rows18_kernel<<<(unsigned)((segments + 7) / 8), 256, (size_t)8 * 18 * 18 * sizeof(float4), s>>>(x, y, W, segments);
+        } else {
+            pack_stem_pairs18_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, W, total);
+        }
+        return cudaGetLastError();
+    }
     if (n_real == 16 && (nv == 1 || nv == 2) && W % 64 == 0 && row_elems == (nv <= 1 ? 32 : 64) &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         const long long segments = (long long)B * H * (W / 64);

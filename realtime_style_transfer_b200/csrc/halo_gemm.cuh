@@ -39,6 +39,9 @@ enum HaloEpi : int {
 // ---- K-step schedules: compile-time A-operand offsets so that the MMA issue loop is fully unrolled ----------------
 // SCH_C3: 3x3 taps x (row_bytes/32) channel slices, halo 10x18.     SCH_T2: 2x2 taps (stride-2 transposed conv), halo 9x17.
 // SCH_HEAD: 9 rows x 12 window pixels over 4-pixel row units, halo 16x18.
+// SCH_STEM2B: the 18-channel variant of SCH_STEM2.  A pair row is [pixel 0: 16 real | pixel 1: 16 real | window of channel 16 |
+//          window of channel 17] (4 x 16 slots = 128 B, both windows x0-4 .. x0+5 shared by the pair): 90 + 9 + 9 K-steps.  Unit
+//          sequences of consecutive row taps share their zero unit ([0, W8..W0] x 9, then one 0) so that everything stays resident.
 // SCH_HEAD8: the same 9x9 transposed conv with EIGHT pixels per GEMM row = two adjacent 4-pixel row units (the A descriptor's
 //          8-row-group stride is doubled): 9 rows x 16 window pixels, N = 8 x (3 + 1 pad) columns, halo 16x35.  A third fewer
 //          K-steps per pixel at the same ~41 cycles per MMA.  B is a block-Toeplitz matrix over 4-row weight units (one per
@@ -54,14 +57,16 @@ enum HaloEpi : int {
 //          TWO ADJACENT units through a shifted SWIZZLE_32B descriptor (the halo trick applied to the weights).
 //          The 17th channel is stored ONCE per pair, as the 10-wide window x0-4 .. x0+5 in the even pixel's spare slots:
 //          one K-step per row tap serves both pixels (units [Wa, Wb] = the 9 taps at slot offsets 0 and 1): 90 + 9 K-steps.
-enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM2 = 4, SCH_HEAD8 = 5, SCH_STEM = 10 };
-__host__ __device__ constexpr bool sched_b_units(int sch) { return sch == SCH_STEM2 || sch == SCH_HEAD8; }
+enum HaloSched : int { SCH_C3 = 0, SCH_T2 = 1, SCH_HEAD = 2, SCH_S2D = 3, SCH_STEM2 = 4, SCH_HEAD8 = 5, SCH_STEM2B = 6, SCH_STEM = 10 };
+__host__ __device__ constexpr bool sched_b_units(int sch) { return sch == SCH_STEM2 || sch == SCH_HEAD8 || sch == SCH_STEM2B; }
 constexpr int kStem2Units = 9 * 11 + 9 * 2 + 2;      // 99 real + 18 window units + 2 zero units (padding K-step)
 constexpr int kStem2Boxes = (kStem2Units * 32 + 255) / 256;   // TMA boxes of 256 rows (8 KB)
 // unit index (1 KB each) where K-step ks of SCH_STEM2 starts reading its 64 B rows
 __host__ __device__ constexpr int sched_b_unit(int sch, int ks) {
     return sch != SCH_STEM2 ? 0 : ks < 90 ? (ks / 10) * 11 + (9 - ks % 10) : 99 + (ks - 90) * 2;
 }
+constexpr int kStem2BUnits = 9 * 10 + 1 + 2 * 9 * 2;              // 91 real + 36 window units (no padding K-step: 108 % 4 == 0)
+constexpr int kStem2BBoxes = (kStem2BUnits * 32 + 255) / 256;     // 16
 // SCH_HEAD8: 9 row taps x 2 copies x 24 units of 4 rows x 32 B (128 B)
 constexpr int kHead8SeqUnits = 24;
 constexpr int kHead8Rows = 9 * 2 * kHead8SeqUnits * 4;                 // 1728 rows of 32 B
@@ -69,22 +74,25 @@ constexpr int kHead8Boxes = (kHead8Rows + 255) / 256;                  // 7 TMA 
 // B start of K-step ks in 16-byte units relative to the start of the resident weights
 __host__ __device__ constexpr int sched_b_off16(int sch, int ks) {
     if (sch == SCH_STEM2) return sched_b_unit(sch, ks) * 64;
+    if (sch == SCH_STEM2B) return (ks < 90 ? (ks / 10) * 10 + (9 - ks % 10) : 91 + (ks - 90) * 2) * 64;
     if (sch == SCH_HEAD8) { const int dy = ks / 16, m0 = 15 - ks % 16, par = m0 & 1; return ((dy * 2 + par) * kHead8SeqUnits + m0 - par) * 8; }
     return 0;
 }
-__host__ __device__ constexpr int sched_b_boxes(int sch) { return sch == SCH_STEM2 ? kStem2Boxes : sch == SCH_HEAD8 ? kHead8Boxes : 0; }
+__host__ __device__ constexpr int sched_b_boxes(int sch) {
+    return sch == SCH_STEM2 ? kStem2Boxes : sch == SCH_STEM2B ? kStem2BBoxes : sch == SCH_HEAD8 ? kHead8Boxes : 0;
+}
 // GEMM rows advance by this many row units along W (SCH_HEAD8: an 8-pixel row = two 4-pixel units)
 __host__ __device__ constexpr int sched_a_unit_stride(int sch) { return sch == SCH_HEAD8 ? 2 : 1; }
 __host__ __device__ constexpr int sched_real_ksteps(int sch, int rowb) {
     return sch == SCH_C3 ? 9 * (rowb / 32) : sch == SCH_T2 ? 4 * (rowb / 32) : sch == SCH_HEAD ? 108
-           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 99 : sch == SCH_HEAD8 ? 144
+           : sch == SCH_S2D ? 3 * (rowb / 32 + rowb / 64) : sch == SCH_STEM2 ? 99 : sch == SCH_STEM2B ? 108 : sch == SCH_HEAD8 ? 144
            : 81 * ((sch - SCH_STEM) / 4) + 9 * ((sch - SCH_STEM) % 4);
 }
 __host__ __device__ constexpr int sched_ksteps(int sch, int rowb) { return (sched_real_ksteps(sch, rowb) + 3) / 4 * 4; }
 __host__ __device__ constexpr int sched_halo_h(int sch) { return sch == SCH_C3 ? 10 : sch == SCH_T2 ? 9 : sch == SCH_S2D ? 18 : 16; }
-__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : sch == SCH_STEM2 ? 20 : sch == SCH_HEAD8 ? 35 : 24; }
+__host__ __device__ constexpr int sched_halo_w(int sch) { return sch == SCH_C3 ? 18 : sch == SCH_T2 || sch == SCH_S2D ? 17 : sch == SCH_HEAD ? 18 : sch == SCH_STEM2 || sch == SCH_STEM2B ? 20 : sch == SCH_HEAD8 ? 35 : 24; }
 __host__ __device__ constexpr int sched_oy(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : -4; }
-__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD || sch == SCH_HEAD8 ? -1 : sch == SCH_STEM2 ? -2 : -4; }
+__host__ __device__ constexpr int sched_ox(int sch) { return sch == SCH_S2D ? 0 : sch == SCH_C3 || sch == SCH_T2 ? -1 : sch == SCH_HEAD || sch == SCH_HEAD8 ? -1 : sch == SCH_STEM2 || sch == SCH_STEM2B ? -2 : -4; }
 // byte offset of K-step ks into the halo patch
 __host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
     if (ks >= sched_real_ksteps(sch, rowb)) return 0;
@@ -92,6 +100,11 @@ __host__ __device__ constexpr int sched_off(int sch, int rowb, int ks) {
     if (sch == SCH_T2) { const int kper = rowb / 32, tap = ks / kper; return ((tap % 2) * 9 + tap / 2) * rowb + (ks % kper) * 32; }
     if (sch == SCH_HEAD) { const int dy = ks / 12, kx = ks % 12; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
     if (sch == SCH_HEAD8) { const int dy = ks / 16, kx = ks % 16; return ((kx / 4) * 16 + dy) * 128 + (kx % 4) * 32; }
+    if (sch == SCH_STEM2B) {
+        if (ks < 90) { const int ky = ks / 10, kxp = ks % 10; return ((kxp / 2) * 16 + ky) * 128 + (kxp % 2) * 32; }
+        const int g = (ks - 90) / 9, ky = (ks - 90) % 9;
+        return (2 * 16 + ky) * 128 + 64 + g * 32;        // the pair's shared window of channel 16 + g
+    }
     if (sch == SCH_STEM2) {
         if (ks < 90) { const int ky = ks / 10, kxp = ks % 10; return ((kxp / 2) * 16 + ky) * 128 + (kxp % 2) * 64; }
         const int ky = ks - 90;
@@ -162,11 +175,11 @@ bool encode_weight_unit_map(CUtensorMap* out, const void* base, int rows, std::s
 size_t halo_gemm2_smem_bytes(int n_groups);
 cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
                               cudaStream_t s);
-// 2-CTA variant of the pair-pixel stem (halo_stem2cta.cu): tmB_units must cover kStem2Boxes * 256 + 32 rows (the peer CTA's
-// copy of the unit array starts one unit later)
-size_t halo_stem2cta_smem_bytes();
-cudaError_t launch_halo_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p, int num_sms,
-                                 cudaStream_t s);
+// 2-CTA variant of the pair-pixel stems (halo_stem2cta.cu; sch = SCH_STEM2 or SCH_STEM2B): tmB_units must cover
+// sched_b_boxes(sch) * 256 + 32 rows (the peer CTA's copy of the unit array starts one unit later)
+size_t halo_stem2cta_smem_bytes(int sch);
+cudaError_t launch_halo_stem2cta(int sch, const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p,
+                                 int num_sms, cudaStream_t s);
 // Packs B: f(kstep, n, e) -> weight of K-step `kstep`, output column n, K element e (0..15).
 void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, int)>& f, std::vector<__nv_bfloat16>* out);
 
@@ -215,6 +228,8 @@ cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long
 // 16 when n_real > 0][one 16-slot group per remaining channel c: x[y, x-4 .. x+4, c] then 7 zeros].
 // pair_window (SCH_STEM2, one windowed channel, even W): the group of an EVEN pixel holds x[y, x-4 .. x+5, c] (10 values, shared
 // by the pixel pair), the group of an odd pixel is zero.
+// pair_window with TWO windowed channels (SCH_STEM2B, C = 18, even W, row_elems = 32 per pixel): a pixel PAIR is stored as
+// [even pixel: 16 real | odd pixel: 16 real | window of channel 16 | window of channel 17], windows as above.
 cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
                                    int pair_window, cudaStream_t s);
 

@@ -12,18 +12,19 @@ namespace rst {
 using namespace umma;
 
 constexpr int kSN = 64;                                             // output columns: 2 pixels x 32 channels
-constexpr int kSKS = sched_ksteps(SCH_STEM2, 128);                  // 100 K-steps (99 real)
 constexpr int kSHalo = sched_halo_h(SCH_STEM2) * sched_halo_w(SCH_STEM2) * 128;   // 16 x 20 row units x 128 B
 constexpr int kSAStage = (kSHalo + 1023) & ~1023;
 constexpr int kSAStages = 2;
-constexpr int kSBBytes = kStem2Boxes * 8192;
 constexpr int kSTail = 6400;
 constexpr int kSThreads = 96 + 128 * 2;                             // 3 control warps + 8 epilogue warps
 
+// SCH = SCH_STEM2 (17 channels, 100 K-steps, 15 weight boxes) or SCH_STEM2B (18 channels, 108 K-steps, 16 weight boxes)
+template <int SCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSThreads, 1)
 halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloGemmParams p) {
     constexpr int N = kSN, CW = 32, NCH = N / CW;
     constexpr uint32_t TMEM_COLS = 2 * N;
+    constexpr int kSKS = sched_ksteps(SCH, 128), kBoxes = sched_b_boxes(SCH), kSBBytes = kBoxes * 8192;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -94,14 +95,14 @@ halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ================= B producer (both CTAs): the whole unit array once; the peer CTA's copy starts one unit later ===
         if (lane == 0 && pair_begin < pair_end) {
             if (leader_cta) mbar_expect_tx(&b_full[0], 2 * kSBBytes);
-            for (int kb = 0; kb < kStem2Boxes; ++kb)
+            for (int kb = 0; kb < kBoxes; ++kb)
                 tma_load_2d_2sm(sB + kb * 8192, &tmB, &b_full[0], 0, kb * 256 + (int)rank * 32);
         }
     } else if (warp == 2) {
         // ================= MMA issuer: leader CTA only ==========================================================
         if (leader_cta) {
             const uint32_t idesc = make_idesc_bf16(256, N);
-            const uint64_t da_const = make_smem_desc(0, 16, sched_halo_h(SCH_STEM2) * 128, SWIZZLE_128B);
+            const uint64_t da_const = make_smem_desc(0, 16, sched_halo_h(SCH) * 128, SWIZZLE_128B);
             const uint64_t db_const = make_smem_desc(0, 16, 256, SWIZZLE_32B);
             const bool issuer = elect_one();
             uint32_t as = 0, aph = 0, cs = 0, cph = 0;
@@ -118,8 +119,8 @@ halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t a_base16 = sA16 + as * (kSAStage >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kSKS; ++ks) {
-                    const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH_STEM2, 128, ks) >> 4));
-                    const uint64_t db = db_const | (uint64_t)(sB16 + sched_b_unit(SCH_STEM2, ks) * 64);
+                    const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH, 128, ks) >> 4));
+                    const uint64_t db = db_const | (uint64_t)(sB16 + sched_b_off16(SCH, ks));
                     if (issuer) mma_f16_ss_2sm(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
                 }
                 if (issuer) mma_commit_2sm(&a_empty[as], 3);
@@ -171,14 +172,15 @@ halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
-size_t halo_stem2cta_smem_bytes() { return (size_t)kSAStages * kSAStage + kSBBytes + kSTail + 1024; }
+size_t halo_stem2cta_smem_bytes(int sch) { return (size_t)kSAStages * kSAStage + sched_b_boxes(sch) * 8192 + kSTail + 1024; }
 
-cudaError_t launch_halo_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p, int num_sms,
-                                 cudaStream_t s) {
+template <int SCH>
+static cudaError_t launch_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p, int num_sms,
+                                   cudaStream_t s) {
     static bool configured = false;
-    const size_t smem = halo_stem2cta_smem_bytes();
+    const size_t smem = halo_stem2cta_smem_bytes(SCH);
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(halo_stem2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(halo_stem2cta_kernel<SCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -187,8 +189,15 @@ cudaError_t launch_halo_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tmB_
     const int pairs = (total + 1) / 2;
     int clusters = num_sms / 2;
     if (pairs < clusters) clusters = pairs;
-    halo_stem2cta_kernel<<<2 * clusters, kSThreads, smem, s>>>(tmA, tmB_units, p);
+    halo_stem2cta_kernel<SCH><<<2 * clusters, kSThreads, smem, s>>>(tmA, tmB_units, p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_halo_stem2cta(int sch, const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p,
+                                 int num_sms, cudaStream_t s) {
+    if (sch == SCH_STEM2B) return launch_stem2cta<SCH_STEM2B>(tmA, tmB_units, p, num_sms, s);
+    if (sch == SCH_STEM2) return launch_stem2cta<SCH_STEM2>(tmA, tmB_units, p, num_sms, s);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace rst

@@ -21,7 +21,7 @@ struct HaloConv {
     HaloGemmLaunch launch;
     HaloGemmParams p;
     CUtensorMap tmA, tmB, tmB_half;
-    bool stem_2cta = false;        // SCH_STEM2: cta_group::2 kernel (halo_stem2cta.cu)
+    bool stem_2cta = false;        // SCH_STEM2 / SCH_STEM2B: cta_group::2 kernel (halo_stem2cta.cu)
     bool two_cta = false;          // 128->128 3x3 convs: cta_group::2 kernel with resident weights
     __nv_bfloat16* w_packed = nullptr;
     float* col_bias = nullptr;     // [N] bias expanded to GEMM columns
@@ -65,7 +65,7 @@ struct HaloConv {
         if (launch.sched == SCH_HEAD8) {
             if (!encode_weight_unit_map(&tmB, w_packed, kHead8Boxes * 256, err)) return false;
         } else if (sched_b_units(launch.sched)) {
-            if (!encode_weight_unit_map(&tmB, w_packed, (kStem2Boxes + 1) * 256, err)) return false;
+            if (!encode_weight_unit_map(&tmB, w_packed, (sched_b_boxes(launch.sched) + 1) * 256, err)) return false;
             const char* env2 = getenv("RST_STEM_2CTA");
             stem_2cta = !(env2 && env2[0] == '0') && launch.mode == (HALO_MODE_RELU | HALO_MODE_POST);
         } else if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
@@ -83,7 +83,7 @@ struct HaloConv {
         if (getenv("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiments only (wrong results)
         if (getenv("RST_EXP_NOSTORE")) q.H = 0;
         if (two_cta && !y_f32) return launch_halo_gemm2(tmA, tmB_half, q, num_sms, s);
-        if (stem_2cta && !y_f32 && !q.stats) return launch_halo_stem2cta(tmA, tmB, q, num_sms, s);
+        if (stem_2cta && !y_f32 && !q.stats) return launch_halo_stem2cta(launch.sched, tmA, tmB, q, num_sms, s);
         return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
     }
 };
@@ -185,6 +185,39 @@ static void setup_stem2(HaloConv* c, const float* k, const float* bias, const fl
                 put(99 + ky * 2, o, e, w);                   // even pixel x0: tap kx = e
                 put(99 + ky * 2 + 1, o, e + 1, w);           // odd pixel x0 + 1: tap kx = e at slot e + 1
             }
+    }
+    col_bias->resize(64); col_scale->resize(64); col_shift->resize(64);
+    for (int n = 0; n < 64; ++n) {
+        (*col_bias)[n] = bias[n % co]; (*col_scale)[n] = bn_scale[n % co]; (*col_shift)[n] = bn_shift[n % co];
+    }
+}
+
+// 18-channel variant (SCH_STEM2B): pair rows [even pixel 16 real | odd pixel 16 real | window ch 16 | window ch 17]; the unit
+// sequences of consecutive row taps share their zero unit: [0, W(ky,8) .. W(ky,0)] x 9, one final 0, then 2 units per (ch, ky).
+static void setup_stem2b(HaloConv* c, const float* k, const float* bias, const float* bn_scale, const float* bn_shift,
+                         std::vector<__nv_bfloat16>* packed, std::vector<float>* col_bias, std::vector<float>* col_scale,
+                         std::vector<float>* col_shift) {
+    const int C = 18, co = 32;
+    c->launch.N = 64; c->launch.row_bytes = 128; c->launch.epi = EPI_NHWC;
+    c->launch.mode = HALO_MODE_RELU | HALO_MODE_POST;
+    c->in_C = 64; c->p.n_groups = 1;
+    use_sched(c, SCH_STEM2B);
+    c->p.out_C = 64; c->p.stats_c = 64;
+    packed->assign((size_t)(kStem2BBoxes + 1) * 256 * 16, __float2bfloat16(0.f));  // + one zero box for the 2-CTA peer's shifted copy
+    auto put = [&](int unit, int row, int e, float w) { (*packed)[((size_t)unit * 32 + row) * 16 + e] = __float2bfloat16(w); };
+    for (int ky = 0; ky < 9; ++ky) {
+        for (int s = 1; s <= 9; ++s) {                       // unit s of the sequence holds column tap kx = 9 - s
+            const int kx = 9 - s;
+            for (int o = 0; o < co; ++o)
+                for (int e = 0; e < 16; ++e) put(ky * 10 + s, o, e, k[((size_t)(ky * 9 + kx) * C + e) * co + o]);
+        }
+        for (int g = 0; g < 2; ++g)
+            for (int o = 0; o < co; ++o)                     // window slot e holds column x0 - 4 + e of channel 16 + g
+                for (int e = 0; e < 9; ++e) {
+                    const float w = k[((size_t)(ky * 9 + e) * C + 16 + g) * co + o];
+                    put(91 + (g * 9 + ky) * 2, o, e, w);             // even pixel x0: tap kx = e
+                    put(91 + (g * 9 + ky) * 2 + 1, o, e + 1, w);     // odd pixel x0 + 1: tap kx = e at slot e + 1
+                }
     }
     col_bias->resize(64); col_scale->resize(64); col_shift->resize(64);
     for (int n = 0; n < 64; ++n) {
@@ -371,9 +404,10 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, cudaMemcpy(scale.data(), c->folded[L.name + "/bn/scale"], L.co * 4, cudaMemcpyDeviceToHost));
         RST_CUDA(c, cudaMemcpy(shift.data(), c->folded[L.name + "/bn/shift"], L.co * 4, cudaMemcpyDeviceToHost));
         const char* env2 = getenv("RST_STEM_PAIRS");
-        const bool pairs = L.ci == 17 && L.co == 32 && L.wi % 2 == 0 && !(env2 && env2[0] == '0');
+        const bool pairs = (L.ci == 17 || L.ci == 18) && L.co == 32 && L.wi % 2 == 0 && !(env2 && env2[0] == '0');
         if (pairs) {
-            setup_stem2(&st->stem, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb, &cs, &csh);
+            if (L.ci == 18) st->stem_layout.row_elems = 32;             // pair rows: 64 elements per two pixels
+            (L.ci == 18 ? setup_stem2b : setup_stem2)(&st->stem, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb, &cs, &csh);
         } else if (!setup_stem(&st->stem, L.ci, L.co, k->host.data(), b->host.data(), scale.data(), shift.data(), &packed, &cb,
                                &cs, &csh)) {
             return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: stem channel layout");
@@ -467,7 +501,7 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
     {
         LaunchScope ls(c, s, "pack_input");
         RST_CUDA(c, launch_pack_stem_input(d_content, st->s_in, batch, g.in_h, g.in_w, g.in_c, st->stem_layout.n_real,
-                                           st->stem_layout.row_elems, st->stem.launch.sched == SCH_STEM2 ? 1 : 0, s));
+                                           st->stem_layout.row_elems, st->stem.launch.sched == SCH_STEM2 || st->stem.launch.sched == SCH_STEM2B ? 1 : 0, s));
     }
     {
         LaunchScope ls(c, s, "stem_umma");
@@ -575,8 +609,9 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
     } else if (kind == STEM) {
         std::vector<float> one(co, 1.f), zero(co, 0.f);
         stem_layout(ci, &SL);
-        if (ci == 17 && w % 2 == 0 && !getenv("RST_STEM_PAIRS_OFF")) {
-            setup_stem2(&hc, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
+        if ((ci == 17 || ci == 18) && co == 32 && w % 2 == 0 && !getenv("RST_STEM_PAIRS_OFF")) {
+            if (ci == 18) SL.row_elems = 32;
+            (ci == 18 ? setup_stem2b : setup_stem2)(&hc, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
             wru = w / 2; stem_pairs = true;
         } else {
             setup_stem(&hc, ci, co, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);

@@ -37,6 +37,8 @@ def bf16_round(a):
     (1, 120, 240, 128, 128, 3, 1, False),    # full bottleneck resolution of rst-960-120-128-*
     (2, 24, 40, 17, 32, 9, 1, False),        # 9x9 stem: 16 real channels + 1 windowed channel per pixel
     (1, 21, 37, 18, 32, 9, 1, False),        # 18-channel variant (two windowed channels, 128-byte rows)
+    (2, 24, 40, 18, 32, 9, 1, False),        # 18 channels, even width: pixel-pair rows with two shared windows (SCH_STEM2B)
+    (1, 19, 128, 18, 32, 9, 1, False),       # ... and the warp-per-segment packing kernel (W % 64 == 0)
     (1, 16, 32, 3, 32, 9, 1, False),         # RGB stem: three windowed channels
     (2, 24, 40, 32, 16, 3, 2, False),        # contract_0: stride-2 conv over the space-to-depth view
     (1, 16, 36, 16, 32, 3, 2, False),        # contract_1
