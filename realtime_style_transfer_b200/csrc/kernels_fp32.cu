@@ -4,6 +4,8 @@
 // every layer the tensor-core path does not cover yet.  NHWC throughout.
 #include "rst_internal.cuh"
 
+#include <cstdlib>
+
 namespace rst {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -157,9 +159,130 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct stride-1 convolution for thin outputs (Co <= 32) on large images: the 9x9 stem, the 16 -> 3 head (forward and
+// input gradient) and the loss model's 64 -> 3 input gradient.  The implicit-GEMM kernel above wastes its 16- / 64-wide
+// column tile on them and pays an im2col index computation per gathered element.
+// A CTA owns a 32x32 output tile; per chunk of CK input channels it stages the (32+K-1)^2 halo channel-planar in shared
+// memory (lanes read consecutive pixels: conflict-free) plus the chunk's weights (read as warp-wide broadcasts).
+// A thread owns a column of 4 output pixels x CO channels: for one (column tap, channel) it loads the 4+K-1 inputs of its
+// column once and slides the K row taps over them in registers: (4+K-1) + K*CO/4 loads per 4*K*CO FMAs.
+// ---------------------------------------------------------------------------------------------
+template <int CO, int KS>
+__global__ void __launch_bounds__(256) conv_direct_f32_kernel(const ConvF32 p, int CK, int tiles_x) {
+    constexpr int T = 32, PX = 4, HH = T + KS - 1, HWP = HH | 1, NX = PX + KS - 1;
+    extern __shared__ float direct_smem[];
+    const int plane = HH * HWP + ((HH * HWP) % 2 == 0 ? 1 : 0);              // odd plane stride: the chunk loader writes ck-fastest
+    float* xs = direct_smem;                                                   // [CK][HH][HWP]
+    float* ws = direct_smem + ((CK * plane + 3) & ~3);                         // [KS*KS][CK][CO], 16-byte aligned
+    const int tid = threadIdx.x, tx = tid & 31, tg = tid >> 5;
+    const int n = blockIdx.y;
+    const int x0 = (blockIdx.x % tiles_x) * T, y0 = (blockIdx.x / tiles_x) * T;
+    // halo origin in input coordinates and the tap order along the halo (the input-gradient form walks the taps backwards)
+    const int hy0 = p.transposed ? y0 + p.pad_t - (KS - 1) : y0 - p.pad_t;
+    const int hx0 = p.transposed ? x0 + p.pad_l - (KS - 1) : x0 - p.pad_l;
+    float acc[PX][CO];
+#pragma unroll
+    for (int j = 0; j < PX; ++j)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+    const float* xn = p.x + (long long)n * p.Hi * p.Wi * p.Ci;
+    for (int c0 = 0; c0 < p.Ci; c0 += CK) {
+        __syncthreads();
+        for (int e = tid; e < CK * HH * HH; e += 256) {
+            const int ck = e % CK, pix = e / CK, hx = pix % HH, hy = pix / HH;
+            const int iy = hy0 + hy, ix = hx0 + hx;
+            float v = 0.f;
+            if (c0 + ck < p.Ci && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi)
+                v = fmaf(__ldg(xn + ((long long)iy * p.Wi + ix) * p.Ci + c0 + ck), p.in_scale, p.in_shift);
+            xs[ck * plane + hy * HWP + hx] = v;
+        }
+        for (int e = tid; e < KS * KS * CK * CO; e += 256) {
+            const int co = e % CO, ck = (e / CO) % CK, t = e / (CO * CK);
+            const int dy = t / KS, dx = t % KS;
+            const int tap = p.transposed ? (KS - 1 - dy) * KS + (KS - 1 - dx) : t;
+            ws[e] = (co < p.Co && c0 + ck < p.Ci) ? __ldg(p.w + tap * p.w_tap + (c0 + ck) * p.w_ci + co * p.w_co) : 0.f;
+        }
+        __syncthreads();
+        for (int dx = 0; dx < KS; ++dx) {
+            for (int ck = 0; ck < CK; ++ck) {
+                float xv[NX];
+                const float* xc = xs + ck * plane + (tg * PX) * HWP + tx + dx;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) xv[j] = xc[j * HWP];
+#pragma unroll
+                for (int dy = 0; dy < KS; ++dy) {
+                    const float4* w4 = reinterpret_cast<const float4*>(ws + ((dy * KS + dx) * CK + ck) * CO);
+#pragma unroll
+                    for (int c = 0; c < CO / 4; ++c) {
+                        const float4 w = w4[c];
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) {
+                            acc[j][4 * c + 0] = fmaf(xv[j + dy], w.x, acc[j][4 * c + 0]);
+                            acc[j][4 * c + 1] = fmaf(xv[j + dy], w.y, acc[j][4 * c + 1]);
+                            acc[j][4 * c + 2] = fmaf(xv[j + dy], w.z, acc[j][4 * c + 2]);
+                            acc[j][4 * c + 3] = fmaf(xv[j + dy], w.w, acc[j][4 * c + 3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const int ox = x0 + tx;
+    if (ox >= p.Wo) return;
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+        const int oy = y0 + tg * PX + j;
+        if (oy >= p.Ho) continue;
+        const long long o0 = (((long long)n * p.Ho + oy) * p.Wo + ox) * p.Co;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+            if (c >= p.Co) continue;
+            float v = acc[j][c];
+            if (p.bias) v += __ldg(p.bias + c);
+            v = apply_act(v, p.act1);
+            if (p.post_scale) v = v * __ldg(p.post_scale + c) + __ldg(p.post_shift + c);
+            v = apply_act(v, p.act2);
+            if (p.residual) v += __ldg(p.residual + o0 + c);
+            if (p.out_tf32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
+            p.y[o0 + c] = v;
+        }
+    }
+}
+
+template <int CO, int KS>
+static cudaError_t launch_conv_direct(const ConvF32& p, cudaStream_t s) {
+    constexpr int HH = 32 + KS - 1, HWP = HH | 1;
+    const int plane = HH * HWP + ((HH * HWP) % 2 == 0 ? 1 : 0);
+    // channels per chunk: as many as fit in ~64 KB together with their weights (3 CTAs per SM when CO is small)
+    int ck = p.Ci < 16 ? p.Ci : 16;
+    auto bytes = [&](int k) { return (size_t)(((k * plane + 3) & ~3) + KS * KS * k * CO) * sizeof(float); };
+    const size_t budget = CO >= 32 ? 160 * 1024 : 72 * 1024;         // CO = 32 is register-limited to one CTA per SM anyway
+    while (ck > 1 && bytes(ck) > budget) --ck;
+    ck = ceil_div(p.Ci, ceil_div(p.Ci, ck));                         // equal chunks
+    const size_t smem = bytes(ck);
+    static size_t configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv_direct_f32_kernel<CO, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int tiles_x = ceil_div(p.Wo, 32), tiles_y = ceil_div(p.Ho, 32);
+    dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)p.B);
+    conv_direct_f32_kernel<CO, KS><<<grid, 256, smem, s>>>(p, ck, tiles_x);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
     long long M = (long long)p.B * p.Ho * p.Wo;
     if (M == 0) return cudaSuccess;
+    static const bool direct_off = [] { const char* e = getenv("RST_CONV_DIRECT"); return e && e[0] == '0'; }();
+    if (!direct_off && p.stride == 1 && p.kh == p.kw && p.Ho >= 64 && p.Wo >= 64 && p.B <= 65535) {
+        if (p.kh == 9 && p.Co <= 4) return launch_conv_direct<4, 9>(p, s);
+        if (p.kh == 9 && p.Co <= 16) return launch_conv_direct<16, 9>(p, s);
+        if (p.kh == 9 && p.Co <= 32) return launch_conv_direct<32, 9>(p, s);
+        if (p.kh == 3 && p.Co <= 4) return launch_conv_direct<4, 3>(p, s);
+    }
     if (p.Co > 16) {
         dim3 grid((unsigned)((M + 63) / 64), (unsigned)ceil_div(p.Co, 64));
         conv_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);

@@ -71,6 +71,12 @@ def test_create_rejects_bad_configs(cuda_device):
     (2, 12, 20, 16, 3, 9, 1, True),       # head
     (1, 5, 7, 3, 1, 9, 5, False),         # DUMMY predictor conv
     (0, 8, 8, 4, 4, 3, 1, False),         # empty batch
+    # images of 64x64 and more: thin stride-1 layers take the direct (shared-memory halo) kernel
+    (2, 70, 100, 17, 32, 9, 1, False),    # stem, ragged 32x32 tiles, two channel chunks
+    (1, 64, 96, 16, 3, 9, 1, True),       # head (input-gradient form walks the taps backwards)
+    (2, 67, 64, 3, 16, 9, 1, False),      # head's input gradient: 3 -> 16
+    (1, 65, 130, 64, 3, 3, 1, False),     # loss model conv1_1 input gradient: 64 -> 3, four channel chunks
+    (1, 64, 64, 64, 3, 3, 1, True),
 ])
 def test_op_conv2d_fp32(cuda_device, b, h, w, ci, co, k, s, transposed):
     rng = np.random.default_rng(b * 1000 + h * 10 + k)
