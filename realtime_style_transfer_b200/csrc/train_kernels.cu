@@ -2,6 +2,8 @@
 // activation backward, RMSprop.  Correctness-first CUDA-core kernels (the tensor-core training path is future work).
 #include "train_kernels.cuh"
 
+#include <cstdlib>
+
 namespace rst {
 
 static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
@@ -87,10 +89,20 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
 #pragma unroll 8
         for (int q = 0; q < PIX; ++q) {
             float a[RM], g[RN];
-            if (RM == 4) { const float4 t = *reinterpret_cast<const float4*>(&As[q][ty * 4]); a[0] = t.x; a[1] = t.y; a[RM - 2] = t.z; a[RM - 1] = t.w; }
-            else { const float2 t = *reinterpret_cast<const float2*>(&As[q][ty * 2]); a[0] = t.x; a[1] = t.y; }
-            if (RN == 4) { const float4 t = *reinterpret_cast<const float4*>(&Gs[q][tx * 4]); g[0] = t.x; g[1] = t.y; g[RN - 2] = t.z; g[RN - 1] = t.w; }
-            else { const float2 t = *reinterpret_cast<const float2*>(&Gs[q][tx * 2]); g[0] = t.x; g[1] = t.y; }
+            if (RM % 4 == 0) {
+#pragma unroll
+                for (int h = 0; h < RM / 4; ++h) {       // RM = 8: columns ty*4 and 64 + ty*4 (conflict-free float4 reads)
+                    const float4 t = *reinterpret_cast<const float4*>(&As[q][h * 64 + ty * 4]);
+                    a[4 * h] = t.x; a[4 * h + 1] = t.y; a[4 * h + 2] = t.z; a[4 * h + 3] = t.w;
+                }
+            } else { const float2 t = *reinterpret_cast<const float2*>(&As[q][ty * 2]); a[0] = t.x; a[1] = t.y; }
+            if (RN % 4 == 0) {
+#pragma unroll
+                for (int h = 0; h < RN / 4; ++h) {
+                    const float4 t = *reinterpret_cast<const float4*>(&Gs[q][h * 64 + tx * 4]);
+                    g[4 * h] = t.x; g[4 * h + 1] = t.y; g[4 * h + 2] = t.z; g[4 * h + 3] = t.w;
+                }
+            } else { const float2 t = *reinterpret_cast<const float2*>(&Gs[q][tx * 2]); g[0] = t.x; g[1] = t.y; }
 #pragma unroll
             for (int i = 0; i < RM; ++i)
 #pragma unroll
@@ -102,7 +114,9 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
     for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < RN; ++j) {
-            const int cin = ci0 + ty * RM + i, co = c0 + tx * RN + j;
+            // register i of a thread is tile row (i / 4) * 64 + ty * 4 + i % 4 when the tile is read as float4 halves (RM = 8)
+            const int cin = ci0 + (RM % 4 == 0 ? (i / 4) * 64 + ty * 4 + i % 4 : ty * RM + i);
+            const int co = c0 + (RN % 4 == 0 ? (j / 4) * 64 + tx * 4 + j % 4 : tx * RN + j);
             if (ROWMODE) {
                 if (cin < row_len && co < p.Co) atomicAdd(p.dw + ((long long)ky * row_len + cin) * p.Co + co, acc[i][j]);
             } else if (GROW) {
@@ -114,13 +128,140 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the thin 9x9 stride-1 layers at full resolution (stem 17 -> 32, head 16 -> 3): a sliding-window kernel.
+//   dW[ky, kx, a, b] = sum_{n,y,x} P[n, y + ky - pt, x + kx - pl, a] * Q[n, y, x, b]
+// conv: P = layer input (A = Ci), Q = output gradient (NB = Co); convT: P = output gradient (A = Co), Q = layer input (NB = Ci).
+// A thread owns dW[ky, 0..KS-1, a, 4 consecutive b]: walking along an image row it loads ONE new P value and one float4 of Q
+// per pixel and keeps the KS-wide P window in registers (KS * 4 FMAs per 2 shared-memory loads; the GEMM-style kernel above
+// manages 8 per 2).  A CTA covers KYB filter rows and stages 4 x 72-pixel tiles (+ halo) in shared memory; out-of-image
+// pixels are stored as zeros, so no masks are needed in the inner loop.  CTAs are persistent: one atomicAdd per weight each.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradDirect {
+    const float* P; const float* Q; float* dw;
+    int B, H, W, NB, pad_t, pad_l;
+    float p_scale, p_shift;
+};
+template <int A, int NBG, int KS, int KYB>
+__global__ void __launch_bounds__((KYB * A * NBG + 31) / 32 * 32)
+wgrad_direct_f32_kernel(const WgradDirect p, int tiles_x, int tiles_y, int blocks_per_group) {
+    constexpr int TH = 4, TW = 8 * KS, PW = TW + KS - 1, PH = TH + KYB - 1, NB4 = NBG * 4, NT = KYB * A * NBG;
+    extern __shared__ __align__(16) float wd_smem[];
+    float* Qs = wd_smem;                                   // [TH][TW][NB4]
+    float* Ps = wd_smem + TH * TW * NB4;                   // [PH][PW][A]
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int kg = blockIdx.x / blocks_per_group, bi = blockIdx.x % blocks_per_group;
+    const int ky0 = kg * KYB;
+    const bool active = tid < NT;
+    const int bg = tid % NBG, a = (tid / NBG) % A, kyl = active ? tid / (NBG * A) : 0;
+    float acc[KS][4];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { acc[k][0] = 0.f; acc[k][1] = 0.f; acc[k][2] = 0.f; acc[k][3] = 0.f; }
+    const long long total_tiles = (long long)p.B * tiles_y * tiles_x;
+    for (long long t = bi; t < total_tiles; t += blocks_per_group) {
+        const int txi = (int)(t % tiles_x);
+        const long long rr = t / tiles_x;
+        const int tyi = (int)(rr % tiles_y), n = (int)(rr / tiles_y);
+        const int x0 = txi * TW, y0 = tyi * TH;
+        const long long img = (long long)n * p.H * p.W;
+        __syncthreads();
+        for (int e = tid; e < TH * TW * NB4; e += nthreads) {
+            const int b = e % NB4, pix = e / NB4, gx = x0 + pix % TW, gy = y0 + pix / TW;
+            Qs[e] = (b < p.NB && gy < p.H && gx < p.W) ? __ldg(p.Q + (img + (long long)gy * p.W + gx) * p.NB + b) : 0.f;
+        }
+        for (int e = tid; e < PH * PW * A; e += nthreads) {
+            const int c = e % A, pix = e / A, px = x0 + pix % PW - p.pad_l, py = y0 + pix / PW + ky0 - p.pad_t;
+            Ps[e] = (py >= 0 && py < p.H && px >= 0 && px < p.W)
+                        ? fmaf(__ldg(p.P + (img + (long long)py * p.W + px) * A + c), p.p_scale, p.p_shift) : 0.f;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int r = 0; r < TH; ++r) {
+                const float* prow = Ps + (r + kyl) * PW * A + a;
+                const float4* qrow = reinterpret_cast<const float4*>(Qs + r * TW * NB4) + bg;
+                float w[KS];
+#pragma unroll
+                for (int c = 0; c < KS - 1; ++c) w[c] = prow[c * A];
+#pragma unroll 1
+                for (int x9 = 0; x9 < TW; x9 += KS) {
+#pragma unroll
+                    for (int u = 0; u < KS; ++u) {
+                        const int xx = x9 + u;
+                        w[(u + KS - 1) % KS] = prow[(xx + KS - 1) * A];
+                        const float4 q = qrow[xx * NBG];
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx) {
+                            const float pv = w[(u + kx) % KS];
+                            acc[kx][0] = fmaf(pv, q.x, acc[kx][0]); acc[kx][1] = fmaf(pv, q.y, acc[kx][1]);
+                            acc[kx][2] = fmaf(pv, q.z, acc[kx][2]); acc[kx][3] = fmaf(pv, q.w, acc[kx][3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = bg * 4 + j;
+            if (b < p.NB) atomicAdd(p.dw + ((long long)((ky0 + kyl) * KS + kx) * A + a) * p.NB + b, acc[kx][j]);
+        }
+}
+template <int A, int NBG, int KS, int KYB>
+static cudaError_t launch_wgrad_direct(const WgradDirect& p, cudaStream_t s) {
+    constexpr int TH = 4, TW = 8 * KS, PW = TW + KS - 1, PH = TH + KYB - 1, NT = KYB * A * NBG, THREADS = (NT + 31) / 32 * 32;
+    const size_t smem = (size_t)(TH * TW * NBG * 4 + PH * PW * A) * sizeof(float);
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_direct_f32_kernel<A, NBG, KS, KYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wgrad_direct_f32_kernel<A, NBG, KS, KYB>, THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles_x = ceil_div(p.W, TW), tiles_y = ceil_div(p.H, TH), groups = KS / KYB;
+    const long long tiles = (long long)p.B * tiles_x * tiles_y;
+    long long bpg = (long long)sms * per_sm / groups;
+    if (bpg > tiles) bpg = tiles;
+    if (bpg < 1) bpg = 1;
+    wgrad_direct_f32_kernel<A, NBG, KS, KYB><<<(unsigned)(bpg * groups), THREADS, smem, s>>>(p, tiles_x, tiles_y, (int)bpg);
+    return cudaGetLastError();
+}
+// thin 9x9 stride-1 'same' layers on images of at least 64 x 64 pixels; false = not handled here
+static bool try_wgrad_direct(const WgradF32& p, cudaStream_t s, cudaError_t* e) {
+    static const bool off = [] { const char* v = getenv("RST_WGRAD_DIRECT"); return v && v[0] == '0'; }();
+    if (off || p.stride != 1 || p.kh != 9 || p.kw != 9 || p.Hx != p.Hg || p.Wx != p.Wg || p.Hx < 64 || p.Wx < 64) return false;
+    WgradDirect d{};
+    d.dw = p.dw; d.B = p.B; d.H = p.Hx; d.W = p.Wx; d.pad_t = p.pad_t; d.pad_l = p.pad_l;
+    if (!p.transposed) {
+        if (p.Co != 32) return false;
+        d.P = p.x; d.Q = p.g; d.NB = p.Co; d.p_scale = p.in_scale; d.p_shift = p.in_shift;
+        if (p.Ci == 17) *e = launch_wgrad_direct<17, 8, 9, 3>(d, s);
+        else if (p.Ci == 18) *e = launch_wgrad_direct<18, 8, 9, 3>(d, s);
+        else if (p.Ci == 3) *e = launch_wgrad_direct<3, 8, 9, 9>(d, s);
+        else return false;
+        return true;
+    }
+    if (p.Co != 3 || p.Ci != 16 || p.in_scale != 1.f || p.in_shift != 0.f) return false;
+    d.P = p.g; d.Q = p.x; d.NB = p.Ci; d.p_scale = 1.f; d.p_shift = 0.f;
+    *e = launch_wgrad_direct<3, 4, 9, 9>(d, s);
+    return true;
+}
+
 cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     if (NP == 0) return cudaSuccess;
+    { cudaError_t e = cudaSuccess; if (try_wgrad_direct(p, s, &e)) return e; }
     const int rmode = p.stride != 1 ? 0 : (p.transposed ? 2 : 1);
     const int m_extent = rmode == 1 ? p.kw * p.Ci : p.Ci, n_extent = rmode == 2 ? p.kw * p.Co : p.Co;
     const bool wide_m = m_extent > 32, wide_n = n_extent > 32;
-    const int tm = wide_m ? 64 : 32, tn = wide_n ? 64 : 32;
+    const bool big = rmode == 1 && m_extent % 128 == 0 && n_extent % 128 == 0;     // trunk 128 -> 128: 8 x 8 register tiles
+    const int tm = big ? 128 : wide_m ? 64 : 32, tn = big ? 128 : wide_n ? 64 : 32;
     const int ci_blocks = ceil_div(m_extent, tm);
     const int groups = rmode ? p.kh : p.kh * p.kw;
     // enough pixel slabs to fill the GPU a few times over, but long enough to amortise the atomics
@@ -136,7 +277,8 @@ cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
         else if (rmode == 2) wgrad_f32_kernel<TM_, TN_, 2><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);            \
         else wgrad_f32_kernel<TM_, TN_, 0><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);                            \
     } while (0)
-    if (wide_m && wide_n) RST_WGRAD(64, 64);
+    if (big) wgrad_f32_kernel<128, 128, 1><<<grid, 256, 0, s>>>(p, ci_blocks, pix_per_split);
+    else if (wide_m && wide_n) RST_WGRAD(64, 64);
     else if (wide_m) RST_WGRAD(64, 32);
     else if (wide_n) RST_WGRAD(32, 64);
     else RST_WGRAD(32, 32);

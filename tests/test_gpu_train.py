@@ -307,11 +307,15 @@ def test_training_step_tf32_trunk(cuda_device):
     tr.close()
 
 
-def test_training_step_split_tf32_trunk_keeps_fp32_accuracy(cuda_device):
-    """Default (fp32) math with a 64-filter trunk: the residual trunk's convolutions run on the tensor cores as
+@pytest.mark.parametrize("channels,filters", [(5, 64), (17, 128), (3, 128)])
+def test_training_step_split_tf32_trunk_keeps_fp32_accuracy(cuda_device, channels, filters):
+    """(17, 128) and (3, 128) are the channel counts of the BASELINE configurations: they select the sliding-window weight-gradient
+    kernel of the 9x9 stem and the 128x128-tile weight-gradient kernel of the trunk.
+    Default (fp32) math with a 64-filter trunk: the residual trunk's convolutions run on the tensor cores as
     error-compensated split tf32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulation).  The fp32 bars must hold: prediction
     1e-4 and the network's backward pass within VJP_TOL of fp64 autograd for the same upstream gradient."""
-    batch, filters = 2, 64
+    batch = 2
+    IN_SHAPE = (64, 96, channels)
     spec = O.TransferSpec(IN_SHAPE, OUT_SHAPE, RES_Y, filters, 1)
     tw = O.init_transfer_weights(spec, seed=21, trained_like=True)
     pw = O.init_predictor_weights("DUMMY", spec.num_style_parameters, seed=22)
