@@ -453,7 +453,9 @@ cudaError_t launch_norm_bwd_reduce(const float* g, const float* x, const float* 
                                    int C, int per_sample, cudaStream_t s) {
     if (B == 0 || P == 0) return cudaSuccess;
     const int threads = C <= 256 ? C * (256 / C) : 256;
-    const int pix_per_block = 2048;
+    // enough CTAs to fill the GPU even for the small, wide tensors of the predictor (a CTA walks its pixels serially)
+    int pix_per_block = 2048;
+    while (pix_per_block > 64 && (long long)ceil_div(P, pix_per_block) * B < 148 * 8) pix_per_block /= 2;
     dim3 grid((unsigned)ceil_div(P, pix_per_block), (unsigned)B);
     norm_bwd_reduce_kernel<<<grid, threads, 2 * threads * sizeof(double), s>>>(g, x, mean, inv, r, P, C, per_sample, pix_per_block);
     return cudaGetLastError();
