@@ -544,13 +544,14 @@ bool umma_init(std::string* err) {
 
 // Dims ordered (C, H, WRU, B) so that a box enumerates rows (h) fastest among row units.
 bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, int C, int row_elems, int halo_h,
-                     int halo_w, std::string* err) {
+                     int halo_w, std::string* err, bool atom32) {
     if (!umma_init(err)) return false;
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)WRU, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)WRU * C * 2, (cuuint64_t)C * 2, (cuuint64_t)H * WRU * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)halo_h, (cuuint32_t)halo_w, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUtensorMapSwizzle sw = row_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    if (atom32 && row_elems == 64) sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;    // MN-major tf32 operands (wgrad_tf32.cu)
     if (row_elems != 64 && row_elems != 32) {
         if (err) *err = "encode_halo_map: row must be 32 or 64 bf16 elements";
         return false;

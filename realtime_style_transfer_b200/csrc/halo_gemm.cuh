@@ -163,7 +163,7 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
 // ---- host helpers -------------------------------------------------------------------------------
 // Activation tensor (B, H, WRU, row_elems*n_groups) bf16 viewed for the halo box (row_elems, halo_h, halo_w, 1).
 bool encode_halo_map(CUtensorMap* out, const void* base, int B, int H, int WRU, int C, int row_elems, int halo_h,
-                     int halo_w, std::string* err);
+                     int halo_w, std::string* err, bool atom32 = false);   // atom32: 128-byte swizzle in 32-byte chunks
 // Packed weights: nblocks*N rows of 64 bf16; box = (64, N).
 // Space-to-depth view of an NHWC tensor (B, H, W, C), H and W even: dims (2C, H/2, 2, W/2, B), box (2C, 9, 2, 17, 1).
 bool encode_s2d_map(CUtensorMap* out, const void* base, int B, int H, int W, int C, std::string* err);

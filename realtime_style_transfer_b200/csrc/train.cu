@@ -198,6 +198,11 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
     }
     float* dgrad_tmp = (tensor_core && x->needs_grad) ? falloc(t, x->n()) : nullptr;
     float* dgrad_scratch = (split && x->needs_grad) ? falloc(t, 3LL * y->n()) : nullptr;
+    // 128 -> 128: the weight gradient runs on the tensor cores as well (wgrad_tf32.cu); its scratch is free until the input gradient
+    const char* wgrad_env = getenv("RST_WGRAD_TF32");                  // read per step: the tests toggle it
+    const bool wgrad_tc_off = wgrad_env && wgrad_env[0] == '0';
+    const bool wgrad_tc = tensor_core && ci == 128 && co == 128 && !wgrad_tc_off;
+    float* wgrad_scratch = (wgrad_tc && split) ? (dgrad_scratch ? dgrad_scratch : falloc(t, 2LL * y->n())) : nullptr;
     double* st = dalloc(t, (long long)x->B * co * 2);
     double* st2 = dalloc(t, (long long)co * 2);
     const ConvSpec spec = cs;
@@ -211,7 +216,13 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
         wg.transposed = spec.transposed ? 1 : 0;
         wg.Hb = spec.transposed ? x->H : ho; wg.Wb = spec.transposed ? x->W : wo;
         wg.in_scale = spec.in_scale; wg.in_shift = spec.in_shift;
-        TCUDA(t, launch_wgrad_f32(wg, t->s));
+        if (wgrad_tc) {
+            std::string err;
+            TCUDA(t, launch_wgrad_tf32(x->d, y->g, vk->g, wgrad_scratch, x->B, x->H, x->W, split, t->num_sms, t->s, &err));
+            t->m->launches += split ? 2 : 0;
+        } else {
+            TCUDA(t, launch_wgrad_f32(wg, t->s));
+        }
         t->m->launches += 2;
         if (vb) { int rc = bias_grad(t, y->g, y->B, y->P(), co, vb->g, st, st2); if (rc) return rc; }
         Tf32Conv3x3* bwd = (tensor_core && x->needs_grad) ? tf32_conv(t, t->tf32_bwd, kname, ci, co, false, true, split) : nullptr;

@@ -1,5 +1,6 @@
 // Kernel launchers used by the training step (train.cu).
 #pragma once
+#include <string>
 
 #include "rst_internal.cuh"
 
@@ -17,6 +18,11 @@ struct WgradF32 {
     float in_scale = 1.f, in_shift = 0.f;   // the forward's input rescaling (in-bounds taps only)
 };
 cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s);
+// tensor-core (kind::tf32, MN-major operands) weight gradient of a 3x3 stride-1 'same' convolution 128 -> 128 (wgrad_tf32.cu);
+// split = error-compensated (fp32-level accuracy), needs wgrad_tf32_scratch_floats() floats of scratch
+size_t wgrad_tf32_scratch_floats(int B, int H, int W);
+cudaError_t launch_wgrad_tf32(const float* x, const float* g, float* dw, float* lo_scratch, int B, int H, int W, bool split,
+                              int num_sms, cudaStream_t s, std::string* err);
 
 cudaError_t launch_reduce_over_batch(const double* in, double* out, int B, int C2, cudaStream_t s);
 cudaError_t launch_norm_finalize(const double* stats, int G, int C, double count, float eps, const float* scale,

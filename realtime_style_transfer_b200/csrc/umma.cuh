@@ -205,7 +205,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors -------------------------------------------------------------------------------
-enum : uint64_t { SWIZZLE_NONE = 0, SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6 };
+// SWIZZLE_128B_BASE32B: 128-byte rows swizzled in 32-byte chunks over 4 rows -- the only layout tcgen05 accepts for MN-major tf32
+enum : uint64_t { SWIZZLE_NONE = 0, SWIZZLE_128B_BASE32B = 1, SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6 };
 
 // K-major operand tile.  start/lbo/sbo in bytes (multiples of 16).
 __host__ __device__ inline uint64_t make_smem_desc(uint32_t start_addr, uint32_t lbo, uint32_t sbo, uint64_t swizzle,

@@ -346,3 +346,37 @@ def test_training_step_split_tf32_trunk_keeps_fp32_accuracy(cuda_device, channel
         assert rel < VJP_TOL or rel <= 4 * rel32, (name, rel, rel32)
     print("split-tf32 trunk: worst vjp rel l2", worst)
     tr.close()
+
+
+def test_tensor_core_weight_gradient_matches_cuda_cores_at_scale(cuda_device, monkeypatch):
+    """The trunk's weight gradients (3x3, 128 -> 128) run on tcgen05 with MN-major tf32 operands, error-compensated
+    (hi*hi + hi*lo + lo*hi) and with periodic accumulator flushes.  The small VJP tests above check the indexing; this one
+    checks the long reductions (2 x 64 x 128 = 16 K pixels per weight) against the fp32 CUDA-core kernel on identical inputs."""
+    batch, filters = 2, 128
+    in_shape, out_shape = (256, 512, 17), (256, 512, 3)
+    spec = O.TransferSpec(in_shape, out_shape, 64, filters, 1)
+    tw = O.init_transfer_weights(spec, seed=5, trained_like=True)
+    pw = O.init_predictor_weights("DUMMY", spec.num_style_parameters, seed=6)
+    vgg = O.init_vgg16_weights(seed=3)
+    rng = np.random.default_rng(7)
+    content = rng.uniform(0, 1, (batch,) + in_shape).astype(np.float32)
+    style = rng.uniform(0, 1, (batch,) + out_shape).astype(np.float32)
+    gt = rng.uniform(0, 1, (batch,) + out_shape).astype(np.float32)
+    names = [n for n in tw if n.startswith("residual_block") and n.endswith("/kernel")]
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RST_WGRAD_TF32", mode)
+        tr = _native.NativeTrainer(in_shape=in_shape, out_shape=out_shape, bottleneck_res_y=64, bottleneck_num_filters=filters,
+                                   max_batch=batch, extractor=_native.EXTRACTOR_DUMMY, style_shape=out_shape[:2])
+        tr.model.set_weights({**tw, **pw})
+        tr.loss.set_weights(vgg)
+        _step(tr, cuda_device, content, style, gt)
+        grads[mode] = {n: tr.read_gradient(n, tw[n].shape).astype(np.float64) for n in names}
+        tr.close()
+    worst = 0.0
+    for n in names:
+        ref, got = grads["0"][n], grads["1"][n]
+        rel = np.sqrt(((got - ref) ** 2).sum() / max((ref ** 2).sum(), 1e-300))
+        worst = max(worst, rel)
+        assert rel < 1e-4, (n, rel)
+    print("tensor-core vs CUDA-core weight gradients: worst rel l2", worst)
