@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) conv_direct_f32_kernel(const ConvF32 p, i
     float* xs = direct_smem;                                                   // [CK][HH][HWP]
     float* ws = direct_smem + ((CK * plane + 3) & ~3);                         // [KS*KS][CK][CO], 16-byte aligned
     const int tid = threadIdx.x, tx = tid & 31, tg = tid >> 5;
-    const int n = blockIdx.y;
+    const int n = blockIdx.y, co0 = blockIdx.z * CO;                           // wider layers: CO output channels per CTA
     const int x0 = (blockIdx.x % tiles_x) * T, y0 = (blockIdx.x / tiles_x) * T;
     // halo origin in input coordinates and the tap order along the halo (the input-gradient form walks the taps backwards)
     const int hy0 = p.transposed ? y0 + p.pad_t - (KS - 1) : y0 - p.pad_t;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) conv_direct_f32_kernel(const ConvF32 p, i
             const int co = e % CO, ck = (e / CO) % CK, t = e / (CO * CK);
             const int dy = t / KS, dx = t % KS;
             const int tap = p.transposed ? (KS - 1 - dy) * KS + (KS - 1 - dx) : t;
-            ws[e] = (co < p.Co && c0 + ck < p.Ci) ? __ldg(p.w + tap * p.w_tap + (c0 + ck) * p.w_ci + co * p.w_co) : 0.f;
+            ws[e] = (co0 + co < p.Co && c0 + ck < p.Ci) ? __ldg(p.w + tap * p.w_tap + (c0 + ck) * p.w_ci + (co0 + co) * p.w_co) : 0.f;
         }
         __syncthreads();
         for (int dx = 0; dx < KS; ++dx) {
@@ -234,18 +234,28 @@ __global__ void __launch_bounds__(256) conv_direct_f32_kernel(const ConvF32 p, i
     for (int j = 0; j < PX; ++j) {
         const int oy = y0 + tg * PX + j;
         if (oy >= p.Ho) continue;
-        const long long o0 = (((long long)n * p.Ho + oy) * p.Wo + ox) * p.Co;
+        const long long o0 = (((long long)n * p.Ho + oy) * p.Wo + ox) * p.Co + co0;
+        float v[CO];
 #pragma unroll
         for (int c = 0; c < CO; ++c) {
-            if (c >= p.Co) continue;
-            float v = acc[j][c];
-            if (p.bias) v += __ldg(p.bias + c);
-            v = apply_act(v, p.act1);
-            if (p.post_scale) v = v * __ldg(p.post_scale + c) + __ldg(p.post_shift + c);
-            v = apply_act(v, p.act2);
-            if (p.residual) v += __ldg(p.residual + o0 + c);
-            if (p.out_tf32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
-            p.y[o0 + c] = v;
+            const int cc = co0 + c < p.Co ? co0 + c : p.Co - 1;             // clamped: values beyond Co are never stored
+            float t = acc[j][c];
+            if (p.bias) t += __ldg(p.bias + cc);
+            t = apply_act(t, p.act1);
+            if (p.post_scale) t = t * __ldg(p.post_scale + cc) + __ldg(p.post_shift + cc);
+            t = apply_act(t, p.act2);
+            if (p.residual) t += __ldg(p.residual + o0 - co0 + cc);
+            if (p.out_tf32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t)); t = __uint_as_float(r); }
+            v[c] = t;
+        }
+        if (p.Co % 4 == 0) {                                                   // 128-bit stores: a pixel's CO channels are contiguous
+#pragma unroll
+            for (int c = 0; c < CO; c += 4)
+                if (co0 + c < p.Co) *reinterpret_cast<float4*>(p.y + o0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CO; ++c)
+                if (co0 + c < p.Co) p.y[o0 + c] = v[c];
         }
     }
 }
@@ -268,7 +278,7 @@ static cudaError_t launch_conv_direct(const ConvF32& p, cudaStream_t s) {
         configured = smem;
     }
     const int tiles_x = ceil_div(p.Wo, 32), tiles_y = ceil_div(p.Ho, 32);
-    dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)p.B);
+    dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)p.B, (unsigned)ceil_div(p.Co, CO));
     conv_direct_f32_kernel<CO, KS><<<grid, 256, smem, s>>>(p, ck, tiles_x);
     return cudaGetLastError();
 }
