@@ -479,13 +479,8 @@ bool halo_gemm_plan(HaloGemmLaunch* l, HaloGemmParams* p, std::string* err) {
 template <int N, int ROWB, int EPI, int MODE, int SCH, bool BRES>
 static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloGemmParams& p,
                             int num_sms, cudaStream_t s) {
-    static size_t configured = 0;
-    if (configured < l.smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
-        if (e != cudaSuccess) return e;
-        configured = l.smem_bytes;
-    }
+    static SmemAttrCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES>, l.smem_bytes, configured)) return e;
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;

@@ -246,13 +246,9 @@ size_t halo_gemm2_smem_bytes(int n_groups) {
 // Weights for the 2-CTA kernel use the same packed blocks; the tensor map's box is 64 rows (one CTA's half of N).
 cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
                               cudaStream_t s) {
-    static size_t configured = 0;
+    static SmemAttrCache configured;
     const size_t smem = halo_gemm2_smem_bytes(p.n_groups);
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(halo_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel, smem, configured)) return e;
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int pairs = (total + 1) / 2;

@@ -177,13 +177,9 @@ size_t halo_stem2cta_smem_bytes(int sch) { return (size_t)kSAStages * kSAStage +
 template <int SCH>
 static cudaError_t launch_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tmB_units, const HaloGemmParams& p, int num_sms,
                                    cudaStream_t s) {
-    static bool configured = false;
+    static SmemAttrCache configured;
     const size_t smem = halo_stem2cta_smem_bytes(SCH);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(halo_stem2cta_kernel<SCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(halo_stem2cta_kernel<SCH>, smem, configured)) return e;
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int pairs = (total + 1) / 2;

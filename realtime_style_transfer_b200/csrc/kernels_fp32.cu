@@ -271,12 +271,8 @@ static cudaError_t launch_conv_direct(const ConvF32& p, cudaStream_t s) {
     while (ck > 1 && bytes(ck) > budget) --ck;
     ck = ceil_div(p.Ci, ceil_div(p.Ci, ck));                         // equal chunks
     const size_t smem = bytes(ck);
-    static size_t configured = 0;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(conv_direct_f32_kernel<CO, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemAttrCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(conv_direct_f32_kernel<CO, KS>, smem, configured)) return e;
     const int tiles_x = ceil_div(p.Wo, 32), tiles_y = ceil_div(p.Ho, 32);
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)p.B, (unsigned)ceil_div(p.Co, CO));
     conv_direct_f32_kernel<CO, KS><<<grid, 256, smem, s>>>(p, ck, tiles_x);

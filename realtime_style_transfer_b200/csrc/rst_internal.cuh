@@ -26,6 +26,21 @@ inline int tf_same(int size, int k, int s, int* pad_before) {
     return out;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: remember the largest size configured on each
+// device so that a process that drives several GPUs (or switches device) configures every one of them.
+struct SmemAttrCache { size_t bytes[64] = {}; };
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(F kernel, size_t bytes, SmemAttrCache& cache) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (cache.bytes[dev] >= bytes && bytes > 0) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cache.bytes[dev] = bytes;
+    return e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Generic fp32 direct convolution (CUDA cores).  Correctness anchor + the RST_PRECISION_FP32 path.
 // ---------------------------------------------------------------------------------------------

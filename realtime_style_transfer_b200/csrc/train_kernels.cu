@@ -214,10 +214,11 @@ template <int A, int NBG, int KS, int KYB>
 static cudaError_t launch_wgrad_direct(const WgradDirect& p, cudaStream_t s) {
     constexpr int TH = 4, TW = 8 * KS, PW = TW + KS - 1, PH = TH + KYB - 1, NT = KYB * A * NBG, THREADS = (NT + 31) / 32 * 32;
     const size_t smem = (size_t)(TH * TW * NBG * 4 + PH * PW * A) * sizeof(float);
-    static int per_sm = 0;
+    static SmemAttrCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(wgrad_direct_f32_kernel<A, NBG, KS, KYB>, smem, configured)) return e;
+    static int per_sm = 0;                                     // a property of the kernel and the architecture, not of the device
     if (!per_sm) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_direct_f32_kernel<A, NBG, KS, KYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wgrad_direct_f32_kernel<A, NBG, KS, KYB>, THREADS, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wgrad_direct_f32_kernel<A, NBG, KS, KYB>, THREADS, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }

@@ -192,12 +192,8 @@ cudaError_t launch_wgrad_tf32(const float* x, const float* g, float* dw, float* 
         !encode_halo_map(&tmG, g, B, H, W, 256, 64, 1, kWgTW, err, true) || !encode_halo_map(&tmGlo, glo, B, H, W, 256, 64, 1, kWgTW, err, true))
         return cudaErrorInvalidValue;
     const size_t smem = (size_t)kWgStages * kWgStage + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemAttrCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(wgrad_tf32_kernel, smem, configured)) return e;
     const int tiles_w = ceil_div(W, kWgTW);
     const long long items = (long long)B * H * tiles_w;
     int nslices = num_sms / 3;

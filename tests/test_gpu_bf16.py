@@ -265,3 +265,23 @@ def test_streaming_predict_frames_matches_predict(cuda_device):
         model.close()
     finally:
         mixed_precision.set_global_policy("float32")
+
+
+def test_two_devices_in_one_process(cuda_device):
+    """Kernel attributes (dynamic shared-memory limits) are per device: a process that serves two GPUs must configure both.
+    Runs the same frames on cuda:0 and cuda:1 from one process and expects identical outputs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    shape_in, shape_out = (64, 128, 17), (64, 128, 3)
+    spec = O.TransferSpec(shape_in, shape_out, 16, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=17).channels, seed=0, unit_depth=True)
+    params = np.random.default_rng(2).uniform(0.3, 1.2, (2, 1, spec.num_style_parameters)).astype(np.float32)
+    outs = []
+    for device in (0, 1):
+        ctx = _native.NativeContext(in_shape=shape_in, out_shape=shape_out, bottleneck_res_y=16, bottleneck_num_filters=128,
+                                    num_styles=1, max_batch=2, precision=_native.PRECISION_BF16, device=device)
+        ctx.set_weights(weights)
+        outs.append(ctx.transfer_forward_host(content, params))
+        ctx.close()
+    assert np.isfinite(outs[1]).all() and np.array_equal(outs[0], outs[1])
