@@ -22,7 +22,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // conv2d / conv2d_transpose, padding='same' semantics supplied by the caller as pad_t/pad_l.
 // GEMM view: M = B*Ho*Wo output pixels, N = Co, K = kh*kw*Ci.  BMxBN tile per CTA, BK = 16.
 // ---------------------------------------------------------------------------------------------
-template <int BM, int BN, int TM, int TN>
+// PHASE (stride-2 input-gradient form only): one launch per output parity (ph_y, ph_x).  Only the filter taps whose parity
+// meets the stride are enumerated (1, 2, 2 or 4 of the 9 taps of a 3x3 kernel) instead of multiplying the others by zero.
+template <int BM, int BN, int TM, int TN, bool PHASE>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const ConvF32 p) {
     constexpr int BK = 16;
     constexpr int NT = (BM / TM) * (BN / TN);
@@ -36,8 +38,12 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
     __shared__ float Bs[BK][BN + 4];
 
     const int tid = threadIdx.x;
-    const long long M = (long long)p.B * p.Ho * p.Wo;
-    const int K = p.kh * p.kw * p.Ci;
+    // PHASE: the pixel grid of this launch is the (Hp x Wp) sub-lattice oy = 2 i + ph_y, ox = 2 j + ph_x
+    const int Hp = PHASE ? (p.Ho - p.ph_y + 1) / 2 : p.Ho, Wp = PHASE ? (p.Wo - p.ph_x + 1) / 2 : p.Wo;
+    const int ky0 = PHASE ? (p.ph_y + p.pad_t) & 1 : 0, kx0 = PHASE ? (p.ph_x + p.pad_l) & 1 : 0;
+    const int nky = PHASE ? (p.kh - ky0 + 1) / 2 : p.kh, nkx = PHASE ? (p.kw - kx0 + 1) / 2 : p.kw;
+    const long long M = (long long)p.B * Hp * Wp;
+    const int K = nky * nkx * p.Ci;
     const long long m0 = (long long)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
 
@@ -48,11 +54,11 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
     for (int j = 0; j < A_PASSES; ++j) {
         long long m = m0 + a_r + j * A_ROWS;
         if (m < M) {
-            int ox = (int)(m % p.Wo);
-            long long t = m / p.Wo;
-            a_ox[j] = ox;
-            a_oy[j] = (int)(t % p.Ho);
-            a_n[j] = (int)(t / p.Ho);
+            int ox = (int)(m % Wp);
+            long long t = m / Wp;
+            a_ox[j] = PHASE ? 2 * ox + p.ph_x : ox;
+            a_oy[j] = PHASE ? 2 * (int)(t % Hp) + p.ph_y : (int)(t % Hp);
+            a_n[j] = (int)(t / Hp);
         } else {
             a_n[j] = -1; a_oy[j] = 0; a_ox[j] = 0;
         }
@@ -77,8 +83,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
             if (kvalid) {
                 int tap = kk / p.Ci;
                 ci = kk - tap * p.Ci;
-                ky = tap / p.kw;
-                kx = tap - ky * p.kw;
+                ky = tap / nkx;
+                kx = tap - ky * nkx;
+                if (PHASE) { ky = ky0 + 2 * ky; kx = kx0 + 2 * kx; }
             }
 #pragma unroll
             for (int j = 0; j < A_PASSES; ++j) {
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
                 if (kk < K && co < p.Co) {
                     int tap = kk / p.Ci;
                     int ci = kk - tap * p.Ci;
+                    if (PHASE) { const int ty_ = tap / nkx; tap = (ky0 + 2 * ty_) * p.kw + kx0 + 2 * (tap - ty_ * nkx); }
                     v = __ldg(p.w + tap * p.w_tap + ci * p.w_ci + co * p.w_co);
                 }
                 Bs[r][b_c] = v;
@@ -152,6 +160,11 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_f32_kernel(const C
             if (p.post_scale) v = v * __ldg(p.post_scale + co) + __ldg(p.post_shift + co);
             v = apply_act(v, p.act2);
             long long o = m * p.Co + co;
+            if (PHASE) {
+                const int ox = (int)(m % Wp);
+                const long long t = m / Wp;
+                o = ((((long long)(t / Hp)) * p.Ho + 2 * (int)(t % Hp) + p.ph_y) * p.Wo + 2 * ox + p.ph_x) * p.Co + co;
+            }
             if (p.residual) v += __ldg(p.residual + o);
             if (p.out_tf32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
             p.y[o] = v;
@@ -289,12 +302,30 @@ cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
         if (p.kh == 9 && p.Co <= 32) return launch_conv_direct<32, 9>(p, s);
         if (p.kh == 3 && p.Co <= 4) return launch_conv_direct<4, 3>(p, s);
     }
+    static const bool phases_off = [] { const char* e = getenv("RST_CONV_PHASES"); return e && e[0] == '0'; }();
+    if (p.transposed && p.stride == 2 && !phases_off) {
+        // four launches, one per output parity, each over its own quarter of the pixels and its own subset of the taps
+        for (int ph = 0; ph < 4; ++ph) {
+            ConvF32 q = p;
+            q.ph_y = ph >> 1; q.ph_x = ph & 1;
+            const long long Mp = (long long)p.B * ((p.Ho - q.ph_y + 1) / 2) * ((p.Wo - q.ph_x + 1) / 2);
+            if (Mp == 0) continue;
+            if (p.Co > 16) {
+                dim3 grid((unsigned)((Mp + 63) / 64), (unsigned)ceil_div(p.Co, 64));
+                conv_f32_kernel<64, 64, 4, 4, true><<<grid, 256, 0, s>>>(q);
+            } else {
+                dim3 grid((unsigned)((Mp + 127) / 128), 1);
+                conv_f32_kernel<128, 16, 4, 2, true><<<grid, 256, 0, s>>>(q);
+            }
+        }
+        return cudaGetLastError();
+    }
     if (p.Co > 16) {
         dim3 grid((unsigned)((M + 63) / 64), (unsigned)ceil_div(p.Co, 64));
-        conv_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
+        conv_f32_kernel<64, 64, 4, 4, false><<<grid, 256, 0, s>>>(p);
     } else {
         dim3 grid((unsigned)((M + 127) / 128), 1);
-        conv_f32_kernel<128, 16, 4, 2><<<grid, 256, 0, s>>>(p);
+        conv_f32_kernel<128, 16, 4, 2, false><<<grid, 256, 0, s>>>(p);
     }
     return cudaGetLastError();
 }

@@ -60,6 +60,7 @@ struct ConvF32 {
     int act2 = ACT_NONE;
     const float* residual = nullptr;
     int out_tf32 = 0;                       // round the stored value to tf32 (it feeds a tf32 tensor-core conv, which truncates)
+    int ph_y = 0, ph_x = 0;                 // set by launch_conv_f32: output parity of one launch of a stride-2 input-gradient conv
 };
 cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s);
 
