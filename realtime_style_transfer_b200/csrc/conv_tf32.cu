@@ -14,6 +14,7 @@ Tf32Conv3x3::~Tf32Conv3x3() {
 
 // packed[j][blk][n][r]: K-step ks = 4*blk + r/8, element e = r%8 -> channel group g = ks/36, tap = (ks%36)/4,
 // input channel g*32 + ((ks%36)%4)*8 + e; output channel j*nb + n.  Rounded to tf32 (nearest).
+// Split convs: the activation side is [x_hi | x_lo | x_hi], the weight side [w_hi | w_hi | w_lo].
 __global__ void tf32_pack_weights_kernel(const float* __restrict__ k, float* __restrict__ out, int ci_layer, int co_layer,
                                          int input_gradient, int nb, int blocks, int ci_real, long long total) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,20 +37,33 @@ __global__ void tf32_pack_weights_kernel(const float* __restrict__ k, float* __r
     out[idx] = v;
 }
 
-// x (P, c) -> [tf32(x) | tf32(x - tf32(x)) | tf32(x)] (P, 3c)
-__global__ void tf32_split_expand_kernel(const float* __restrict__ x, float* __restrict__ out, int c, long long total) {
+// x (P, c) -> [tf32(x) | tf32(x - tf32(x))] (P, 2c), four channels per thread; the conv reads [x_hi | x_lo | x_hi] out of it
+__global__ void tf32_split_expand_kernel(const float* __restrict__ x, float* __restrict__ out, int c4, long long total4) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const long long pix = i / c;
-    const int ch = (int)(i - pix * c);
-    const float v = x[i];
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    const float hi = __uint_as_float(r);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - hi));
-    const float lo = __uint_as_float(r);
-    float* o = out + pix * 3 * c + ch;
-    o[0] = hi; o[c] = lo; o[2 * c] = hi;
+    if (i >= total4) return;
+    const long long pix = i / c4;
+    const int ch4 = (int)(i - pix * c4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 hi = make_float4(umma::round_tf32(v.x), umma::round_tf32(v.y), umma::round_tf32(v.z), umma::round_tf32(v.w));
+    float4 lo = make_float4(umma::round_tf32(v.x - hi.x), umma::round_tf32(v.y - hi.y), umma::round_tf32(v.z - hi.z), umma::round_tf32(v.w - hi.w));
+    float4* o = reinterpret_cast<float4*>(out) + pix * 2 * c4 + ch4;
+    o[0] = hi; o[c4] = lo;
+}
+
+// x_lo = rna_tf32(x - trunc_tf32(x)): the compensation term when the MMA reads the RAW tensor as the hi part (kind::tf32 uses
+// the upper 19 bits of an fp32 operand).  Used by the tensor-core weight gradient (wgrad_tf32.cu).
+__global__ void tf32_lo_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    auto lo = [](float f) { return umma::round_tf32(f - __uint_as_float(__float_as_uint(f) & 0xFFFFE000u)); };
+    reinterpret_cast<float4*>(out)[i] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+}
+cudaError_t launch_tf32_lo(const float* in, float* out, long long n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    if (n % 4 != 0) return cudaErrorInvalidValue;
+    tf32_lo_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(in, out, n / 4);
+    return cudaGetLastError();
 }
 
 bool Tf32Conv3x3::setup_shape(int ci_layer_, int co_layer_, bool relu_, bool input_gradient_, std::string* err, bool split_) {
@@ -116,14 +130,16 @@ bool Tf32Conv3x3::setup(int ci_layer_, int co_layer_, const float* k, const floa
     return true;
 }
 
+// x: (B, H, W, ci) for a plain conv; for a split conv the expanded tensor (B, H, W, 2 ci / 3) = [x_hi | x_lo]
 cudaError_t Tf32Conv3x3::run(const float* x, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err) {
     const CUtensorMap* tmA = nullptr;
     for (auto& b : inputs)
         if (b.x == x && b.B == B && b.H == H && b.W == W) { tmA = &b.tm; break; }
+    const int c_stored = split ? ci / 3 * 2 : ci;
     if (!tmA) {
         BoundInput b{x, B, H, W, {}};
-        // the activation map addresses bytes: an fp32 pixel with ci channels is a row of 2*ci bf16-sized elements
-        if (!encode_halo_map(&b.tm, x, B, H, W, 2 * ci, 64, p.halo_h, p.halo_w, err)) return cudaErrorInvalidValue;
+        // the activation map addresses bytes: an fp32 pixel with c channels is a row of 2*c bf16-sized elements
+        if (!encode_halo_map(&b.tm, x, B, H, W, 2 * c_stored, 64, p.halo_h, p.halo_w, err)) return cudaErrorInvalidValue;
         if (inputs.size() >= 8) inputs.erase(inputs.begin());
         inputs.push_back(b);
         tmA = &inputs.back().tm;
@@ -134,6 +150,7 @@ cudaError_t Tf32Conv3x3::run(const float* x, float* y, int B, int H, int W, int 
     q.out_H = H; q.out_W = W; q.out_C = co;
     q.y_f32 = 1; q.stats = nullptr;
     q.store_exact = split ? 1 : 0;
+    q.a_wrap = split ? c_stored / 32 : 0;
     for (int j = 0; j < nblk; ++j) {
         q.y = y + (size_t)j * nb;
         q.bias = ext_bias ? ext_bias + (size_t)j * nb : nullptr;
@@ -147,9 +164,9 @@ cudaError_t Tf32Conv3x3::run_split(const float* x, float* scratch, float* y, int
                                    std::string* err) {
     if (!split) return run(x, y, B, H, W, num_sms, s, err);
     const int c = ci / 3;
-    const long long total = (long long)B * H * W * c;
-    if (total == 0) return cudaSuccess;
-    tf32_split_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, scratch, c, total);
+    const long long total4 = (long long)B * H * W * c / 4;
+    if (total4 == 0) return cudaSuccess;
+    tf32_split_expand_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(x, scratch, c / 4, total4);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return run(scratch, y, B, H, W, num_sms, s, err);

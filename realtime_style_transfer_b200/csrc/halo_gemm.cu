@@ -127,7 +127,11 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     mbar_expect_tx(&a_full[stage], halo_bytes);
                     if (SCH == SCH_S2D) tma_load_5d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], 0, h0, 0, w0, n);
-                    else tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 * p.a_w_mul + p.ox, n);
+                    else if ((MODE & MODE_TF32) && p.a_wrap) {
+                        // split tf32: one conv over [x_hi | x_lo | x_hi]; the tensor stores [x_hi | x_lo], the third part re-reads the first
+                        tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], (g >= p.a_wrap ? g - p.a_wrap : g) * ROW_ELEMS,
+                                    h0 + p.oy, w0 * p.a_w_mul + p.ox, n);
+                    } else tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 * p.a_w_mul + p.ox, n);
                     if (++stage == (uint32_t)p.n_astages) { stage = 0; phase ^= 1; }
                 }
             }

@@ -141,6 +141,8 @@ struct HaloGemmParams {
     const float* post_shift = nullptr;
     double* stats = nullptr;             // (B, stats_c, 2) [sum, sumsq] or null
     int stats_c = 0;
+    int a_wrap = 0;                      // split tf32: the tensor holds a_wrap channel groups [x_hi | x_lo]; groups >= a_wrap re-read
+                                         // group g - a_wrap (the conv runs over [x_hi | x_lo | x_hi] without storing x_hi twice)
     int store_exact = 0;                 // MODE_TF32: store the fp32 accumulator as is (split-tf32 convs) instead of rounding to tf32
 };
 
@@ -186,6 +188,8 @@ void pack_b_blocks(int total_ksteps, int N, const std::function<float(int, int, 
 // ---- tf32 3x3 convolution on fp32 NHWC tensors (conv_tf32.cu): the VGG16 loss model's layers and their input gradients ----
 // 3x3, stride 1, 'same'; Cin % 32 == 0, Cout % 64 == 0.  Operands are fp32 bit patterns consumed as tf32 by tcgen05
 // (kind::tf32, fp32 accumulation); weights are rounded to tf32 (nearest) once, outputs are stored rounded to tf32.
+// x_lo = rna_tf32(x - trunc_tf32(x)), n % 4 == 0 (conv_tf32.cu)
+cudaError_t launch_tf32_lo(const float* in, float* out, long long n, cudaStream_t s);
 struct Tf32Conv3x3 {
     int ci = 0, co = 0, nb = 128, nblk = 0;
     bool relu = false;
@@ -214,7 +218,7 @@ struct Tf32Conv3x3 {
     // [x_hi | x_lo | x_hi] with weights [w_hi | w_hi | w_lo]; run() then needs a scratch tensor of 3x the input size.
     bool setup_shape(int ci_layer, int co_layer, bool relu, bool input_gradient, std::string* err, bool split = false);
     bool split = false;
-    size_t scratch_floats(int B, int H, int W) const { return split ? (size_t)B * H * W * ci : 0; }
+    size_t scratch_floats(int B, int H, int W) const { return split ? (size_t)B * H * W * (ci / 3) * 2 : 0; }   // [x_hi | x_lo]
     cudaError_t run_split(const float* x, float* scratch, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
     cudaError_t repack(const float* d_kernel, const float* d_bias, cudaStream_t s);
     cudaError_t run(const float* x, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);

@@ -31,14 +31,6 @@ constexpr int kWgStages = 3;
 constexpr int kWgThreads = 192;                        // TMA warp, MMA warp, 4 epilogue warps
 constexpr int kWgFlush = 40;                           // work items between accumulator flushes
 
-__global__ void tf32_lo_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
-    auto lo = [](float f) { return round_tf32(f - __uint_as_float(__float_as_uint(f) & 0xFFFFE000u)); };
-    reinterpret_cast<float4*>(out)[i] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
-}
-
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmGlo, float* __restrict__ dw,
@@ -182,8 +174,9 @@ cudaError_t launch_wgrad_tf32(const float* x, const float* g, float* dw, float* 
     if (split) {
         float* a = lo_scratch;
         float* b = lo_scratch + n;
-        tf32_lo_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(x, a, (long long)(n / 4));
-        tf32_lo_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(g, b, (long long)(n / 4));
+        cudaError_t e = launch_tf32_lo(x, a, (long long)n, s);
+        if (e == cudaSuccess) e = launch_tf32_lo(g, b, (long long)n, s);
+        if (e != cudaSuccess) return e;
         xlo = a; glo = b;
     }
     CUtensorMap tmX, tmXlo, tmG, tmGlo;
