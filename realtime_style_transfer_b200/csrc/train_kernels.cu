@@ -15,9 +15,9 @@ static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 // One CTA = one filter tap x 32 input channels x 32 output channels x a slab of base pixels.
 // ---------------------------------------------------------------------------------------------------------------
 // TM x TN = input-channel x output-channel tile of one tap; 16 x 16 threads, each a (TM/16) x (TN/16) register tile.
-// RMODE 1 (stride-1 Conv2D): the M dimension of a CTA is a block of (kx, ci) pairs of ONE filter row ky -- for a fixed output
+// RMODE 1 (Conv2D): the M dimension of a CTA is a block of (kx, ci) pairs of ONE filter row ky -- for a fixed output
 // pixel these kw*Ci inputs are contiguous in NHWC memory, so thin layers (17 input channels, 81 taps) fill the tile.
-// RMODE 2 (stride-1 Conv2DTranspose): the same on the gradient side, N = block of (kx, co) pairs (16 -> 3 head: 27 columns).
+// RMODE 2 (Conv2DTranspose): the same on the gradient side, N = block of (kx, co) pairs (16 -> 3 head: 27 columns).
 template <int TM, int TN, int RMODE>
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradF32 p, int ci_blocks, int pix_per_split) {
     constexpr int RM = TM / 16, RN = TN / 16, PIX = 32;
@@ -258,7 +258,9 @@ cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
     const long long NP = (long long)p.B * p.Hb * p.Wb;
     if (NP == 0) return cudaSuccess;
     { cudaError_t e = cudaSuccess; if (try_wgrad_direct(p, s, &e)) return e; }
-    const int rmode = p.stride != 1 ? 0 : (p.transposed ? 2 : 1);
+    // row-contiguous tiles work for any stride: the kw taps of one filter row touch kw ADJACENT pixels of the tap-shifted tensor
+    static const bool rows_s1_only = [] { const char* e = getenv("RST_WGRAD_ROWS_S1"); return e && e[0] == '1'; }();
+    const int rmode = (p.stride != 1 && rows_s1_only) ? 0 : (p.transposed ? 2 : 1);
     const int m_extent = rmode == 1 ? p.kw * p.Ci : p.Ci, n_extent = rmode == 2 ? p.kw * p.Co : p.Co;
     const bool wide_m = m_extent > 32, wide_n = n_extent > 32;
     const bool big = rmode == 1 && m_extent % 128 == 0 && n_extent % 128 == 0;     // trunk 128 -> 128: 8 x 8 register tiles
