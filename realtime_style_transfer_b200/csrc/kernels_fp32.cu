@@ -292,10 +292,93 @@ static cudaError_t launch_conv_direct(const ConvF32& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pointwise (1x1, stride 1) convolution = a plain GEMM over the pixels: the predictor's expand / project layers and their
+// input gradients.  The implicit-GEMM kernel above spends its time on im2col index arithmetic and scalar accesses there
+// (0.44 TB/s on a 16 -> 64 layer); here a pixel row is loaded with 128-bit accesses and stored the same way.
+// 64 pixels x 64 output channels per CTA, 4 x 4 register tiles, K in chunks of 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1x1_f32_kernel(const ConvF32 p) {
+    constexpr int BM = 64, BN = 64, BK = 32;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long M = (long long)p.B * p.Ho * p.Wo;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN, K = p.Ci;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int e = tid; e < BM * BK / 4; e += 256) {            // 8 float4 per pixel row of the chunk
+            const int px = e >> 3, k4 = (e & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + px < M && k0 + k4 < K) {
+                v = __ldg(reinterpret_cast<const float4*>(p.x + (m0 + px) * K + k0 + k4));
+                v.x = v.x * p.in_scale + p.in_shift; v.y = v.y * p.in_scale + p.in_shift;
+                v.z = v.z * p.in_scale + p.in_shift; v.w = v.w * p.in_scale + p.in_shift;
+            }
+            As[k4][px] = v.x; As[k4 + 1][px] = v.y; As[k4 + 2][px] = v.z; As[k4 + 3][px] = v.w;
+        }
+#pragma unroll
+        for (int e = tid; e < BK * BN; e += 256) {
+            const int k = e / BN, c = e % BN;
+            Bs[k][c] = (k0 + k < K && n0 + c < p.Co) ? __ldg(p.w + (long long)(k0 + k) * p.w_ci + (long long)(n0 + c) * p.w_co) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const int co0 = n0 + tx * 4;
+    if (co0 >= p.Co) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + j < p.Co ? co0 + j : p.Co - 1;   // clamped: never stored
+            float t = acc[i][j];
+            if (p.bias) t += __ldg(p.bias + co);
+            t = apply_act(t, p.act1);
+            if (p.post_scale) t = t * __ldg(p.post_scale + co) + __ldg(p.post_shift + co);
+            t = apply_act(t, p.act2);
+            if (p.residual) t += __ldg(p.residual + m * p.Co + co);
+            if (p.out_tf32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t)); t = __uint_as_float(r); }
+            v[j] = t;
+        }
+        float* o = p.y + m * p.Co + co0;
+        if (p.Co % 4 == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (co0 + j < p.Co) o[j] = v[j];
+        }
+    }
+}
+
 cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
     long long M = (long long)p.B * p.Ho * p.Wo;
     if (M == 0) return cudaSuccess;
     static const bool direct_off = [] { const char* e = getenv("RST_CONV_DIRECT"); return e && e[0] == '0'; }();
+    if (!direct_off && p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad_t == 0 && p.pad_l == 0 && p.Hi == p.Ho && p.Wi == p.Wo &&
+        p.Ci % 4 == 0 && M >= 4096 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0) {
+        dim3 grid((unsigned)((M + 63) / 64), (unsigned)ceil_div(p.Co, 64));
+        conv1x1_f32_kernel<<<grid, 256, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     if (!direct_off && p.stride == 1 && p.kh == p.kw && p.Ho >= 64 && p.Wo >= 64 && p.B <= 65535) {
         if (p.kh == 9 && p.Co <= 4) return launch_conv_direct<4, 9>(p, s);
         if (p.kh == 9 && p.Co <= 16) return launch_conv_direct<16, 9>(p, s);

@@ -77,6 +77,10 @@ def test_create_rejects_bad_configs(cuda_device):
     (2, 67, 64, 3, 16, 9, 1, False),      # head's input gradient: 3 -> 16
     (1, 65, 130, 64, 3, 3, 1, False),     # loss model conv1_1 input gradient: 64 -> 3, four channel chunks
     (1, 64, 64, 64, 3, 3, 1, True),
+    # pointwise layers of the predictor: plain GEMM kernel (1x1, stride 1, Ci % 4 == 0, at least 4096 pixels)
+    (2, 64, 64, 16, 72, 1, 1, False),
+    (1, 64, 80, 72, 24, 1, 1, False),     # K = 72: three chunks, the last one partial
+    (1, 70, 61, 8, 6, 1, 1, False),       # ragged pixel tile, Co % 4 != 0
 ])
 def test_op_conv2d_fp32(cuda_device, b, h, w, ci, co, k, s, transposed):
     rng = np.random.default_rng(b * 1000 + h * 10 + k)
