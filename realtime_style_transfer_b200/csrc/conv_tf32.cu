@@ -38,12 +38,18 @@ __global__ void tf32_pack_weights_kernel(const float* __restrict__ k, float* __r
 }
 
 // x (P, c) -> [tf32(x) | tf32(x - tf32(x))] (P, 2c), four channels per thread; the conv reads [x_hi | x_lo | x_hi] out of it
-__global__ void tf32_split_expand_kernel(const float* __restrict__ x, float* __restrict__ out, int c4, long long total4) {
+// relu_mask (optional): x is a gradient that still has to be masked by the ReLU of its layer, v = mask > 0 ? x : 0
+__global__ void tf32_split_expand_kernel(const float* __restrict__ x, float* __restrict__ out, int c4, long long total4,
+                                         const float* __restrict__ relu_mask) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const long long pix = i / c4;
     const int ch4 = (int)(i - pix * c4);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    if (relu_mask) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(relu_mask) + i);
+        v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    }
     float4 hi = make_float4(umma::round_tf32(v.x), umma::round_tf32(v.y), umma::round_tf32(v.z), umma::round_tf32(v.w));
     float4 lo = make_float4(umma::round_tf32(v.x - hi.x), umma::round_tf32(v.y - hi.y), umma::round_tf32(v.z - hi.z), umma::round_tf32(v.w - hi.w));
     float4* o = reinterpret_cast<float4*>(out) + pix * 2 * c4 + ch4;
@@ -161,12 +167,12 @@ cudaError_t Tf32Conv3x3::run(const float* x, float* y, int B, int H, int W, int 
 }
 
 cudaError_t Tf32Conv3x3::run_split(const float* x, float* scratch, float* y, int B, int H, int W, int num_sms, cudaStream_t s,
-                                   std::string* err) {
-    if (!split) return run(x, y, B, H, W, num_sms, s, err);
+                                   std::string* err, const float* relu_mask) {
+    if (!split) return relu_mask ? cudaErrorInvalidValue : run(x, y, B, H, W, num_sms, s, err);   // the mask rides on the expansion
     const int c = ci / 3;
     const long long total4 = (long long)B * H * W * c / 4;
     if (total4 == 0) return cudaSuccess;
-    tf32_split_expand_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(x, scratch, c / 4, total4);
+    tf32_split_expand_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(x, scratch, c / 4, total4, relu_mask);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return run(scratch, y, B, H, W, num_sms, s, err);

@@ -219,7 +219,9 @@ struct Tf32Conv3x3 {
     bool setup_shape(int ci_layer, int co_layer, bool relu, bool input_gradient, std::string* err, bool split = false);
     bool split = false;
     size_t scratch_floats(int B, int H, int W) const { return split ? (size_t)B * H * W * (ci / 3) * 2 : 0; }   // [x_hi | x_lo]
-    cudaError_t run_split(const float* x, float* scratch, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
+    // relu_mask (split convs only): the input is masked by (relu_mask > 0) while it is expanded (ReLU backward fused into the pass)
+    cudaError_t run_split(const float* x, float* scratch, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err,
+                          const float* relu_mask = nullptr);
     cudaError_t repack(const float* d_kernel, const float* d_bias, cudaStream_t s);
     cudaError_t run(const float* x, float* y, int B, int H, int W, int num_sms, cudaStream_t s, std::string* err);
 };

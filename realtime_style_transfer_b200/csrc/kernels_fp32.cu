@@ -393,9 +393,12 @@ cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
             q.ph_y = ph >> 1; q.ph_x = ph & 1;
             const long long Mp = (long long)p.B * ((p.Ho - q.ph_y + 1) / 2) * ((p.Wo - q.ph_x + 1) / 2);
             if (Mp == 0) continue;
-            if (p.Co > 16) {
+            if (p.Co > 32) {
                 dim3 grid((unsigned)((Mp + 63) / 64), (unsigned)ceil_div(p.Co, 64));
                 conv_f32_kernel<64, 64, 4, 4, true><<<grid, 256, 0, s>>>(q);
+            } else if (p.Co > 16) {
+                dim3 grid((unsigned)((Mp + 127) / 128), 1);
+                conv_f32_kernel<128, 32, 4, 4, true><<<grid, 256, 0, s>>>(q);
             } else {
                 dim3 grid((unsigned)((Mp + 127) / 128), 1);
                 conv_f32_kernel<128, 16, 4, 2, true><<<grid, 256, 0, s>>>(q);
@@ -403,9 +406,12 @@ cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
         }
         return cudaGetLastError();
     }
-    if (p.Co > 16) {
+    if (p.Co > 32) {
         dim3 grid((unsigned)((M + 63) / 64), (unsigned)ceil_div(p.Co, 64));
         conv_f32_kernel<64, 64, 4, 4, false><<<grid, 256, 0, s>>>(p);
+    } else if (p.Co > 16) {                                       // 17..32 output channels: no half-empty 64-wide tile
+        dim3 grid((unsigned)((M + 127) / 128), 1);
+        conv_f32_kernel<128, 32, 4, 4, false><<<grid, 256, 0, s>>>(p);
     } else {
         dim3 grid((unsigned)((M + 127) / 128), 1);
         conv_f32_kernel<128, 16, 4, 2, false><<<grid, 256, 0, s>>>(p);

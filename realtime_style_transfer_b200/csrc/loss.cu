@@ -455,10 +455,13 @@ extern "C" int rst_loss_backward(rst_loss* c, const float* d_pred, float* d_grad
                 LCUDA(c, launch_conv_f32(p, s));
             }
         }
-        relu_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(g, c->act[i], n);
-        if (c->bwd[i] && !getenv("RST_EXP_LOSS_BWD_FP32")) {      // (env: experiment switch, see profiles/r01_03_experiments.md)
+        const bool tc_bwd = c->bwd[i] && !getenv("RST_EXP_LOSS_BWD_FP32");      // (env: experiment switch, see profiles/r01_03_experiments.md)
+        const bool fused_mask = tc_bwd && c->bwd[i]->split;                      // the split expansion applies the ReLU mask itself
+        if (!fused_mask) relu_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(g, c->act[i], n);
+        if (tc_bwd) {
             std::string err;
-            cudaError_t e = c->bwd[i]->run_split(g, c->split_scratch, gn, B, c->lh[i], c->lw[i], c->num_sms, s, &err);
+            cudaError_t e = c->bwd[i]->run_split(g, c->split_scratch, gn, B, c->lh[i], c->lw[i], c->num_sms, s, &err,
+                                                 fused_mask ? c->act[i] : nullptr);
             if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "tf32 dgrad " + kVgg[i].name + ": " + (err.empty() ? cudaGetErrorString(e) : err));
             std::swap(g, gn);
             continue;
