@@ -66,4 +66,9 @@ def allreduce_sum_(tensor):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+        if getattr(tensor, "is_cuda", False):
+            # NCCL runs on torch's stream, the native trainer on its own: the optimizer step that follows must not start
+            # before the reduced gradient has landed (and the next backward must not overwrite it while it is being read)
+            import torch
+            torch.cuda.synchronize(tensor.device)
     return tensor
