@@ -3,10 +3,28 @@
 #include "train_kernels.cuh"
 
 #include <cstdlib>
+#include <initializer_list>
 
 namespace rst {
 
 static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
+
+// V consecutive floats per thread (V = 4: one 128-bit access) for the elementwise passes over NHWC tensors
+template <int V> __device__ __forceinline__ void ldv(const float* p, float* v);
+template <> __device__ __forceinline__ void ldv<1>(const float* p, float* v) { v[0] = *p; }
+template <> __device__ __forceinline__ void ldv<4>(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <int V> __device__ __forceinline__ void stv(float* p, const float* v);
+template <> __device__ __forceinline__ void stv<1>(float* p, const float* v) { *p = v[0]; }
+template <> __device__ __forceinline__ void stv<4>(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+// V = 4 needs whole groups of 4 channels and 16-byte aligned tensors
+static inline bool vec4_ok(long long total, int C, std::initializer_list<const void*> ptrs) {
+    if (total % 4 != 0 || C % 4 != 0) return false;
+    for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 15) return false;
+    return true;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight gradient of Conv2D / Conv2DTranspose ('same'), split over base pixels with fp32 atomics.
@@ -339,64 +357,95 @@ cudaError_t launch_norm_finalize(const double* stats, int G, int C, double count
 }
 
 // y = act(x*a[g,c] + b[g,c]) (+ residual);  g = sample index when per_sample, else 0
+template <int V>
 __global__ void affine_act_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ a,
                                   const float* __restrict__ b, const float* __restrict__ residual, long long PC, int C,
                                   int per_sample, int act, long long total) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (i >= total) return;
     const int c = (int)(i % C);
     const long long gidx = per_sample ? (i / PC) * C + c : c;
-    float v = fmaf(x[i], a[gidx], b[gidx]);
-    if (act == ACT_RELU) v = fmaxf(v, 0.f);
-    else if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
-    else if (act == ACT_HSIGMOID) v = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    else if (act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    if (residual) v += residual[i];
-    y[i] = v;
+    float xv[V], rv[V], yv[V];
+    ldv<V>(x + i, xv);
+    if (residual) ldv<V>(residual + i, rv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        float v = fmaf(xv[j], a[gidx + j], b[gidx + j]);
+        if (act == ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+        else if (act == ACT_HSIGMOID) v = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        else if (act == ACT_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        if (residual) v += rv[j];
+        yv[j] = v;
+    }
+    stv<V>(y + i, yv);
 }
 cudaError_t launch_affine_act(const float* x, float* y, const float* a, const float* b, const float* residual, int B, long long P,
                               int C, int per_sample, int act, cudaStream_t s) {
     const long long total = (long long)B * P * C;
     if (total == 0) return cudaSuccess;
-    affine_act_kernel<<<nblk(total), 256, 0, s>>>(x, y, a, b, residual, P * C, C, per_sample, act, total);
+    if (vec4_ok(total, C, {x, y, residual}))
+        affine_act_kernel<4><<<nblk(total / 4), 256, 0, s>>>(x, y, a, b, residual, P * C, C, per_sample, act, total);
+    else
+        affine_act_kernel<1><<<nblk(total), 256, 0, s>>>(x, y, a, b, residual, P * C, C, per_sample, act, total);
     return cudaGetLastError();
 }
 
 // g *= act'(out)   (ReLU: out > 0;  sigmoid: out*(1-out))
+template <int V>
 __global__ void act_bwd_kernel(float* __restrict__ g, const float* __restrict__ out, int act, long long n) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (i >= n) return;
-    const float o = out[i];
-    if (act == ACT_RELU) { if (!(o > 0.f)) g[i] = 0.f; }
-    else if (act == ACT_SIGMOID) g[i] *= o * (1.f - o);
-    else if (act == ACT_HSIGMOID) g[i] = (o > 0.f && o < 1.f) ? g[i] * (1.f / 6.f) : 0.f;
+    float ov[V], gv[V];
+    ldv<V>(out + i, ov);
+    ldv<V>(g + i, gv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const float o = ov[j];
+        if (act == ACT_RELU) { if (!(o > 0.f)) gv[j] = 0.f; }
+        else if (act == ACT_SIGMOID) gv[j] *= o * (1.f - o);
+        else if (act == ACT_HSIGMOID) gv[j] = (o > 0.f && o < 1.f) ? gv[j] * (1.f / 6.f) : 0.f;
+    }
+    stv<V>(g + i, gv);
 }
 cudaError_t launch_act_bwd(float* g, const float* out, int act, long long n, cudaStream_t s) {
     if (n == 0 || act == ACT_NONE) return cudaSuccess;
-    act_bwd_kernel<<<nblk(n), 256, 0, s>>>(g, out, act, n);
+    if (vec4_ok(n, 4, {g, out})) act_bwd_kernel<4><<<nblk(n / 4), 256, 0, s>>>(g, out, act, n);
+    else act_bwd_kernel<1><<<nblk(n), 256, 0, s>>>(g, out, act, n);
     return cudaGetLastError();
 }
 
 // g *= act'(u), u = x*a[g,c] + b[g,c] recomputed from the saved pre-normalisation tensor
+template <int V>
 __global__ void affine_act_bwd_kernel(float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ a,
                                       const float* __restrict__ b, long long PC, int C, int per_sample, int act, long long total) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (i >= total) return;
     const int c = (int)(i % C);
     const long long gidx = per_sample ? (i / PC) * C + c : c;
-    const float u = fmaf(x[i], a[gidx], b[gidx]);
-    float d = 1.f;
-    if (act == ACT_RELU) d = u > 0.f ? 1.f : 0.f;
-    else if (act == ACT_SIGMOID) { const float sg = 1.f / (1.f + expf(-u)); d = sg * (1.f - sg); }
-    else if (act == ACT_HSIGMOID) d = (u > -3.f && u < 3.f) ? 1.f / 6.f : 0.f;
-    else if (act == ACT_HSWISH) d = u <= -3.f ? 0.f : (u >= 3.f ? 1.f : (2.f * u + 3.f) / 6.f);
-    g[i] *= d;
+    float xv[V], gv[V];
+    ldv<V>(x + i, xv);
+    ldv<V>(g + i, gv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const float u = fmaf(xv[j], a[gidx + j], b[gidx + j]);
+        float d = 1.f;
+        if (act == ACT_RELU) d = u > 0.f ? 1.f : 0.f;
+        else if (act == ACT_SIGMOID) { const float sg = 1.f / (1.f + expf(-u)); d = sg * (1.f - sg); }
+        else if (act == ACT_HSIGMOID) d = (u > -3.f && u < 3.f) ? 1.f / 6.f : 0.f;
+        else if (act == ACT_HSWISH) d = u <= -3.f ? 0.f : (u >= 3.f ? 1.f : (2.f * u + 3.f) / 6.f);
+        gv[j] *= d;
+    }
+    stv<V>(g + i, gv);
 }
 cudaError_t launch_affine_act_bwd(float* g, const float* x, const float* a, const float* b, int B, long long P, int C,
                                   int per_sample, int act, cudaStream_t s) {
     const long long total = (long long)B * P * C;
     if (total == 0 || act == ACT_NONE) return cudaSuccess;
-    affine_act_bwd_kernel<<<nblk(total), 256, 0, s>>>(g, x, a, b, P * C, C, per_sample, act, total);
+    if (vec4_ok(total, C, {g, x}))
+        affine_act_bwd_kernel<4><<<nblk(total / 4), 256, 0, s>>>(g, x, a, b, P * C, C, per_sample, act, total);
+    else
+        affine_act_bwd_kernel<1><<<nblk(total), 256, 0, s>>>(g, x, a, b, P * C, C, per_sample, act, total);
     return cudaGetLastError();
 }
 
@@ -465,25 +514,38 @@ cudaError_t launch_norm_bwd_reduce(const float* g, const float* x, const float* 
 }
 
 // gx = a[g,c] * (g - r1/N - xhat * r2/N);   r indexed per sample (CIN) or per channel (BatchNorm, already reduced over n)
+template <int V>
 __global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
                                       const float* __restrict__ inv, const float* __restrict__ a, const double* __restrict__ r,
                                       float* __restrict__ gx, long long PC, int C, int per_sample, double invN, int accumulate,
                                       long long total) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (i >= total) return;
     const int c = (int)(i % C);
-    const long long gi = per_sample ? (i / PC) * C + c : c;
-    const float xh = (x[i] - mean[gi]) * inv[gi];
-    const float m1 = (float)(r[gi * 2] * invN), m2 = (float)(r[gi * 2 + 1] * invN);
-    const float v = a[gi] * (g[i] - m1 - xh * m2);
-    gx[i] = accumulate ? gx[i] + v : v;
+    const long long g0 = per_sample ? (i / PC) * C + c : c;
+    float gv[V], xv[V], ov[V];
+    ldv<V>(g + i, gv);
+    ldv<V>(x + i, xv);
+    if (accumulate) ldv<V>(gx + i, ov);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const long long gi = g0 + j;
+        const float xh = (xv[j] - mean[gi]) * inv[gi];
+        const float m1 = (float)(r[gi * 2] * invN), m2 = (float)(r[gi * 2 + 1] * invN);
+        const float v = a[gi] * (gv[j] - m1 - xh * m2);
+        ov[j] = accumulate ? ov[j] + v : v;
+    }
+    stv<V>(gx + i, ov);
 }
 cudaError_t launch_norm_bwd_apply(const float* g, const float* x, const float* mean, const float* inv, const float* a,
                                   const double* r, float* gx, int B, long long P, int C, int per_sample, double count,
                                   int accumulate, cudaStream_t s) {
     const long long total = (long long)B * P * C;
     if (total == 0) return cudaSuccess;
-    norm_bwd_apply_kernel<<<nblk(total), 256, 0, s>>>(g, x, mean, inv, a, r, gx, P * C, C, per_sample, 1.0 / count, accumulate, total);
+    if (vec4_ok(total, C, {g, x, gx}))
+        norm_bwd_apply_kernel<4><<<nblk(total / 4), 256, 0, s>>>(g, x, mean, inv, a, r, gx, P * C, C, per_sample, 1.0 / count, accumulate, total);
+    else
+        norm_bwd_apply_kernel<1><<<nblk(total), 256, 0, s>>>(g, x, mean, inv, a, r, gx, P * C, C, per_sample, 1.0 / count, accumulate, total);
     return cudaGetLastError();
 }
 
