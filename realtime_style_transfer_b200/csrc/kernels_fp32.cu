@@ -639,10 +639,11 @@ cudaError_t launch_weights_concat(const float* w_in, float* w_out, long long pix
     return cudaGetLastError();
 }
 
-template <bool MAX>
+// V channels per thread (V = 4: 128-bit accesses when C % 4 == 0 and the tensors are 16-byte aligned)
+template <bool MAX, int V>
 __global__ void pool2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi, int C,
                                  long long total) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (idx >= total) return;
     const int Ho = Hi / 2, Wo = Wi / 2;
     int c = (int)(idx % C);
@@ -652,20 +653,34 @@ __global__ void pool2_f32_kernel(const float* __restrict__ x, float* __restrict_
     int oy = (int)(t % Ho);
     long long n = t / Ho;
     const float* b = x + ((n * Hi + 2 * oy) * Wi + 2 * ox) * C + c;
-    float v00 = b[0], v01 = b[C], v10 = b[(long long)Wi * C], v11 = b[(long long)Wi * C + C];
-    y[idx] = MAX ? fmaxf(fmaxf(v00, v01), fmaxf(v10, v11)) : (v00 + v01 + v10 + v11) * 0.25f;
+    if (V == 4) {
+        const float4 v00 = *reinterpret_cast<const float4*>(b), v01 = *reinterpret_cast<const float4*>(b + C);
+        const float4 v10 = *reinterpret_cast<const float4*>(b + (long long)Wi * C), v11 = *reinterpret_cast<const float4*>(b + (long long)Wi * C + C);
+        float4 o;
+        o.x = MAX ? fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x)) : (v00.x + v01.x + v10.x + v11.x) * 0.25f;
+        o.y = MAX ? fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y)) : (v00.y + v01.y + v10.y + v11.y) * 0.25f;
+        o.z = MAX ? fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z)) : (v00.z + v01.z + v10.z + v11.z) * 0.25f;
+        o.w = MAX ? fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w)) : (v00.w + v01.w + v10.w + v11.w) * 0.25f;
+        *reinterpret_cast<float4*>(y + idx) = o;
+    } else {
+        float v00 = b[0], v01 = b[C], v10 = b[(long long)Wi * C], v11 = b[(long long)Wi * C + C];
+        y[idx] = MAX ? fmaxf(fmaxf(v00, v01), fmaxf(v10, v11)) : (v00 + v01 + v10 + v11) * 0.25f;
+    }
+}
+template <bool MAX>
+static cudaError_t launch_pool2(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
+    long long total = (long long)B * (Hi / 2) * (Wi / 2) * C;
+    if (total == 0) return cudaSuccess;
+    const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (vec) pool2_f32_kernel<MAX, 4><<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(x, y, Hi, Wi, C, total);
+    else pool2_f32_kernel<MAX, 1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, Hi, Wi, C, total);
+    return cudaGetLastError();
 }
 cudaError_t launch_avgpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
-    long long total = (long long)B * (Hi / 2) * (Wi / 2) * C;
-    if (total == 0) return cudaSuccess;
-    pool2_f32_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, Hi, Wi, C, total);
-    return cudaGetLastError();
+    return launch_pool2<false>(x, y, B, Hi, Wi, C, s);
 }
 cudaError_t launch_maxpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s) {
-    long long total = (long long)B * (Hi / 2) * (Wi / 2) * C;
-    if (total == 0) return cudaSuccess;
-    pool2_f32_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, Hi, Wi, C, total);
-    return cudaGetLastError();
+    return launch_pool2<true>(x, y, B, Hi, Wi, C, s);
 }
 
 __global__ void scale_channels_kernel(const float* __restrict__ x, const float* __restrict__ z,
