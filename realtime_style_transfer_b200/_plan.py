@@ -108,6 +108,10 @@ class PredictorPlan:
         self.feature_extractor = feature_extractor
         self.num_top_parameters = int(num_top_parameters)
         self.num_style_parameters = int(num_style_parameters)
+        if self.num_style_parameters != 100:
+            # the native predictor head (StylePredictor 576 -> 100 -> P) has the reference's default bottleneck width built in
+            # (stylePrediction.py:26); no reference script passes another value
+            raise NotImplementedError(f"num_style_parameters={num_style_parameters}: only the reference default of 100 is built")
         if feature_extractor not in ("DUMMY", "MOBILE_NET"):
             # the reference also has EFFICIENT_NET (EfficientNetV2S); it is never selected by ShapeConfig
             raise ValueError(f"{feature_extractor} is not a valid value for feature_extractor. "

@@ -17,12 +17,15 @@ is available offline): parity with a real TensorFlow-written file 
 """
 from __future__ import annotations
 
+import logging
 import os
 import re
 import struct
 from typing import Dict, List, Tuple
 
 import numpy as np
+log = logging.getLogger(__name__)
+
 
 _TABLE_MAGIC = 0xDB4775248B80FB57
 _DT_FLOAT, _DT_STRING = 1, 7
@@ -273,8 +276,9 @@ def match_checkpoint_to_model(ckpt_vars: Dict[str, dict], model):
     (the order in which create_style_transfer_model builds them, styleTransfer.py:224-232)."""
     mine = model._all_variables()
     assignment, used = {}, set()
+    source_key: Dict[str, str] = {}
     bn_groups: Dict[int, Dict[str, Tuple[str, np.ndarray]]] = {}
-    for key, e in ckpt_vars.items():
+    for key, e in sorted(ckpt_vars.items()):
         if not key.endswith(_VALUE_SUFFIX) or "optimizer" in key.split("/")[0] or "/.OPTIMIZER_SLOT/" in key:
             continue
         full = e["full_name"]
@@ -284,7 +288,19 @@ def match_checkpoint_to_model(ckpt_vars: Dict[str, dict], model):
             continue
         ours = _keras_to_ours(full)
         if ours in mine and tuple(e["value"].shape) == mine[ours].shape:
+            if ours in source_key:
+                # Two checkpoint entries carry the same Keras full_name: a training checkpoint holds the frozen loss model
+                # next to the inference model, and StyleLossModelMobileNet shares MobileNetV3's layer names with the predictor.
+                # The object-graph path disambiguates: entries below `loss_model` never belong to the inference variables.
+                old_is_loss, new_is_loss = "loss_model" in source_key[ours], "loss_model" in key
+                if new_is_loss and not old_is_loss:
+                    continue
+                if not (old_is_loss and not new_is_loss):
+                    log.warning("checkpoint entries %s and %s both name %s; keeping the first", source_key[ours], key, full)
+                    continue
+                used.discard(source_key[ours])
             assignment[ours] = e["value"].astype(np.float32)
+            source_key[ours] = key
             used.add(key)
     contract_names = sorted({k.split("/")[0] for k in mine if k.startswith("contract_") and "/bn/" in k},
                             key=lambda s: (-1 if s.endswith("start") else int(s.split("_")[1])))

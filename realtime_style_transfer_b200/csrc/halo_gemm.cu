@@ -1135,7 +1135,7 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
     if (p.x_f32 && p.residual) return cudaErrorInvalidValue;
     const bool blend = p.num_styles == 2 && p.weights != nullptr;
     if (!p.x_f32 && !p.y_f32 && p.act != ACT_SIGMOID && (p.C == 16 || p.C == 32 || p.C == 64 || p.C == 128)) {
-        static const int ppb_scale = getenv("RST_NORM_PPB") ? atoi(getenv("RST_NORM_PPB")) : 65536;
+        static const int ppb_scale = ab_env("RST_NORM_PPB") ? atoi(ab_env("RST_NORM_PPB")) : 65536;
         const int pix_per_block = max(64, ppb_scale / p.C);       // swept on B200 (profiles/r01_03_experiments.md): ~3 CTAs per SM is the optimum
         dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
         if (blend && p.residual) cin_apply_fast_kernel<true, true><<<grid, 256, 0, s>>>(p, pix_per_block);

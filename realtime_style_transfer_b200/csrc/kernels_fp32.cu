@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) conv1x1_f32_kernel(const ConvF32 p) {
 cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
     long long M = (long long)p.B * p.Ho * p.Wo;
     if (M == 0) return cudaSuccess;
-    static const bool direct_off = [] { const char* e = getenv("RST_CONV_DIRECT"); return e && e[0] == '0'; }();
+    static const bool direct_off = [] { const char* e = ab_env("RST_CONV_DIRECT"); return e && e[0] == '0'; }();
     if (!direct_off && p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad_t == 0 && p.pad_l == 0 && p.Hi == p.Ho && p.Wi == p.Wo &&
         p.Ci % 4 == 0 && M >= 4096 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0) {
         dim3 grid((unsigned)((M + 63) / 64), (unsigned)ceil_div(p.Co, 64));
@@ -385,7 +385,7 @@ cudaError_t launch_conv_f32(const ConvF32& p, cudaStream_t s) {
         if (p.kh == 9 && p.Co <= 32) return launch_conv_direct<32, 9>(p, s);
         if (p.kh == 3 && p.Co <= 4) return launch_conv_direct<4, 3>(p, s);
     }
-    static const bool phases_off = [] { const char* e = getenv("RST_CONV_PHASES"); return e && e[0] == '0'; }();
+    static const bool phases_off = [] { const char* e = ab_env("RST_CONV_PHASES"); return e && e[0] == '0'; }();
     if (p.transposed && p.stride == 2 && !phases_off) {
         // four launches, one per output parity, each over its own quarter of the pixels and its own subset of the taps
         for (int ph = 0; ph < 4; ++ph) {

@@ -274,7 +274,7 @@ extern "C" int rst_loss_commit(rst_loss* c) {
             LCUDA(c, cudaMemcpy(d, it->second.data(), it->second.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
     for (int i = 0; i < 13; ++i) { c->fwd[i].reset(); c->bwd[i].reset(); }
-    const bool cuda_core_only = c->math == RST_PRECISION_FP32 && getenv("RST_LOSS_CUDA_CORE") != nullptr;
+    const bool cuda_core_only = c->math == RST_PRECISION_FP32 && ab_env("RST_LOSS_CUDA_CORE") != nullptr;
     if (!cuda_core_only) {
         const bool split = c->math == RST_PRECISION_FP32;
         cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -337,7 +337,7 @@ static int vgg_forward(rst_loss* c, const float* img, int batch, bool keep, cuda
     int flip = 0;
     for (int i = 0; i < 13; ++i) {
         float* y = keep ? c->act[i] : (flip ? c->sb : c->sa);
-        if (c->fwd[i] && !getenv("RST_EXP_LOSS_FWD_FP32")) {
+        if (c->fwd[i] && !exp_env("RST_EXP_LOSS_FWD_FP32")) {
             std::string err;
             cudaError_t e = c->fwd[i]->run_split(cur, c->split_scratch, y, batch, c->lh[i], c->lw[i], c->num_sms, s, &err);
             if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "tf32 conv " + kVgg[i].name + ": " + (err.empty() ? cudaGetErrorString(e) : err));
@@ -455,7 +455,7 @@ extern "C" int rst_loss_backward(rst_loss* c, const float* d_pred, float* d_grad
                 LCUDA(c, launch_conv_f32(p, s));
             }
         }
-        const bool tc_bwd = c->bwd[i] && !getenv("RST_EXP_LOSS_BWD_FP32");      // (env: experiment switch, see profiles/r01_03_experiments.md)
+        const bool tc_bwd = c->bwd[i] && !exp_env("RST_EXP_LOSS_BWD_FP32");      // (env: experiment switch, see profiles/r01_03_experiments.md)
         const bool fused_mask = tc_bwd && c->bwd[i]->split;                      // the split expansion applies the ReLU mask itself
         if (!fused_mask) relu_bwd_kernel<<<blocks_for(n), 256, 0, s>>>(g, c->act[i], n);
         if (tc_bwd) {

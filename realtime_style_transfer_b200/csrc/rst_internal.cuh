@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <map>
 #include <string>
@@ -14,6 +15,19 @@
 namespace rst {
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_HSIGMOID = 3, ACT_SIGMOID = 4 };
+
+// Environment switches.  ab_env(): A/B selection between kernels that compute the SAME result; only ever read at plan / commit
+// time, never on a launch path.  exp_env(): bisecting / timing experiments (some give WRONG results); they exist only in builds
+// with -DRST_EXPERIMENTS and read as "unset" in the release library.
+inline const char* ab_env(const char* name) { return getenv(name); }
+inline const char* exp_env(const char* name) {
+#ifdef RST_EXPERIMENTS
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -185,7 +185,7 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
                              (cs.act == ACT_RELU || cs.act == ACT_NONE) && cs.in_scale == 1.f && cs.in_shift == 0.f &&
                              (t->math == RST_PRECISION_TF32 || t->split_tf32 == 1);
     const bool split = tensor_core && t->math != RST_PRECISION_TF32;
-    Tf32Conv3x3* fwd = (tensor_core && !getenv("RST_EXP_TRUNK_FWD_FP32")) ? tf32_conv(t, t->tf32_fwd, kname, ci, co, cs.act == ACT_RELU, false, split) : nullptr;
+    Tf32Conv3x3* fwd = (tensor_core && !exp_env("RST_EXP_TRUNK_FWD_FP32")) ? tf32_conv(t, t->tf32_fwd, kname, ci, co, cs.act == ACT_RELU, false, split) : nullptr;
     if (fwd) {
         std::string err;
         float* scratch = split ? falloc(t, (long long)fwd->scratch_floats(x->B, x->H, x->W)) : nullptr;
@@ -199,7 +199,7 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
     float* dgrad_tmp = (tensor_core && x->needs_grad) ? falloc(t, x->n()) : nullptr;
     float* dgrad_scratch = (split && x->needs_grad) ? falloc(t, 2LL * y->n()) : nullptr;   // [g_hi | g_lo] for the input gradient; [x_lo | g_lo] for the weight gradient before it
     // 128 -> 128: the weight gradient runs on the tensor cores as well (wgrad_tf32.cu); its scratch is free until the input gradient
-    const char* wgrad_env = getenv("RST_WGRAD_TF32");                  // read per step: the tests toggle it
+    const char* wgrad_env = ab_env("RST_WGRAD_TF32");                  // read per step: the tests toggle it
     const bool wgrad_tc_off = wgrad_env && wgrad_env[0] == '0';
     const bool wgrad_tc = tensor_core && ci == 128 && co == 128 && !wgrad_tc_off;
     float* wgrad_scratch = (wgrad_tc && split) ? (dgrad_scratch ? dgrad_scratch : falloc(t, 2LL * y->n())) : nullptr;
@@ -225,7 +225,7 @@ static Tensor* op_conv(rst_trainer* t, Tensor* x, const std::string& kname, cons
         }
         t->m->launches += 2;
         if (vb) { int rc = bias_grad(t, y->g, y->B, y->P(), co, vb->g, st, st2); if (rc) return rc; }
-        Tf32Conv3x3* bwd = (tensor_core && x->needs_grad && !getenv("RST_EXP_TRUNK_BWD_FP32")) ? tf32_conv(t, t->tf32_bwd, kname, ci, co, false, true, split) : nullptr;
+        Tf32Conv3x3* bwd = (tensor_core && x->needs_grad && !exp_env("RST_EXP_TRUNK_BWD_FP32")) ? tf32_conv(t, t->tf32_bwd, kname, ci, co, false, true, split) : nullptr;
         if (bwd) {
             std::string err;
             float* dst = x->g_init ? dgrad_tmp : x->g;
@@ -532,7 +532,7 @@ extern "C" int rst_train_create(const rst_config* cfg, int device, rst_trainer**
     if (rc != RST_OK) { g_train_create_error = rst_loss_last_error(nullptr); rst_train_destroy(t); return rc; }
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, device);
-    if (const char* env = getenv("RST_TRAIN_SPLIT_TF32")) t->split_tf32 = env[0] == '0' ? 0 : 1;
+    if (const char* env = ab_env("RST_TRAIN_SPLIT_TF32")) t->split_tf32 = env[0] == '0' ? 0 : 1;
     // one arena for every variable: trainable ones first, so that gradients / RMSprop slots are flat arrays of the same layout
     auto padded = [](int64_t n) { return (n + 63) / 64 * 64; };
     auto trainable = [](const std::string& n) {

@@ -253,7 +253,7 @@ static cudaError_t launch_wgrad_direct(const WgradDirect& p, cudaStream_t s) {
 }
 // thin 9x9 stride-1 'same' layers on images of at least 64 x 64 pixels; false = not handled here
 static bool try_wgrad_direct(const WgradF32& p, cudaStream_t s, cudaError_t* e) {
-    static const bool off = [] { const char* v = getenv("RST_WGRAD_DIRECT"); return v && v[0] == '0'; }();
+    static const bool off = [] { const char* v = ab_env("RST_WGRAD_DIRECT"); return v && v[0] == '0'; }();
     if (off || p.stride != 1 || p.kh != 9 || p.kw != 9 || p.Hx != p.Hg || p.Wx != p.Wg || p.Hx < 64 || p.Wx < 64) return false;
     WgradDirect d{};
     d.dw = p.dw; d.B = p.B; d.H = p.Hx; d.W = p.Wx; d.pad_t = p.pad_t; d.pad_l = p.pad_l;
@@ -277,7 +277,7 @@ cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s) {
     if (NP == 0) return cudaSuccess;
     { cudaError_t e = cudaSuccess; if (try_wgrad_direct(p, s, &e)) return e; }
     // row-contiguous tiles work for any stride: the kw taps of one filter row touch kw ADJACENT pixels of the tap-shifted tensor
-    static const bool rows_s1_only = [] { const char* e = getenv("RST_WGRAD_ROWS_S1"); return e && e[0] == '1'; }();
+    static const bool rows_s1_only = [] { const char* e = ab_env("RST_WGRAD_ROWS_S1"); return e && e[0] == '1'; }();
     const int rmode = (p.stride != 1 && rows_s1_only) ? 0 : (p.transposed ? 2 : 1);
     const int m_extent = rmode == 1 ? p.kw * p.Ci : p.Ci, n_extent = rmode == 2 ? p.kw * p.Co : p.Co;
     const bool wide_m = m_extent > 32, wide_n = n_extent > 32;

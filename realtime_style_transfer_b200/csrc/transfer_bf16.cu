@@ -66,10 +66,10 @@ struct HaloConv {
             if (!encode_weight_unit_map(&tmB, w_packed, kHead8Boxes * 256, err)) return false;
         } else if (sched_b_units(launch.sched)) {
             if (!encode_weight_unit_map(&tmB, w_packed, (sched_b_boxes(launch.sched) + 1) * 256, err)) return false;
-            const char* env2 = getenv("RST_STEM_2CTA");
+            const char* env2 = ab_env("RST_STEM_2CTA");
             stem_2cta = !(env2 && env2[0] == '0') && launch.mode == (HALO_MODE_RELU | HALO_MODE_POST);
         } else if (!encode_weight_map(&tmB, w_packed, total_ksteps / 4, launch.N, err)) return false;
-        const char* env = getenv("RST_TRUNK_2CTA");
+        const char* env = ab_env("RST_TRUNK_2CTA");
         two_cta = launch.sched == SCH_C3 && launch.N == 128 && launch.row_bytes == 128 && launch.epi == EPI_NHWC &&
                   launch.mode == HALO_MODE_RELU && !(env && env[0] == '0') &&
                   halo_gemm2_smem_bytes(p.n_groups) <= 227 * 1024;
@@ -80,8 +80,10 @@ struct HaloConv {
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
-        if (getenv("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiments only (wrong results)
-        if (getenv("RST_EXP_NOSTORE")) q.H = 0;
+#ifdef RST_EXPERIMENTS
+        if (exp_env("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiments only (wrong results)
+        if (exp_env("RST_EXP_NOSTORE")) q.H = 0;
+#endif
         if (two_cta && !y_f32) return launch_halo_gemm2(tmA, tmB_half, q, num_sms, s);
         if (stem_2cta && !y_f32 && !q.stats) return launch_halo_stem2cta(launch.sched, tmA, tmB, q, num_sms, s);
         return launch_halo_gemm(launch, tmA, tmB, q, num_sms, s);
@@ -403,7 +405,7 @@ int bf16_commit(rst_ctx* c) {
         std::vector<float> scale(L.co), shift(L.co);
         RST_CUDA(c, cudaMemcpy(scale.data(), c->folded[L.name + "/bn/scale"], L.co * 4, cudaMemcpyDeviceToHost));
         RST_CUDA(c, cudaMemcpy(shift.data(), c->folded[L.name + "/bn/shift"], L.co * 4, cudaMemcpyDeviceToHost));
-        const char* env2 = getenv("RST_STEM_PAIRS");
+        const char* env2 = ab_env("RST_STEM_PAIRS");
         const bool pairs = (L.ci == 17 || L.ci == 18) && L.co == 32 && L.wi % 2 == 0 && !(env2 && env2[0] == '0');
         if (pairs) {
             if (L.ci == 18) st->stem_layout.row_elems = 32;             // pair rows: 64 elements per two pixels
@@ -458,7 +460,7 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, st->e1.upload(packed, cb, nullptr, nullptr));
         st->e1.p.out_H = L1.ho; st->e1.p.out_W = L1.wo;
         if (!st->e1.bind_input(st->ze0, B, L1.hi, L1.wi, &err)) return fail(c, RST_ERR_CUDA, err);
-        const char* env8 = getenv("RST_HEAD8");
+        const char* env8 = ab_env("RST_HEAD8");
         const bool head8 = L2.wi % 8 == 0 && !(env8 && env8[0] == '0');
         (head8 ? setup_head8 : setup_head)(&st->head, c->find_weight(L2.name + "/conv/kernel")->host.data(),
                    c->find_weight(L2.name + "/conv/bias")->host.data(), &packed, &cb);
@@ -609,7 +611,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
     } else if (kind == STEM) {
         std::vector<float> one(co, 1.f), zero(co, 0.f);
         stem_layout(ci, &SL);
-        if ((ci == 17 || ci == 18) && co == 32 && w % 2 == 0 && !getenv("RST_STEM_PAIRS_OFF")) {
+        if ((ci == 17 || ci == 18) && co == 32 && w % 2 == 0 && !ab_env("RST_STEM_PAIRS_OFF")) {
             if (ci == 18) SL.row_elems = 32;
             (ci == 18 ? setup_stem2b : setup_stem2)(&hc, hk.data(), hb.data(), one.data(), zero.data(), &packed, &cb, &cs, &csh);
             wru = w / 2; stem_pairs = true;
@@ -624,7 +626,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
         setup_convt2(&hc, ci, co, hk.data(), hb.data(), &packed, &cb);
         oh = 2 * h; ow = 2 * w;
     } else {
-        const char* env8 = getenv("RST_HEAD8");
+        const char* env8 = ab_env("RST_HEAD8");
         const bool head8 = w % 8 == 0 && !(env8 && env8[0] == '0');
         (head8 ? setup_head8 : setup_head)(&hc, hk.data(), hb.data(), &packed, &cb);
         wru = w / (head8 ? 8 : 4); y_f32 = true;

@@ -66,8 +66,8 @@ class NativeModel:
         self._variables: Dict[str, np.ndarray] = {}
         self._ctx: Optional[NativeContext] = None
         self._ctx_key = None
-        self._dirty = True
         self._version = 0           # bumped whenever a variable is assigned
+        self._uploaded = None       # _weights_version() at the last upload into the native context
         self._compiled = False
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("RST_DEVICE") is None \
             else int(os.environ["RST_DEVICE"])
@@ -116,8 +116,11 @@ class NativeModel:
         self._mark_dirty()
 
     def _mark_dirty(self):
-        self._dirty = True
         self._version += 1
+
+    def _weights_version(self):
+        """Identifies the variable values this model would upload; a context re-uploads only when it changes."""
+        return self._version
 
     def save_weights(self, filepath, save_format=None):
         """``*.npz`` -> numpy archive; anything else -> a TF2 object-based checkpoint prefix (Keras' default 'tf' format:
@@ -173,10 +176,11 @@ class NativeModel:
             self._ctx = NativeContext(max_batch=max(batch, 1), precision=key[0], device=self.device,
                                       **self._context_kwargs(batch))
             self._ctx_key = key
-            self._dirty = True
-        if self._dirty:
+            self._uploaded = None
+        version = self._weights_version()
+        if self._uploaded != version:
             self._ctx.set_weights(self._native_weights(), commit=True)
-            self._dirty = False
+            self._uploaded = version
         return self._ctx
 
     def close(self):

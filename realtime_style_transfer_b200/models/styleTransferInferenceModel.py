@@ -62,7 +62,6 @@ class StyleTransferInferenceModel(NativeModel):
             self.transfer.set_weights(t)
         if p:
             self.style_predictor.set_weights(p)
-        self._dirty = True
 
     def _context_kwargs(self, max_batch):
         kw = self.transfer._context_kwargs(max_batch)
@@ -70,11 +69,10 @@ class StyleTransferInferenceModel(NativeModel):
                   style_shape=self.style_predictor.plan.input_shape)
         return kw
 
-    def _get_ctx(self, batch):
-        # sub-model weights may have been assigned directly
-        if self.transfer._dirty or self.style_predictor._dirty:
-            self._dirty = True
-        return super()._get_ctx(batch)
+    def _weights_version(self):
+        # the variables live in the sub-models and may be assigned there directly; each context (this model's and the
+        # sub-models' own) remembers the versions IT uploaded, so none of them consumes a flag another one needs
+        return (self.transfer._version, self.style_predictor._version)
 
     def __call__(self, inputs, training=False):
         return self.predict(inputs)

@@ -66,6 +66,9 @@ class StyleTransferTrainingModel(NativeModel):
 
     # -- variables live in the inference model's two sub-models ---------------------------------------------------
     def _all_variables(self):
+        # after train_step the trained values live in the native trainer: weights / get_weights / trainable_variables /
+        # save_weights (checkpoint callbacks in a custom loop) must never see the stale host copies
+        self.sync_to_host()
         return self.inference_model._all_variables()
 
     @property
@@ -78,6 +81,9 @@ class StyleTransferTrainingModel(NativeModel):
 
     def set_weights(self, weights):
         self.inference_model.set_weights(weights)
+
+    def get_weights(self):
+        return [v.copy() for v in self._all_variables().values()]
 
     def count_params(self):
         return self.inference_model.count_params()
@@ -128,7 +134,7 @@ class StyleTransferTrainingModel(NativeModel):
         if self._mirrored != self._versions():
             # variables were assigned on the Python side (initialisation, load_weights, set_weights): upload them.
             # The RMSprop accumulators are kept, as tf.keras keeps its slots when variables are assigned.
-            self._trainer.model.set_weights(self._all_variables(), commit=True)
+            self._trainer.model.set_weights(self.inference_model._all_variables(), commit=True)
             lm = self.loss_model
             if self.math == _native.PRECISION_TF32:
                 self._trainer.set_math(_native.PRECISION_TF32)
@@ -154,11 +160,11 @@ class StyleTransferTrainingModel(NativeModel):
         if self._trainer is None or not self._host_stale:
             return
         tr = self._trainer
+        self._host_stale = False
         tr.sync_weights()
-        fresh = {k: tr.model.get_weight(k, v.shape) for k, v in self._all_variables().items()}
+        fresh = {k: tr.model.get_weight(k, v.shape) for k, v in self.inference_model._all_variables().items()}
         self.inference_model.set_weights(fresh)
         self._mirrored = self._versions()      # the trainer already holds these values: no re-upload on the next step
-        self._host_stale = False
 
     def train_step(self, data):
         """data = (x, y): x {'content': (B,H,W,C), 'style': (B,1,h,w,3)}, y {'content': (B,H,W,3), 'style': (B,1,H,W,3)}.

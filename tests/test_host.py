@@ -262,3 +262,52 @@ def test_exr_reader_roundtrip_and_screenshot_layout(tmp_path):
     assert arr.shape == (h, w, sum(n for _, n in cfg.channels)) and np.array_equal(arr, np.concatenate(truth, axis=-1))
     batches = list(hdrScreenshots.iter_unreal_hdr_screenshots(tmp_path, cfg.channels, batch=2))
     assert len(batches) == 1 and batches[0].shape == (1,) + arr.shape
+
+
+# ---- weight-upload tracking of the combined inference model (shared dirty flag) ---------------------------
+class _StubCtx:
+    """Stands in for NativeContext: counts uploads, echoes one bias so stale weights are visible."""
+    uploads = 0
+
+    def __init__(self, **kw):
+        import types
+        self.cfg = types.SimpleNamespace(max_batch=kw.get("max_batch", 1), out_h=8, out_w=8)
+        self.w = {}
+
+    def set_weights(self, weights, commit=True):
+        type(self).uploads += 1
+        self.w = {k: np.array(v) for k, v in weights.items()}
+
+    def _bias(self):
+        return float(self.w["expand_last/conv/bias"][0])
+
+    def inference_forward_host(self, content, style, weights=None):
+        return np.full((content.shape[0], 1), self._bias(), np.float32)
+
+    def transfer_forward_host(self, content, params, weights=None):
+        return np.full((content.shape[0], 1), self._bias(), np.float32)
+
+    def close(self):
+        pass
+
+
+def test_inference_model_uploads_once_and_never_runs_stale(monkeypatch):
+    from realtime_style_transfer_b200.models import _base
+    monkeypatch.setattr(_base, "NativeContext", _StubCtx)
+    _StubCtx.uploads = 0
+    shape_in, shape_out = (32, 64, 3), (32, 64, 3)
+    models = styleTransferInferenceModel.make_style_transfer_inference_model(
+        1, lambda n: stylePrediction.create_style_prediction_model(shape_out, "DUMMY", n),
+        lambda: styleTransfer.create_style_transfer_model(shape_in, shape_out, 8, 32, 1))
+    x = {"content": np.zeros((1,) + shape_in, np.float32), "style": np.zeros((1, 1) + shape_out, np.float32)}
+    for _ in range(3):
+        models.inference.predict(x)
+    assert _StubCtx.uploads == 1, "every predict() re-uploaded (and re-committed) all weights"
+    # assign through the sub-model, consume the change in the sub-model's OWN context, then use the combined model
+    models.transfer.set_weights({"expand_last/conv/bias": np.full(3, 7.0, np.float32)})
+    params = np.zeros((1, 1, models.transfer.plan.num_style_parameters), np.float32)
+    assert models.transfer.predict({"content": x["content"], "style_params": params})[0, 0] == 7.0
+    assert models.inference.predict(x)[0, 0] == 7.0, "combined model ran with stale transfer weights"
+    n = _StubCtx.uploads
+    models.inference.predict(x)
+    assert _StubCtx.uploads == n
