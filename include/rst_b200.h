@@ -41,6 +41,12 @@ enum rst_precision {
                               * rst_loss_set_math / rst_train_set_math), for operator-level parity tests */
 };
 
+enum rst_dtype {             /* element types at the boundary of the *_typed entry points */
+    RST_DTYPE_F32 = 0,
+    RST_DTYPE_F16 = 1,
+    RST_DTYPE_U8 = 2
+};
+
 enum rst_extractor {         /* stylePrediction.StyleFeatureExtractor, stylePrediction.py:19-22 */
     RST_EXTRACTOR_NONE = 0,
     RST_EXTRACTOR_DUMMY = 1,
@@ -104,6 +110,18 @@ int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, const float*
 int rst_transfer_submit_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
                              const float* h_style_weights, float* h_out, int batch, int64_t* ticket);
 int rst_transfer_wait(rst_ctx* ctx, int64_t ticket);
+/* Reduced-byte variants of the three entry points above for the ends of the video loop that are not float32 in the reference
+ * either: the G-buffer planes of the Unreal capture are HALF EXR channels (dataloaders/hdrScreenshots.py:14-29 widens them to
+ * float32 on the host), and the reference's callers quantise the prediction at once (predict_using_checkpoint.py:99
+ * `np.uint8(... * 255)`, predict_video_using_checkpoint.py:98 `(... * 255).astype(int)`).  content_dtype: RST_DTYPE_F32 or
+ * RST_DTYPE_F16 (IEEE half, same NHWC layout); out_dtype: RST_DTYPE_F32 or RST_DTYPE_U8 (trunc(255*y), (B,out_h,out_w,3) bytes).
+ * Style parameters and style weights stay float32.  The float32 entry points are these with F32 / F32. */
+int rst_transfer_forward_typed(rst_ctx* ctx, const void* d_content, int content_dtype, const float* d_style_params,
+                               const float* d_style_weights, void* d_out, int out_dtype, int batch, void* stream);
+int rst_transfer_forward_host_typed(rst_ctx* ctx, const void* h_content, int content_dtype, const float* h_style_params,
+                                    const float* h_style_weights, void* h_out, int out_dtype, int batch);
+int rst_transfer_submit_host_typed(rst_ctx* ctx, const void* h_content, int content_dtype, const float* h_style_params,
+                                   const float* h_style_weights, void* h_out, int out_dtype, int batch, int64_t* ticket);
 /* style_predictor(style_image) (models/stylePrediction.py:25-75): d_style (B,style_h,style_w,3) in [0,1]
  * -> d_params (B,P). */
 int rst_predict_style(rst_ctx* ctx, const float* d_style, float* d_params, int batch, void* stream);
@@ -195,6 +213,9 @@ rst_loss* rst_train_loss(rst_trainer* trainer);
  * predictor input (B,style_h,style_w,3); d_gt_style the style image at (out_h,out_w) for the loss model. */
 int rst_train_forward_backward(rst_trainer* trainer, const float* d_content, const float* d_style, const float* d_gt_content,
                                const float* d_gt_style, float* d_losses, int batch);
+/* The cudaStream_t (as void*) every kernel of the trainer is launched on: a caller that times a step with CUDA events records
+ * them here (bench.py), and a data-parallel caller orders its all-reduce against it. */
+void* rst_train_stream(rst_trainer* trainer);
 /* Flat fp32 gradient buffer (device) holding every trainable variable's gradient: the buffer a data-parallel caller
  * all-reduces (SUM) over NCCL between rst_train_forward_backward and rst_train_apply_gradients. */
 float* rst_train_gradients(rst_trainer* trainer);

@@ -21,6 +21,26 @@ PRECISION_TF32 = 2
 PRECISION_TF32X3 = 3
 EXTRACTOR_NONE, EXTRACTOR_DUMMY, EXTRACTOR_MOBILE_NET = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 4
+DTYPE_F32, DTYPE_F16, DTYPE_U8 = 0, 1, 2          # enum rst_dtype
+
+
+def content_dtype_code(dtype) -> int:
+    """numpy dtype of a G-buffer array -> rst_dtype (float32, or float16 = the reduced-byte ingest)."""
+    dtype = np.dtype(dtype)
+    if dtype == np.float16:
+        return DTYPE_F16
+    if dtype == np.float32:
+        return DTYPE_F32
+    raise ValueError(f"content dtype must be float32 or float16, got {dtype}")
+
+
+def out_dtype_code(dtype) -> int:
+    dtype = np.dtype(dtype)
+    if dtype == np.uint8:
+        return DTYPE_U8
+    if dtype == np.float32:
+        return DTYPE_F32
+    raise ValueError(f"output dtype must be float32 or uint8, got {dtype}")
 
 
 class RstError(RuntimeError):
@@ -58,6 +78,9 @@ SIGNATURES = {
     "rst_transfer_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
     "rst_transfer_submit_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _i64p]),
     "rst_transfer_wait": (C.c_int, [_vp, C.c_int64]),
+    "rst_transfer_forward_typed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "rst_transfer_forward_host_typed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "rst_transfer_submit_host_typed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _i64p]),
     "rst_predict_style": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "rst_predict_style_host": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "rst_inference_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
@@ -90,6 +113,7 @@ SIGNATURES = {
     "rst_train_model": (_vp, [_vp]),
     "rst_train_loss": (_vp, [_vp]),
     "rst_train_forward_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "rst_train_stream": (_vp, [_vp]),
     "rst_train_gradients": (_vp, [_vp]),
     "rst_train_num_gradient_elements": (C.c_int64, [_vp]),
     "rst_train_variable_range": (C.c_int, [_vp, C.c_char_p, _i64p, _i64p]),
@@ -123,6 +147,13 @@ def load_library() -> C.CDLL:
 
 def _host_f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _host_content(a) -> np.ndarray:
+    """float16 G-buffers stay float16 (half the PCIe bytes); everything else becomes float32 like the reference's tensors."""
+    if isinstance(a, np.ndarray) and a.dtype == np.float16:
+        return np.ascontiguousarray(a)
+    return _host_f32(a)
 
 
 def _ptr(a):
@@ -215,29 +246,34 @@ class NativeContext:
         return out
 
     # -- hot path ---------------------------------------------------------------------------
-    def transfer_forward_host(self, content, style_params, style_weights=None) -> np.ndarray:
-        content = _host_f32(content)
+    def transfer_forward_host(self, content, style_params, style_weights=None, out_dtype=np.float32) -> np.ndarray:
+        """content float32 or float16 (kept as is); out_dtype float32, or uint8 = trunc(255 * y) computed on the device."""
+        content = _host_content(content)
         style_params = _host_f32(style_params)
         sw = _host_f32(style_weights) if style_weights is not None else None
         b = content.shape[0]
-        out = np.empty((b, self.cfg.out_h, self.cfg.out_w, 3), np.float32)
-        self._check(self.lib.rst_transfer_forward_host(self.handle, _ptr(content), _ptr(style_params), _ptr(sw),
-                                                       _ptr(out), b))
+        out = np.empty((b, self.cfg.out_h, self.cfg.out_w, 3), np.dtype(out_dtype))
+        self._check(self.lib.rst_transfer_forward_host_typed(self.handle, _ptr(content), content_dtype_code(content.dtype),
+                                                             _ptr(style_params), _ptr(sw), _ptr(out), out_dtype_code(out.dtype), b))
         return out
 
     def transfer_forward_device(self, d_content: int, d_style_params: int, d_style_weights: Optional[int],
-                                d_out: int, batch: int, stream: int = 0):
-        self._check(self.lib.rst_transfer_forward(self.handle, _vp(d_content), _vp(d_style_params),
-                                                  _vp(d_style_weights) if d_style_weights else None, _vp(d_out),
-                                                  batch, _vp(stream) if stream else None))
+                                d_out: int, batch: int, stream: int = 0, content_dtype: int = DTYPE_F32,
+                                out_dtype: int = DTYPE_F32):
+        self._check(self.lib.rst_transfer_forward_typed(self.handle, _vp(d_content), content_dtype, _vp(d_style_params),
+                                                        _vp(d_style_weights) if d_style_weights else None, _vp(d_out), out_dtype,
+                                                        batch, _vp(stream) if stream else None))
 
     def transfer_submit_host(self, content: np.ndarray, style_params: np.ndarray, style_weights, out: np.ndarray) -> int:
-        """Asynchronous submit; the caller keeps the (ideally pinned) float32 arrays alive until transfer_wait(ticket)."""
+        """Asynchronous submit; the caller keeps the (ideally pinned) arrays alive until transfer_wait(ticket).
+        content: float32 or float16; out: float32 or uint8 (the array dtypes select the entry point's element types)."""
         for a in (content, style_params, out):
-            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+            assert a.flags["C_CONTIGUOUS"]
+        assert style_params.dtype == np.float32 and (style_weights is None or style_weights.dtype == np.float32)
         ticket = C.c_int64()
-        self._check(self.lib.rst_transfer_submit_host(self.handle, _ptr(content), _ptr(style_params), _ptr(style_weights),
-                                                      _ptr(out), content.shape[0], C.byref(ticket)))
+        self._check(self.lib.rst_transfer_submit_host_typed(self.handle, _ptr(content), content_dtype_code(content.dtype),
+                                                            _ptr(style_params), _ptr(style_weights), _ptr(out),
+                                                            out_dtype_code(out.dtype), content.shape[0], C.byref(ticket)))
         return int(ticket.value)
 
     def transfer_wait(self, ticket: int):
@@ -426,6 +462,10 @@ class NativeTrainer:
     def forward_backward(self, d_content: int, d_style: int, d_gt_content: int, d_gt_style: int, d_losses: int, batch: int):
         self._check(self.lib.rst_train_forward_backward(self.handle, _vp(d_content), _vp(d_style), _vp(d_gt_content),
                                                         _vp(d_gt_style), _vp(d_losses), batch))
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the trainer's kernels (wrap with torch.cuda.ExternalStream to record timing events on it)."""
+        return int(self.lib.rst_train_stream(self.handle) or 0)
 
     def gradients_ptr(self) -> int:
         return int(self.lib.rst_train_gradients(self.handle) or 0)

@@ -661,8 +661,21 @@ cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long
     return cudaGetLastError();
 }
 
+// The G-buffer arrives as fp32 (the reference's numpy / TF tensors) or as fp16 (what the EXR planes of the Unreal capture are,
+// dataloaders/hdrScreenshots.py:14-29): the pack kernels are instantiated for both.  ld_quad(base, i) returns elements
+// 4i .. 4i+3 as floats: one 16-byte load of fp32, one 8-byte load of fp16 (the 64-pixel segments are 16- resp. 8-byte aligned).
+__device__ __forceinline__ float in_to_f32(float v) { return v; }
+__device__ __forceinline__ float in_to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float4 ld_quad(const float* base, int i) { return __ldg(reinterpret_cast<const float4*>(base) + i); }
+__device__ __forceinline__ float4 ld_quad(const __half* base, int i) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(base) + i);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 // One thread per (pixel, 8-element slot group of the packed row).
-__global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C,
+template <typename TIn>
+__global__ void pack_stem_input_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C,
                                        int n_real, int row_elems, int pair_window, long long total_slots) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_slots) return;
@@ -670,7 +683,7 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
     const int slot = (int)(i % slots);
     const long long pix = i / slots;
     const int px = (int)(pix % W);
-    const float* xp = x + pix * C;
+    const TIn* xp = x + pix * C;
     float v[8];
     const int e0 = slot * 8;
     const int real_elems = n_real > 0 ? 16 : 0;
@@ -679,14 +692,14 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
         const int e = e0 + j;
         float val = 0.f;
         if (e < real_elems) {
-            if (e < n_real) val = xp[e];
+            if (e < n_real) val = in_to_f32(xp[e]);
         } else {
             const int g = (e - real_elems) / 16, t = (e - real_elems) % 16;   // virtual group g, horizontal tap t
             const int ch = n_real + g;
             const int taps = pair_window ? ((px & 1) ? 0 : 10) : 9;
             if (ch < C && t < taps) {
                 const int sx = px + t - 4;
-                if (sx >= 0 && sx < W) val = xp[(long long)(t - 4) * C + ch];
+                if (sx >= 0 && sx < W) val = in_to_f32(xp[(long long)(t - 4) * C + ch]);
             }
         }
         v[j] = val;
@@ -698,7 +711,8 @@ __global__ void pack_stem_input_kernel(const float* __restrict__ x, __nv_bfloat1
     reinterpret_cast<uint4*>(y)[i] = o;
 }
 // 18-channel pair layout (SCH_STEM2B), any even W: one thread per (pixel pair, 8-element group of the 64-element pair row).
-__global__ void pack_stem_pairs18_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W, long long total_groups) {
+template <typename TIn>
+__global__ void pack_stem_pairs18_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int W, long long total_groups) {
     constexpr int C = 18;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_groups) return;
@@ -706,18 +720,18 @@ __global__ void pack_stem_pairs18_kernel(const float* __restrict__ x, __nv_bfloa
     const long long pair = i >> 3;
     const int pw = W / 2;
     const int x0 = (int)(pair % pw) * 2;
-    const float* xp = x + ((pair / pw) * W + x0) * C;                 // the even pixel
+    const TIn* xp = x + ((pair / pw) * W + x0) * C;                   // the even pixel
     float v[8];
     if (grp < 4) {                                                     // real channels of pixel grp / 2
-        const float* q = xp + (grp >> 1) * C + (grp & 1) * 8;
+        const TIn* q = xp + (grp >> 1) * C + (grp & 1) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = q[j];
+        for (int j = 0; j < 8; ++j) v[j] = in_to_f32(q[j]);
     } else {                                                           // window slots t = 8 * (grp & 1) + j of channel 16 + (grp - 4) / 2
         const int ch = 16 + ((grp - 4) >> 1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int t = (grp & 1) * 8 + j, sx = x0 + t - 4;
-            v[j] = (t < 10 && sx >= 0 && sx < W) ? xp[(long long)(t - 4) * C + ch] : 0.f;
+            v[j] = (t < 10 && sx >= 0 && sx < W) ? in_to_f32(xp[(long long)(t - 4) * C + ch]) : 0.f;
         }
     }
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -727,7 +741,8 @@ __global__ void pack_stem_pairs18_kernel(const float* __restrict__ x, __nv_bfloa
 }
 // Fast variant (W % 64 == 0): one warp per 64-pixel row segment staged in shared memory as in pack_stem_rows_kernel below;
 // each lane assembles ONE pixel pair (128 B), the warp writes its 4 KB of packed pairs as contiguous, coalesced runs.
-__global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
+template <typename TIn>
+__global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
                                                                     long long total_segments) {
     constexpr int C = 18, NF4 = 18 * C;                                // 72 pixels x 18 floats
     extern __shared__ float4 pack_smem[];
@@ -738,12 +753,12 @@ __global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const float*
     const int sx = (int)(seg % segs_per_row);
     const long long pix0 = (seg / segs_per_row) * W + sx * 64;
     float4* s4 = pack_smem + warp * NF4;
-    const float4* g4 = reinterpret_cast<const float4*>(x + (pix0 - 4) * C);
+    const TIn* g4 = x + (pix0 - 4) * C;
     const bool left_oob = sx == 0, right_oob = sx == segs_per_row - 1;
 #pragma unroll
     for (int i = lane; i < NF4; i += 32) {
         const bool oob = (left_oob && i < C) || (right_oob && i >= 17 * C);
-        s4[i] = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(g4 + i);
+        s4[i] = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : ld_quad(g4, i);
     }
     __syncwarp();
     const float* sf = reinterpret_cast<const float*>(s4);
@@ -778,8 +793,8 @@ __global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const float*
 // Fast path for the G-buffer layouts (16 real channels + NV windowed ones, W % 64 == 0): one warp per 64-pixel row segment.
 // The segment plus a 4-pixel halo on each side is 72*C floats = 18*C aligned float4 (coalesced loads) staged in the warp's
 // own shared-memory slice; each lane then assembles two packed pixels (stride-C reads are bank-conflict free for C = 17).
-template <int NV, bool PAIRW>
-__global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
+template <int NV, bool PAIRW, typename TIn>
+__global__ void __launch_bounds__(256) pack_stem_rows_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
                                                              long long total_segments) {
     constexpr int C = 16 + NV, ROW = NV <= 1 ? 32 : 64, NF4 = 18 * C;
     extern __shared__ float4 pack_smem[];
@@ -791,12 +806,12 @@ __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __rest
     const long long row = seg / segs_per_row;                      // n*H + y
     const long long pix0 = row * W + sx * 64;                      // first pixel of the segment
     float4* s4 = pack_smem + warp * NF4;
-    const float4* g4 = reinterpret_cast<const float4*>(x + (pix0 - 4) * C);
+    const TIn* g4 = x + (pix0 - 4) * C;
     const bool left_oob = sx == 0, right_oob = sx == segs_per_row - 1;
 #pragma unroll
     for (int i = lane; i < NF4; i += 32) {
         const bool oob = (left_oob && i < C) || (right_oob && i >= 17 * C);     // 4 pixels = C float4 on each side
-        s4[i] = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(g4 + i);
+        s4[i] = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : ld_quad(g4, i);
     }
     __syncwarp();
     const float* sf = reinterpret_cast<const float*>(s4);
@@ -858,34 +873,42 @@ __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const float* __rest
     }
 }
 
-cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
-                                   int pair_window, cudaStream_t s) {
+template <typename TIn>
+static cudaError_t launch_pack_stem_input_t(const TIn* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
+                                            int pair_window, cudaStream_t s) {
     long long total = (long long)B * H * W * (row_elems / 8);
     if (total == 0) return cudaSuccess;
     const int nv = C - 16;
+    // a 64-pixel segment minus its 4-pixel halo starts at a multiple of 4 elements: 16-byte (fp32) / 8-byte (fp16) vectors
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & (4 * sizeof(TIn) - 1)) == 0;
     if (pair_window && ((nv != 1 && nv != 2) || n_real != 16 || (W & 1))) return cudaErrorInvalidValue;
     if (pair_window && nv == 2) {
         if (row_elems != 32) return cudaErrorInvalidValue;
-        if (W % 64 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if (W % 64 == 0 && aligned) {
             const long long segments = (long long)B * H * (W / 64);
-            pack_stem_pair_rows18_kernel<<<(unsigned)((segments + 7) / 8), 256, (size_t)8 * 18 * 18 * sizeof(float4), s>>>(x, y, W, segments);
+            pack_stem_pair_rows18_kernel<TIn><<<(unsigned)((segments + 7) / 8), 256, (size_t)8 * 18 * 18 * sizeof(float4), s>>>(x, y, W, segments);
         } else {
-            pack_stem_pairs18_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, W, total);
+            pack_stem_pairs18_kernel<TIn><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, W, total);
         }
         return cudaGetLastError();
     }
-    if (n_real == 16 && (nv == 1 || nv == 2) && W % 64 == 0 && row_elems == (nv <= 1 ? 32 : 64) &&
-        (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    if (n_real == 16 && (nv == 1 || nv == 2) && W % 64 == 0 && row_elems == (nv <= 1 ? 32 : 64) && aligned) {
         const long long segments = (long long)B * H * (W / 64);
         const unsigned blocks = (unsigned)((segments + 7) / 8);
         const size_t smem = (size_t)8 * 18 * C * sizeof(float4);
-        if (nv == 1 && pair_window) pack_stem_rows_kernel<1, true><<<blocks, 256, smem, s>>>(x, y, W, segments);
-        else if (nv == 1) pack_stem_rows_kernel<1, false><<<blocks, 256, smem, s>>>(x, y, W, segments);
-        else pack_stem_rows_kernel<2, false><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        if (nv == 1 && pair_window) pack_stem_rows_kernel<1, true, TIn><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        else if (nv == 1) pack_stem_rows_kernel<1, false, TIn><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        else pack_stem_rows_kernel<2, false, TIn><<<blocks, 256, smem, s>>>(x, y, W, segments);
         return cudaGetLastError();
     }
-    pack_stem_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, pair_window, total);
+    pack_stem_input_kernel<TIn><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, pair_window, total);
     return cudaGetLastError();
+}
+
+cudaError_t launch_pack_stem_input(const void* x, int x_f16, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
+                                   int pair_window, cudaStream_t s) {
+    if (x_f16) return launch_pack_stem_input_t(reinterpret_cast<const __half*>(x), y, B, H, W, C, n_real, row_elems, pair_window, s);
+    return launch_pack_stem_input_t(reinterpret_cast<const float*>(x), y, B, H, W, C, n_real, row_elems, pair_window, s);
 }
 
 // Instance-norm apply, VEC channels per thread-iteration (8 for bf16 input, 4 or fewer for fp32 input).
@@ -1064,7 +1087,9 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
 }
 
 // fp32 -> fp32 with 3 channels (the image head): 4 consecutive floats per thread, sigmoid.
-template <bool BLEND>
+// YU8: the image leaves as uint8 = trunc(255 * y), the quantisation the reference's callers apply to the prediction
+// (predict_using_checkpoint.py:99 `np.uint8(... * 255)`, predict_video_using_checkpoint.py:98 `(... * 255).astype(int)`).
+template <bool BLEND, bool YU8>
 __global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
     __shared__ float sa[2][3], sb[2][3];
     const int n = blockIdx.y;
@@ -1087,6 +1112,7 @@ __global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
     const long long groups = (long long)p.P / 4;                     // P % 4 == 0 (checked by the launcher)
     const float4* x4 = reinterpret_cast<const float4*>(p.x) + (long long)n * groups * 3;
     float4* y4 = reinterpret_cast<float4*>(p.y) + (long long)n * groups * 3;
+    uint32_t* y8 = reinterpret_cast<uint32_t*>(p.y) + (long long)n * groups * 3;      // YU8: 12 bytes per 4-pixel group
     const float2* w2 = BLEND ? reinterpret_cast<const float2*>(p.weights) + (long long)n * p.P : nullptr;
     float a[3], b[3], a1[3], b1[3];
 #pragma unroll
@@ -1108,6 +1134,21 @@ __global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
             xo[e] = act == ACT_SIGMOID ? 1.f / (1.f + __expf(-t)) : (act == ACT_RELU ? fmaxf(t, 0.f) : t);
         }
     };
+    auto store = [&](long long grp, const float4 (&out)[3]) {
+        if (!YU8) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) y4[grp * 3 + k] = out[k];
+            return;
+        }
+        const float* xo = reinterpret_cast<const float*>(out);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) word |= min(__float2uint_rz(fmaxf(xo[4 * k + j], 0.f) * 255.f), 255u) << (8 * j);
+            y8[grp * 3 + k] = word;
+        }
+    };
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; g + stride < groups; g += 2 * stride) {                   // two groups (6 independent 16-byte loads) in flight
@@ -1116,16 +1157,15 @@ __global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
         for (int k = 0; k < 3; ++k) { i0[k] = __ldg(x4 + g * 3 + k); i1[k] = __ldg(x4 + (g + stride) * 3 + k); }
         one(i0, g, o0);
         one(i1, g + stride, o1);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { y4[g * 3 + k] = o0[k]; y4[(g + stride) * 3 + k] = o1[k]; }
+        store(g, o0);
+        store(g + stride, o1);
     }
     for (; g < groups; g += stride) {
         float4 i0[3], o0[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) i0[k] = __ldg(x4 + g * 3 + k);
         one(i0, g, o0);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) y4[g * 3 + k] = o0[k];
+        store(g, o0);
     }
 }
 
@@ -1144,12 +1184,15 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
         else cin_apply_fast_kernel<false, false><<<grid, 256, 0, s>>>(p, pix_per_block);
         return cudaGetLastError();
     }
-    if (p.x_f32 && p.y_f32 && p.C == 3 && p.P % 4 == 0) {
+    if (p.y_u8 && !(p.x_f32 && p.C == 3 && p.P % 4 == 0)) return cudaErrorInvalidValue;   // uint8 only for the 3-channel image head
+    if (p.x_f32 && (p.y_f32 || p.y_u8) && p.C == 3 && p.P % 4 == 0) {
         const long long want = ((long long)p.P / 4 + 255) / 256;
         const long long per_sample = max(1, 148 * 4 / p.B);          // ~4 CTAs per SM in total, each streaming a long run
         dim3 grid((unsigned)(want < per_sample ? want : per_sample), (unsigned)p.B);
-        if (blend) cin_apply_c3_kernel<true><<<grid, 256, 0, s>>>(p);
-        else cin_apply_c3_kernel<false><<<grid, 256, 0, s>>>(p);
+        if (blend && p.y_u8) cin_apply_c3_kernel<true, true><<<grid, 256, 0, s>>>(p);
+        else if (blend) cin_apply_c3_kernel<true, false><<<grid, 256, 0, s>>>(p);
+        else if (p.y_u8) cin_apply_c3_kernel<false, true><<<grid, 256, 0, s>>>(p);
+        else cin_apply_c3_kernel<false, false><<<grid, 256, 0, s>>>(p);
         return cudaGetLastError();
     }
     int pix_per_block = max(1, 32768 / p.C);

@@ -236,13 +236,15 @@ cudaError_t launch_bf16_to_f32_slice(const __nv_bfloat16* x, float* y, long long
 // by the pixel pair), the group of an odd pixel is zero.
 // pair_window with TWO windowed channels (SCH_STEM2B, C = 18, even W, row_elems = 32 per pixel): a pixel PAIR is stored as
 // [even pixel: 16 real | odd pixel: 16 real | window of channel 16 | window of channel 17], windows as above.
-cudaError_t launch_pack_stem_input(const float* x, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
+// x: fp32, or fp16 when x_f16 != 0.
+cudaError_t launch_pack_stem_input(const void* x, int x_f16, __nv_bfloat16* y, int B, int H, int W, int C, int n_real, int row_elems,
                                    int pair_window, cudaStream_t s);
 
 // instance-norm apply: y = act(bias + (x-mean)*inv*scale) [+ residual]; x bf16 or fp32, y bf16 or fp32, C % vec == 0
 struct CinApplyV {
     const void* x = nullptr; void* y = nullptr; const __nv_bfloat16* residual = nullptr;
     int x_f32 = 0, y_f32 = 0;
+    int y_u8 = 0;                      // 3-channel fp32 head only: store trunc(255*y) as uint8 (y_f32 ignored)
     const double* stats = nullptr; const float* params = nullptr;
     long long param_bstride = 0, param_sstride = 0; int scale_off = 0, bias_off = 0;
     const float* weights = nullptr;    // (B,P,2) or null

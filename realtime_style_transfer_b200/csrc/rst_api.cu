@@ -223,7 +223,7 @@ static void free_ctx(rst_ctx* c) {
     for (auto& a : c->pvec) if (a) cudaFree(a);
     if (c->stats) cudaFree(c->stats);
     if (c->w_pyramid) cudaFree(c->w_pyramid);
-    for (float* p : {c->st_content, c->st_params, c->st_weights, c->st_out, c->st_style}) if (p) cudaFree(p);
+    for (float* p : {c->st_content, c->st_params, c->st_weights, c->st_out, c->st_style, c->cvt_content, c->cvt_out}) if (p) cudaFree(p);
     for (auto& kv : c->taps) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -580,9 +580,33 @@ static int collect_profile(rst_ctx* c) {
     return RST_OK;
 }
 
+static size_t dtype_size(int dtype) { return dtype == RST_DTYPE_F32 ? 4 : dtype == RST_DTYPE_F16 ? 2 : 1; }
+
+__global__ void f16_to_f32_kernel(const __half2* __restrict__ x, float2* __restrict__ y, long long n2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) y[i] = __half22float2(x[i]);
+}
+__global__ void f32_to_u8_kernel(const float4* __restrict__ x, uint32_t* __restrict__ y, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = x[i];
+    auto q = [](float f) { return min(__float2uint_rz(fmaxf(f, 0.f) * 255.f), 255u); };
+    y[i] = q(v.x) | (q(v.y) << 8) | (q(v.z) << 16) | (q(v.w) << 24);
+}
+
 extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const float* d_style_params,
                                     const float* d_style_weights, float* d_out, int batch, void* stream) {
+    return rst_transfer_forward_typed(ctx, d_content, RST_DTYPE_F32, d_style_params, d_style_weights, d_out, RST_DTYPE_F32, batch,
+                                      stream);
+}
+
+extern "C" int rst_transfer_forward_typed(rst_ctx* ctx, const void* d_content, int content_dtype, const float* d_style_params,
+                                          const float* d_style_weights, void* d_out, int out_dtype, int batch, void* stream) {
     if (!ctx) return RST_ERR_INVALID;
+    if (content_dtype != RST_DTYPE_F32 && content_dtype != RST_DTYPE_F16)
+        return fail(ctx, RST_ERR_INVALID, "rst_transfer_forward: content dtype must be RST_DTYPE_F32 or RST_DTYPE_F16");
+    if (out_dtype != RST_DTYPE_F32 && out_dtype != RST_DTYPE_U8)
+        return fail(ctx, RST_ERR_INVALID, "rst_transfer_forward: output dtype must be RST_DTYPE_F32 or RST_DTYPE_U8");
     if (ctx->cfg.in_h == 0) return fail(ctx, RST_ERR_STATE, "rst_transfer_forward: predictor-only context");
     if (!ctx->committed) return fail(ctx, RST_ERR_STATE, "rst_transfer_forward: weights not committed");
     if (!d_content || !d_style_params || !d_out) return fail(ctx, RST_ERR_INVALID, "rst_transfer_forward: null tensor");
@@ -591,10 +615,33 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
     cudaSetDevice(ctx->device);
     ctx->launches = 0;
     cudaStream_t s = (cudaStream_t)stream;
+    const rst_config& cg = ctx->cfg;
+    const long long n_in = (long long)batch * cg.in_h * cg.in_w * cg.in_c, n_out = (long long)batch * cg.out_h * cg.out_w * 3;
+    if (cg.precision != RST_PRECISION_BF16 && (content_dtype != RST_DTYPE_F32 || out_dtype != RST_DTYPE_F32)) {
+        // the fp32 path computes on fp32 tensors: typed calls convert through two buffers allocated on first use
+        if ((n_in & 1) || (n_out & 3)) return fail(ctx, RST_ERR_UNSUPPORTED, "typed fp32-path call: odd tensor sizes");
+        if (content_dtype == RST_DTYPE_F16 && !ctx->cvt_content)
+            RST_CUDA(ctx, cudaMalloc(&ctx->cvt_content, (size_t)cg.max_batch * cg.in_h * cg.in_w * cg.in_c * sizeof(float)));
+        if (out_dtype == RST_DTYPE_U8 && !ctx->cvt_out)
+            RST_CUDA(ctx, cudaMalloc(&ctx->cvt_out, (size_t)cg.max_batch * cg.out_h * cg.out_w * 3 * sizeof(float)));
+    }
     auto run = [&]() -> int {
-        if (ctx->cfg.precision == RST_PRECISION_BF16)
-            return bf16_transfer_forward(ctx, d_content, d_style_params, d_style_weights, d_out, batch, s);
-        return fp32_transfer_forward(ctx, d_content, d_style_params, d_style_weights, d_out, batch, s);
+        if (cg.precision == RST_PRECISION_BF16)
+            return bf16_transfer_forward(ctx, d_content, content_dtype, d_style_params, d_style_weights, d_out, out_dtype, batch, s);
+        const float* x = (const float*)d_content;
+        float* y = out_dtype == RST_DTYPE_U8 ? ctx->cvt_out : (float*)d_out;
+        if (content_dtype == RST_DTYPE_F16) {
+            LaunchScope ls(ctx, s, "convert");
+            f16_to_f32_kernel<<<(unsigned)((n_in / 2 + 255) / 256), 256, 0, s>>>((const __half2*)d_content, (float2*)ctx->cvt_content, n_in / 2);
+            x = ctx->cvt_content;
+        }
+        int rc2 = fp32_transfer_forward(ctx, x, d_style_params, d_style_weights, y, batch, s);
+        if (rc2 == RST_OK && out_dtype == RST_DTYPE_U8) {
+            LaunchScope ls(ctx, s, "convert");
+            f32_to_u8_kernel<<<(unsigned)((n_out / 4 + 255) / 256), 256, 0, s>>>((const float4*)y, (uint32_t*)d_out, n_out / 4);
+            RST_CUDA(ctx, cudaGetLastError());
+        }
+        return rc2;
     };
     // Replay a captured CUDA graph when the same buffers come back (video loop / pipelined host API); the legacy default
     // stream cannot be captured, profiling and taps need the eager path.
@@ -605,7 +652,7 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
     if (!graphable) return run();
     for (auto& g : ctx->graphs)
         if (g.batch == batch && g.content == d_content && g.params == d_style_params && g.weights == d_style_weights &&
-            g.out == d_out) {
+            g.out == d_out && g.content_dtype == content_dtype && g.out_dtype == out_dtype) {
             RST_CUDA(ctx, cudaGraphLaunch(g.exec, s));
             ctx->launches = g.launches;
             return RST_OK;
@@ -616,10 +663,11 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
         bool seen = false;
         for (auto& g : ctx->graph_candidates)
             seen = seen || (g.batch == batch && g.content == d_content && g.params == d_style_params && g.weights == d_style_weights &&
-                            g.out == d_out);
+                            g.out == d_out && g.content_dtype == content_dtype && g.out_dtype == out_dtype);
         if (!seen) {
             rst_ctx::GraphEntry k;
             k.batch = batch; k.content = d_content; k.params = d_style_params; k.weights = d_style_weights; k.out = d_out;
+            k.content_dtype = content_dtype; k.out_dtype = out_dtype;
             if (ctx->graph_candidates.size() >= 16) ctx->graph_candidates.erase(ctx->graph_candidates.begin());
             ctx->graph_candidates.push_back(k);
             return run();
@@ -640,6 +688,7 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
     }
     rst_ctx::GraphEntry ge;
     ge.batch = batch; ge.content = d_content; ge.params = d_style_params; ge.weights = d_style_weights; ge.out = d_out;
+    ge.content_dtype = content_dtype; ge.out_dtype = out_dtype;
     ge.launches = ctx->launches;
     e = cudaGraphInstantiate(&ge.exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -652,14 +701,21 @@ extern "C" int rst_transfer_forward(rst_ctx* ctx, const float* d_content, const 
 
 extern "C" int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
                                          const float* h_style_weights, float* h_out, int batch) {
+    return rst_transfer_forward_host_typed(ctx, h_content, RST_DTYPE_F32, h_style_params, h_style_weights, h_out, RST_DTYPE_F32, batch);
+}
+
+extern "C" int rst_transfer_forward_host_typed(rst_ctx* ctx, const void* h_content, int content_dtype, const float* h_style_params,
+                                               const float* h_style_weights, void* h_out, int out_dtype, int batch) {
     if (!ctx) return RST_ERR_INVALID;
+    if ((content_dtype != RST_DTYPE_F32 && content_dtype != RST_DTYPE_F16) || (out_dtype != RST_DTYPE_F32 && out_dtype != RST_DTYPE_U8))
+        return fail(ctx, RST_ERR_INVALID, "rst_transfer_forward_host: content dtype F32|F16, output dtype F32|U8");
     if (!h_content || !h_style_params || !h_out) return fail(ctx, RST_ERR_INVALID, "rst_transfer_forward_host: null tensor");
     if (batch < 0 || batch > ctx->cfg.max_batch) return fail(ctx, RST_ERR_INVALID, "rst_transfer_forward_host: batch exceeds max_batch");
     if (batch == 0) return RST_OK;
     cudaSetDevice(ctx->device);
     const rst_config& g = ctx->cfg;
     cudaStream_t s = ctx->own_stream;
-    RST_CUDA(ctx, cudaMemcpyAsync(ctx->st_content, h_content, (size_t)batch * g.in_h * g.in_w * g.in_c * sizeof(float),
+    RST_CUDA(ctx, cudaMemcpyAsync(ctx->st_content, h_content, (size_t)batch * g.in_h * g.in_w * g.in_c * dtype_size(content_dtype),
                                   cudaMemcpyHostToDevice, s));
     RST_CUDA(ctx, cudaMemcpyAsync(ctx->st_params, h_style_params,
                                   (size_t)batch * g.num_styles * ctx->num_style_params * sizeof(float),
@@ -670,10 +726,10 @@ extern "C" int rst_transfer_forward_host(rst_ctx* ctx, const float* h_content, c
                                       (size_t)batch * g.out_h * g.out_w * (g.num_styles - 1) * sizeof(float),
                                       cudaMemcpyHostToDevice, s));
     }
-    int rc = rst_transfer_forward(ctx, ctx->st_content, ctx->st_params, g.num_styles > 1 ? ctx->st_weights : nullptr,
-                                  ctx->st_out, batch, (void*)s);
+    int rc = rst_transfer_forward_typed(ctx, ctx->st_content, content_dtype, ctx->st_params,
+                                        g.num_styles > 1 ? ctx->st_weights : nullptr, ctx->st_out, out_dtype, batch, (void*)s);
     if (rc) return rc;
-    RST_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->st_out, (size_t)batch * g.out_h * g.out_w * 3 * sizeof(float),
+    RST_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->st_out, (size_t)batch * g.out_h * g.out_w * 3 * dtype_size(out_dtype),
                                   cudaMemcpyDeviceToHost, s));
     RST_CUDA(ctx, cudaStreamSynchronize(s));
     if (ctx->profiling) collect_profile(ctx);
@@ -707,7 +763,15 @@ static int pipe_init(rst_ctx* c) {
 
 extern "C" int rst_transfer_submit_host(rst_ctx* ctx, const float* h_content, const float* h_style_params,
                                         const float* h_style_weights, float* h_out, int batch, int64_t* ticket) {
+    return rst_transfer_submit_host_typed(ctx, h_content, RST_DTYPE_F32, h_style_params, h_style_weights, h_out, RST_DTYPE_F32, batch,
+                                          ticket);
+}
+
+extern "C" int rst_transfer_submit_host_typed(rst_ctx* ctx, const void* h_content, int content_dtype, const float* h_style_params,
+                                              const float* h_style_weights, void* h_out, int out_dtype, int batch, int64_t* ticket) {
     if (!ctx) return RST_ERR_INVALID;
+    if ((content_dtype != RST_DTYPE_F32 && content_dtype != RST_DTYPE_F16) || (out_dtype != RST_DTYPE_F32 && out_dtype != RST_DTYPE_U8))
+        return fail(ctx, RST_ERR_INVALID, "rst_transfer_submit_host: content dtype F32|F16, output dtype F32|U8");
     if (ctx->cfg.in_h == 0) return fail(ctx, RST_ERR_STATE, "rst_transfer_submit_host: predictor-only context");
     if (!ctx->committed) return fail(ctx, RST_ERR_STATE, "rst_transfer_submit_host: weights not committed");
     if (!h_content || !h_style_params || !h_out || !ticket) return fail(ctx, RST_ERR_INVALID, "rst_transfer_submit_host: null argument");
@@ -719,7 +783,7 @@ extern "C" int rst_transfer_submit_host(rst_ctx* ctx, const float* h_content, co
     auto& P = ctx->pipe;
     const int slot = (int)(P.next & 1);
     if (P.busy[slot]) RST_CUDA(ctx, cudaEventSynchronize(P.out_done[slot]));     // the slot's previous batch has fully drained
-    RST_CUDA(ctx, cudaMemcpyAsync(P.content[slot], h_content, (size_t)batch * g.in_h * g.in_w * g.in_c * sizeof(float),
+    RST_CUDA(ctx, cudaMemcpyAsync(P.content[slot], h_content, (size_t)batch * g.in_h * g.in_w * g.in_c * dtype_size(content_dtype),
                                   cudaMemcpyHostToDevice, P.s_in));
     RST_CUDA(ctx, cudaMemcpyAsync(P.params[slot], h_style_params,
                                   (size_t)batch * g.num_styles * ctx->num_style_params * sizeof(float), cudaMemcpyHostToDevice, P.s_in));
@@ -731,12 +795,12 @@ extern "C" int rst_transfer_submit_host(rst_ctx* ctx, const float* h_content, co
     }
     RST_CUDA(ctx, cudaEventRecord(P.in_done[slot], P.s_in));
     RST_CUDA(ctx, cudaStreamWaitEvent(ctx->own_stream, P.in_done[slot], 0));
-    rc = rst_transfer_forward(ctx, P.content[slot], P.params[slot], g.num_styles > 1 ? P.weights[slot] : nullptr, P.out[slot],
-                              batch, (void*)ctx->own_stream);
+    rc = rst_transfer_forward_typed(ctx, P.content[slot], content_dtype, P.params[slot],
+                                    g.num_styles > 1 ? P.weights[slot] : nullptr, P.out[slot], out_dtype, batch, (void*)ctx->own_stream);
     if (rc) return rc;
     RST_CUDA(ctx, cudaEventRecord(P.comp_done[slot], ctx->own_stream));
     RST_CUDA(ctx, cudaStreamWaitEvent(P.s_out, P.comp_done[slot], 0));
-    RST_CUDA(ctx, cudaMemcpyAsync(h_out, P.out[slot], (size_t)batch * g.out_h * g.out_w * 3 * sizeof(float),
+    RST_CUDA(ctx, cudaMemcpyAsync(h_out, P.out[slot], (size_t)batch * g.out_h * g.out_w * 3 * dtype_size(out_dtype),
                                   cudaMemcpyDeviceToHost, P.s_out));
     RST_CUDA(ctx, cudaEventRecord(P.out_done[slot], P.s_out));
     P.busy[slot] = true;

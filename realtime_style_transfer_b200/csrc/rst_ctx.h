@@ -80,6 +80,7 @@ struct rst_ctx {
     // host-API staging
     float* st_content = nullptr; float* st_params = nullptr; float* st_weights = nullptr;
     float* st_out = nullptr; float* st_style = nullptr;
+    float* cvt_content = nullptr; float* cvt_out = nullptr;    // fp32 path only: typed (fp16 in / uint8 out) calls convert through these
     cudaStream_t own_stream = nullptr;
     // double-buffered asynchronous host pipeline (rst_transfer_submit_host / rst_transfer_wait)
     struct Pipe {
@@ -98,6 +99,7 @@ struct rst_ctx {
     // ---- CUDA-graph cache of whole forwards (launch-bound inner loop: ~30 kernels per batch) ----
     struct GraphEntry {
         int batch = 0; const void *content = nullptr, *params = nullptr, *weights = nullptr, *out = nullptr;
+        int content_dtype = 0, out_dtype = 0;
         cudaGraphExec_t exec = nullptr; int64_t launches = 0;
     };
     std::vector<GraphEntry> graphs;
@@ -164,8 +166,8 @@ int fp32_expand_stage(rst_ctx* c, float* x, float* t1, const float* d_style_para
 // implemented in transfer_bf16.cu
 int bf16_create(rst_ctx* ctx);
 int bf16_commit(rst_ctx* ctx);
-int bf16_transfer_forward(rst_ctx* ctx, const float* d_content, const float* d_style_params,
-                          const float* d_style_weights, float* d_out, int batch, cudaStream_t s);
+int bf16_transfer_forward(rst_ctx* ctx, const void* d_content, int content_dtype, const float* d_style_params,
+                          const float* d_style_weights, void* d_out, int out_dtype, int batch, cudaStream_t s);
 cudaError_t launch_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t s);
 
 }  // namespace rst

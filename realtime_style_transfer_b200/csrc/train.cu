@@ -624,6 +624,8 @@ extern "C" int rst_train_forward_backward(rst_trainer* t, const float* d_content
     return RST_OK;
 }
 
+extern "C" void* rst_train_stream(rst_trainer* t) { return t ? (void*)t->s : nullptr; }
+
 extern "C" int rst_train_apply_gradients(rst_trainer* t, float learning_rate, float rho, float epsilon) {
     if (!t) return RST_ERR_INVALID;
     cudaSetDevice(t->device);

@@ -473,9 +473,9 @@ int bf16_commit(rst_ctx* c) {
 
 static int norm_pass(rst_ctx* c, const void* x, bool x_f32, void* y, bool y_f32, const __nv_bfloat16* residual,
                      const double* stats, int batch, int P, int C, int width, const float* d_style_params, int param_off,
-                     int act, cudaStream_t s) {
+                     int act, cudaStream_t s, bool y_u8 = false) {
     CinApplyV a;
-    a.x = x; a.x_f32 = x_f32; a.y = y; a.y_f32 = y_f32; a.residual = residual; a.stats = stats;
+    a.x = x; a.x_f32 = x_f32; a.y = y; a.y_f32 = y_f32; a.y_u8 = y_u8 ? 1 : 0; a.residual = residual; a.stats = stats;
     a.params = d_style_params;
     a.param_bstride = (long long)c->cfg.num_styles * c->num_style_params;
     a.param_sstride = c->num_style_params;
@@ -488,8 +488,8 @@ static int norm_pass(rst_ctx* c, const void* x, bool x_f32, void* y, bool y_f32,
     return RST_OK;
 }
 
-int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_style_params, const float* d_style_weights,
-                          float* d_out, int batch, cudaStream_t s) {
+int bf16_transfer_forward(rst_ctx* c, const void* d_content, int content_dtype, const float* d_style_params,
+                          const float* d_style_weights, void* d_out, int out_dtype, int batch, cudaStream_t s) {
     Bf16State* st = c->bf16.get();
     const rst_config& g = c->cfg;
     const int F = g.bottleneck_num_filters;
@@ -502,7 +502,7 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
     // ---- encoder ----
     {
         LaunchScope ls(c, s, "pack_input");
-        RST_CUDA(c, launch_pack_stem_input(d_content, st->s_in, batch, g.in_h, g.in_w, g.in_c, st->stem_layout.n_real,
+        RST_CUDA(c, launch_pack_stem_input(d_content, content_dtype == RST_DTYPE_F16 ? 1 : 0, st->s_in, batch, g.in_h, g.in_w, g.in_c, st->stem_layout.n_real,
                                            st->stem_layout.row_elems, st->stem.launch.sched == SCH_STEM2 || st->stem.launch.sched == SCH_STEM2B ? 1 : 0, s));
     }
     {
@@ -544,7 +544,9 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
             LaunchScope ls(c, s, "convert");
             RST_CUDA(c, launch_bf16_to_f32_slice(st->bx, x, px, F, F, s));
         }
-        return fp32_expand_stage(c, x, t1, d_style_params, cursor, d_out, batch, s);
+        if (out_dtype != RST_DTYPE_F32)
+            return fail(c, RST_ERR_UNSUPPORTED, "uint8 output needs the tensor-core decoder (2 expand blocks, 128 filters, width % 64 == 0)");
+        return fp32_expand_stage(c, x, t1, d_style_params, cursor, (float*)d_out, batch, s);
     }
     const LayerDesc& L0 = c->expand[0];
     const LayerDesc& L1 = c->expand[1];
@@ -569,9 +571,9 @@ int bf16_transfer_forward(rst_ctx* c, const float* d_content, const float* d_sty
     { LaunchScope ls(c, s, "head_umma"); RST_CUDA(c, st->head.run(st->ylast, true, se2, batch, st->num_sms, s)); }
     record_tap(c, L2.name + "/conv", st->ylast, (int64_t)batch * L2.ho * L2.wo * 3, false, s);
     rc = norm_pass(c, st->ylast, true, d_out, true, nullptr, se2, batch, L2.ho * L2.wo, 3, L2.wo, d_style_params, cursor,
-                   ACT_SIGMOID, s);
+                   ACT_SIGMOID, s, out_dtype == RST_DTYPE_U8);
     if (rc) return rc;
-    record_tap(c, L2.name, d_out, (int64_t)batch * L2.ho * L2.wo * 3, false, s);
+    if (out_dtype == RST_DTYPE_F32) record_tap(c, L2.name, d_out, (int64_t)batch * L2.ho * L2.wo * 3, false, s);
     return RST_OK;
 }
 
@@ -639,7 +641,7 @@ int op_conv2d_bf16(const float* d_x, const float* d_kernel, const float* d_bias,
     if (e == cudaSuccess && !y_f32) e = cudaMalloc(&yb, pout * co * 2);
     int rc = RST_OK;
     if (e == cudaSuccess) {
-        if (kind == STEM) e = launch_pack_stem_input(d_x, xb, batch, h, w, ci, SL.n_real, SL.row_elems, stem_pairs ? 1 : 0, s);
+        if (kind == STEM) e = launch_pack_stem_input(d_x, 0, xb, batch, h, w, ci, SL.n_real, SL.row_elems, stem_pairs ? 1 : 0, s);
         else e = launch_f32_to_bf16_pad(d_x, xb, pin, ci, in_c_dev, s);
     }
     if (e == cudaSuccess) {

@@ -78,7 +78,9 @@ def _zip_block(data: bytes) -> bytes:
     return zlib.compress(enc.astype(np.uint8).tobytes())
 
 
-def load(path) -> ExrImage:
+def load(path, keep_half: bool = False) -> ExrImage:
+    """keep_half: HALF channels are returned as float16 planes instead of being widened to float32 (pyroexr's behaviour, and the
+    default here): the values are identical, and a float16 G-buffer crosses PCIe in half the bytes (rst_transfer_*_typed)."""
     buf = Path(path).read_bytes()
     magic, version = struct.unpack_from("<iI", buf, 0)
     if magic != MAGIC:
@@ -116,7 +118,8 @@ def load(path) -> ExrImage:
     nblocks = (height + lines - 1) // lines
     offsets = struct.unpack_from(f"<{nblocks}Q", buf, pos)
     line_bytes = sum(dt.itemsize for _, dt in chans) * width
-    planes = {name: np.empty((height, width), np.float32) for name, _ in chans}
+    planes = {name: np.empty((height, width), np.float16 if (keep_half and dt == np.dtype("<f2")) else np.float32)
+              for name, dt in chans}
     for off in offsets:
         y, nbytes = struct.unpack_from("<ii", buf, off)
         payload = buf[off + 8:off + 8 + nbytes]
@@ -128,7 +131,7 @@ def load(path) -> ExrImage:
         for r in range(rows):
             for name, dt in chans:
                 n = width * dt.itemsize
-                planes[name][y - y0 + r] = np.frombuffer(payload, dtype=dt, count=width, offset=p).astype(np.float32)
+                planes[name][y - y0 + r] = np.frombuffer(payload, dtype=dt, count=width, offset=p)
                 p += n
     info = {"channels": [c for c, _ in chans], "compression": COMPRESSION_NAMES[compression], "dataWindow": (x0, y0, x1, y1)}
     return ExrImage(planes, info)

@@ -27,18 +27,22 @@ def _planes_of(image: "exr.ExrImage", count: int) -> np.ndarray:
     return np.stack([image.channel(n) for n in names], axis=-1)
 
 
-def load_unreal_hdr_screenshot(base_png_filepath, expected_channels):
-    """Returns ((H, W, sum of plane widths) float32, the png path), planes concatenated in ``expected_channels`` order."""
+def load_unreal_hdr_screenshot(base_png_filepath, expected_channels, dtype=np.float32):
+    """Returns ((H, W, sum of plane widths), the png path), planes concatenated in ``expected_channels`` order.
+    dtype float32 is the reference's result; dtype float16 keeps HALF planes as they are stored (same values, half the bytes:
+    the array can be passed as 'content' to predict / predict_frames, which then upload float16)."""
     png = Path(base_png_filepath)
-    stack = [_planes_of(exr.load(png.with_name(f"{png.stem}_{name}.exr")), width) for name, width in expected_channels]
-    return np.concatenate(stack, axis=-1).astype(np.float32, copy=False), png
+    keep_half = np.dtype(dtype) == np.float16
+    stack = [_planes_of(exr.load(png.with_name(f"{png.stem}_{name}.exr"), keep_half=keep_half), width)
+             for name, width in expected_channels]
+    return np.concatenate(stack, axis=-1).astype(dtype, copy=False), png
 
 
-def iter_unreal_hdr_screenshots(content_image_dir, expected_channels, batch: int = 1):
-    """Yields (batch, H, W, C) float32 arrays for every ``*.png`` stem in the directory (the last batch may be short)."""
+def iter_unreal_hdr_screenshots(content_image_dir, expected_channels, batch: int = 1, dtype=np.float32):
+    """Yields (batch, H, W, C) arrays for every ``*.png`` stem in the directory (the last batch may be short)."""
     chunk = []
     for png in sorted(Path(content_image_dir).glob('*.png')):
-        chunk.append(load_unreal_hdr_screenshot(png, expected_channels)[0])
+        chunk.append(load_unreal_hdr_screenshot(png, expected_channels, dtype)[0])
         if len(chunk) == batch:
             yield np.stack(chunk)
             chunk = []

@@ -189,6 +189,13 @@ class NativeModel:
             self._ctx = None
 
 
+def as_content(x) -> np.ndarray:
+    """G-buffer input: float16 arrays stay float16 (reduced-byte ingest, rst_transfer_*_typed), anything else -> float32."""
+    if isinstance(x, np.ndarray) and x.dtype == np.float16:
+        return np.ascontiguousarray(x)
+    return as_numpy(x)
+
+
 def as_numpy(x) -> np.ndarray:
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()

@@ -149,6 +149,51 @@ def test_transfer_bf16_full_resolution(cuda_device):
     assert out.min() >= 0 and out.max() <= 1
 
 
+def test_transfer_bf16_full_resolution_batch8(cuda_device):
+    """The benchmarked configuration itself: rst-960-120-128-17 at batch 8 (more tiles per cluster and more atomics per
+    statistic than batch 2), bf16 vs the fp32 oracle on all eight frames."""
+    cfg = ShapeConfig.from_spec("rst-960-120-128-17")
+    spec = O.TransferSpec(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(8, 480, 960, cfg.channels, seed=11)
+    params = np.random.default_rng(12).uniform(0.3, 1.2, (8, 1, spec.num_style_parameters)).astype(np.float32)
+    ref = O.transfer_forward(spec, weights, content, params).numpy()
+    out, _, launches = run_bf16(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1, weights, content, params)
+    err = np.abs(out - ref)
+    print(f"bf16 full-res B=8: rel_l2={rel_l2(out, ref):.4e} max_abs={err.max():.4e} p99.9={np.quantile(err, 0.999):.4e}")
+    for i in range(8):
+        assert rel_l2(out[i], ref[i]) <= BF16_REL_TOL, i
+    assert np.quantile(err, 0.99) <= 2e-2 and np.quantile(err, 0.999) <= 5e-2
+
+
+@pytest.mark.parametrize("trained_like", [False, True])
+def test_bf16_error_is_the_ideal_bf16_error(cuda_device, trained_like):
+    """Separates inherent bf16 error from kernel defects at full resolution: the oracle's emulate_bf16 mode rounds the same
+    tensors to bf16 at the same points as the CUDA path and is exact everywhere else (float64).  The kernels may differ from
+    it only where an fp32 accumulation flips a bf16 rounding; the large tail against the fp32 oracle (instance norm with
+    eps = 1e-5 on near-constant channels) must already be present in the emulation."""
+    cfg = ShapeConfig.from_spec("rst-960-120-128-17")
+    spec = O.TransferSpec(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1, trained_like=trained_like)
+    content = O.synthetic_content(2, 480, 960, cfg.channels, seed=0)
+    params = np.random.default_rng(2).uniform(0.3, 1.2, (2, 1, spec.num_style_parameters)).astype(np.float32)
+    ref = O.transfer_forward(spec, weights, content, params).numpy()
+    emu = O.transfer_forward(spec, weights, content, params, dtype=torch.float64, emulate_bf16=True).float().numpy()
+    out, _, _ = run_bf16(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1, weights, content, params)
+    e_ref, e_emu, emu_ref = np.abs(out - ref), np.abs(out - emu), np.abs(emu - ref)
+    q = lambda e: (float(e.max()), float(np.quantile(e, 0.999)), float(np.quantile(e, 0.99)))
+    print(f"trained_like={trained_like}: kernel-vs-fp32 max/p99.9/p99 = {q(e_ref)}; kernel-vs-ideal-bf16 = {q(e_emu)}; "
+          f"ideal-bf16-vs-fp32 = {q(emu_ref)}; rel_l2 kernel-vs-fp32 {rel_l2(out, ref):.3e}, kernel-vs-ideal {rel_l2(out, emu):.3e}, "
+          f"ideal-vs-fp32 {rel_l2(emu, ref):.3e}")
+    assert rel_l2(out, ref) <= BF16_REL_TOL
+    # the kernel is as close to the fp32 reference as an ideal bf16 execution is (within 25 %), at every error level ...
+    assert rel_l2(out, ref) <= 1.25 * rel_l2(emu, ref) + 1e-4
+    assert np.quantile(e_ref, 0.999) <= 1.25 * np.quantile(emu_ref, 0.999) + 1e-3
+    # ... and much closer to the ideal bf16 execution than that is to fp32
+    assert rel_l2(out, emu) <= 0.75 * rel_l2(emu, ref) + 1e-4
+    assert np.quantile(e_emu, 0.99) <= 5e-3
+
+
 def test_transfer_bf16_full_resolution_dual_style(cuda_device):
     """rst-960-120-128-18 (BASELINE.json configs[2]): 18-channel G-buffer, two predicted style-parameter sets blended per pixel
     by the weight map and its mips (styleTransfer.py:36-44, :297-303), batch 1, bf16 vs the fp32 oracle."""

@@ -380,3 +380,93 @@ def test_tensor_core_weight_gradient_matches_cuda_cores_at_scale(cuda_device, mo
         worst = max(worst, rel)
         assert rel < 1e-4, (n, rel)
     print("tensor-core vs CUDA-core weight gradients: worst rel l2", worst)
+
+
+def test_training_step_at_the_baseline_geometry(cuda_device):
+    """BASELINE config 4 at its own geometry: 480x960, 17 channels, 128 filters, MobileNetV3 predictor (batch 2 to keep the
+    CPU oracle to seconds; the geometry, not the batch, selects the kernels: sliding-window 9x9 stem, tcgen05 split-tf32 trunk
+    and VGG convolutions, tensor-core weight gradients).  Bars (north_star): prediction <= 1e-4 max abs, the four loss scalars
+    <= 1e-3 relative, against the fp32 oracle forward in training mode (BatchNorm on batch statistics)."""
+    batch = 2
+    in_shape, out_shape = (480, 960, 17), (480, 960, 3)
+    spec = O.TransferSpec(in_shape, out_shape, 120, 128, 1)
+    tw = O.init_transfer_weights(spec, seed=31)
+    pw = O.init_predictor_weights("MOBILE_NET", spec.num_style_parameters, seed=32)
+    vgg = O.init_vgg16_weights(seed=3)
+    from realtime_style_transfer_b200.shape_config import ShapeConfig
+    content = O.synthetic_content(batch, 480, 960, ShapeConfig(num_channels=17).channels, seed=33, unit_depth=True)
+    rng = np.random.default_rng(34)
+    style = rng.uniform(0, 1, (batch,) + out_shape).astype(np.float32)
+    gt = rng.uniform(0, 1, (batch,) + out_shape).astype(np.float32)
+    with torch.no_grad():
+        W = {k: torch.as_tensor(v) for k, v in {**tw, **pw}.items()}
+        params = O._predictor_forward_t("MOBILE_NET", W, torch.as_tensor(style), training=True)[:, None, :]
+        ref_pred = O._transfer_forward_t(spec, W, torch.as_tensor(content), params, training=True)
+        ref_losses = O.style_loss_vgg(vgg, ref_pred, gt, torch.as_tensor(style), dtype=torch.float32)
+    tr = _native.NativeTrainer(in_shape=in_shape, out_shape=out_shape, bottleneck_res_y=120, bottleneck_num_filters=128,
+                               max_batch=batch, extractor=_native.EXTRACTOR_MOBILE_NET, style_shape=out_shape[:2])
+    tr.model.set_weights({**tw, **pw})
+    tr.loss.set_weights(vgg)
+    losses = _step(tr, cuda_device, content, style, gt)
+    err = np.abs(tr.read_prediction(batch) - ref_pred.numpy()).max()
+    print("config-4 geometry: prediction max abs err", err)
+    assert err <= 1e-4
+    for i, key in enumerate(("loss", "feature_loss", "style_loss", "total_variation_loss")):
+        r = ref_losses[key].numpy()
+        rel = np.abs(losses[:, i] - r).max() / np.abs(r).max()
+        print(f"config-4 geometry: {key} rel err {rel:.2e} (value {float(r.mean()):.4e})")
+        assert rel <= 1e-3, key
+    # every trainable variable received a finite gradient; a second step after the update still runs and lowers nothing to NaN
+    flat = torch.as_tensor(_DeviceArrayView(tr.gradients_ptr(), tr.num_gradient_elements), device=cuda_device)
+    assert torch.isfinite(flat).all() and float(flat.abs().max()) > 0
+    tr.apply_gradients()
+    again = _step(tr, cuda_device, content, style, gt)
+    assert np.isfinite(again).all()
+    tr.close()
+
+
+class _DeviceArrayView:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def test_data_parallel_in_process_sum_of_shard_gradients(cuda_device):
+    """The data-parallel step on ONE GPU (never skipped): two trainers stand in for two ranks, each runs forward/backward on its
+    own shard, the flat gradient buffers are summed by hand (what the NCCL all-reduce(SUM) of distributed.allreduce_sum_ does)
+    and both apply the same RMSprop update.  Checked against the oracle: fp64 autograd gradients of each shard, summed, then
+    oracle RMSprop -- the replicas must end with identical variables equal to the oracle's."""
+    spec, tw, pw, vgg, content, style, gt = _setup("DUMMY", 4, seed=9)
+    shards = [(content[:2], style[:2], gt[:2]), (content[2:], style[2:], gt[2:])]
+    trainers = [_trainer(_native.EXTRACTOR_DUMMY, 2, tw, pw, vgg) for _ in shards]
+    flats = []
+    for tr, (c, s, g) in zip(trainers, shards):
+        _step(tr, cuda_device, c, s, g)
+        flats.append(torch.as_tensor(_DeviceArrayView(tr.gradients_ptr(), tr.num_gradient_elements), device=cuda_device))
+    total = flats[0] + flats[1]
+    for f in flats:
+        f.copy_(total)
+    torch.cuda.synchronize()
+    weights = {k: np.asarray(v, np.float64) for k, v in {**tw, **pw}.items() if not k.endswith(("moving_mean", "moving_variance"))}
+    ref_sum = None
+    for c, s, g in shards:
+        _, grads, _ = O.training_forward_backward(spec, tw, "DUMMY", pw, vgg, c, s, g)
+        ref_sum = grads if ref_sum is None else {k: ref_sum[k] + grads[k] for k in grads}
+    # the summed native gradient is the oracle's summed gradient (end-to-end bar of this file)
+    for k, v in weights.items():
+        got = trainers[0].read_gradient(k, v.shape)
+        ref = ref_sum[k].numpy()
+        norm = np.sqrt((ref ** 2).sum())
+        if norm > 1e-9:
+            assert np.sqrt(((got - ref) ** 2).sum()) / norm < GRAD_TOL, k
+    native_grads = {k: torch.tensor(trainers[0].read_gradient(k, v.shape)) for k, v in weights.items()}
+    expect, _ = O.rmsprop_update(weights, native_grads, {k: np.zeros_like(v) for k, v in weights.items()})
+    for tr in trainers:
+        tr.apply_gradients()
+        tr.sync_weights()
+    for k, v in expect.items():
+        a = trainers[0].model.get_weight(k, v.shape)
+        b = trainers[1].model.get_weight(k, v.shape)
+        assert np.array_equal(a, b), k                      # replicas stay in lock step
+        assert np.abs(a - v).max() < 2e-6 * max(1.0, np.abs(v).max()), k
+    for tr in trainers:
+        tr.close()

@@ -284,7 +284,7 @@ class _StubCtx:
     def inference_forward_host(self, content, style, weights=None):
         return np.full((content.shape[0], 1), self._bias(), np.float32)
 
-    def transfer_forward_host(self, content, params, weights=None):
+    def transfer_forward_host(self, content, params, weights=None, out_dtype=np.float32):
         return np.full((content.shape[0], 1), self._bias(), np.float32)
 
     def close(self):

@@ -163,3 +163,25 @@ def test_loss_is_per_sample_vector_and_zero_at_identity():
     np.testing.assert_allclose(out["loss"].numpy(), 0.1 * tv.numpy(), rtol=1e-6)
     with pytest.raises(AssertionError):
         O.style_loss_vgg(vgg, img, img, np.stack([img, img], axis=1))
+
+
+def test_bf16_emulation_mode_rounds_activations_and_bounds_the_error():
+    """emulate_bf16 is the fp32 graph with bf16 storage: identical when off, small but non-zero deviation when on, every
+    stored activation exactly representable in bf16."""
+    import torch
+    spec = O.TransferSpec((32, 64, 17), (32, 64, 3), 8, 32, 1)
+    w = O.init_transfer_weights(spec, seed=3)
+    from realtime_style_transfer_b200.shape_config import ShapeConfig
+    c = O.synthetic_content(1, 32, 64, ShapeConfig(num_channels=17).channels, seed=1, unit_depth=True)
+    p = np.random.default_rng(0).uniform(0.3, 1.2, (1, 1, spec.num_style_parameters)).astype(np.float32)
+    ref = O.transfer_forward(spec, w, c, p).numpy()
+    same = O.transfer_forward(spec, w, c, p, emulate_bf16=False).numpy()
+    assert np.array_equal(ref, same)
+    taps = {}
+    emu = O.transfer_forward(spec, w, c, p, dtype=torch.float64, emulate_bf16=True, taps=taps).numpy()
+    err = np.abs(emu - ref)
+    assert 0 < err.max() < 5e-2 and np.sqrt((err ** 2).sum() / (ref ** 2).sum()) < 1e-2
+    for name in ("contract_start", "residual_block_0/conv0/relu", "residual_block_2", "expand_0/conv", "expand_1"):
+        t = taps[name]
+        assert torch.equal(t, t.to(torch.bfloat16).to(t.dtype)), name
+    assert not torch.equal(taps["expand_last/conv"], taps["expand_last/conv"].to(torch.bfloat16).to(torch.float64))
