@@ -144,6 +144,20 @@ struct HaloGemmParams {
     int a_wrap = 0;                      // split tf32: the tensor holds a_wrap channel groups [x_hi | x_lo]; groups >= a_wrap re-read
                                          // group g - a_wrap (the conv runs over [x_hi | x_lo | x_hi] without storing x_hi twice)
     int store_exact = 0;                 // MODE_TF32: store the fp32 accumulator as is (split-tf32 convs) instead of rounding to tf32
+    // Fused input transform (halo_gemm2.cu, fuse != 0): the A operand is not the bound tensor as stored but the conditional
+    // instance norm of the RAW output of the previous convolution, computed by loader warps on the way into shared memory:
+    //   fuse 1:  A = relu(a[n,c] * x + b[n,c])                  (first norm of a residual block, styleTransfer.py:173-182)
+    //   fuse 2:  A = skip + a[n,c] * x + b[n,c]  (or without skip), also written to fin_out: the block output (:184)
+    // with a = rsqrt(var + eps) * scale, b = bias - mean * a from the statistics the previous conv's epilogue accumulated.
+    int fuse = 0;
+    const __nv_bfloat16* fin_x = nullptr;      // raw previous conv output, same geometry as the bound tensor
+    const __nv_bfloat16* fin_skip = nullptr;
+    __nv_bfloat16* fin_out = nullptr;
+    const double* fin_stats = nullptr;         // (B, C, 2) [sum, sumsq] over the H*W pixels of fin_x
+    const float* fin_params = nullptr;         // style parameters, element (b, j) at fin_params[b * fin_param_bstride + j]
+    long long fin_param_bstride = 0;
+    int fin_scale_off = 0, fin_bias_off = 0;
+    float fin_eps = 1e-5f;
 };
 
 constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4, HALO_MODE_TF32 = 8;

@@ -43,8 +43,46 @@ constexpr int kPrefetchPairs = 3;         // L2 prefetch distance of the A produ
 
 constexpr int kThreads2 = 96 + 128 * 4;  // 3 control warps + 16 epilogue warps (one per lane quadrant and 32-column chunk)
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// FUSE != 0 (HaloGemmParams::fuse): the TMA A producer is replaced by loader warps that read the RAW output of the previous
+// convolution from global memory (L2), apply its conditional instance norm in registers and write the swizzled halo stage
+// themselves -- the bytes TMA would have written, so the shared-memory port sees no extra traffic (a transform that rewrites
+// a TMA-landed stage in place was measured in round 1: it read and wrote every stage once more and stalled the tensor pipe).
+// Warps: 0 = B producer + L2 prefetch of later halos, 1 = MMA issuer, 2 .. 2+2*NL-1 = loaders (NL warps per 64-channel
+// group; a thread owns 8 fixed channels, so its 16 coefficients live in registers), then the 16 epilogue warps.
+constexpr int kLoadWarpsPerGroup = 1;
+constexpr int kThreads2F = 64 + 2 * kLoadWarpsPerGroup * 32 + 128 * 4;
+
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint4 ld_global_nc_16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_shared_16(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int FUSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? kThreads2F : kThreads2, 1)
 halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloGemmParams p) {
+    constexpr int NL = kLoadWarpsPerGroup;
+    constexpr int W_APROD = FUSE ? -1 : 0, W_BPROD = FUSE ? 0 : 1, W_MMA = FUSE ? 1 : 2;
+    (void)W_APROD;
+    constexpr int W_LOAD0 = 2, W_EPI0 = FUSE ? 2 + 2 * NL : 3;
     constexpr int N = kN2, CW = 32, NCH = N / CW, ESPLIT = 4;
     constexpr uint32_t TMEM_COLS = 2 * N;
     extern __shared__ uint8_t smem_raw[];
@@ -74,7 +112,8 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pair_end = min(total_pairs, pair_begin + ppc);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        // FUSE: every loader warp of both CTAs that fills a stage arrives once on the leader's full barrier
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], FUSE ? 2 * NL : 1); mbar_init(&a_empty[i], 1); }
         mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 4 * ESPLIT); }
         fence_barrier_init();
@@ -84,7 +123,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) stat_s[i] = 0.f;
     __syncthreads();
     cluster_sync();                                           // barriers of both CTAs are initialised
-    if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    if (warp == W_MMA) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -97,7 +136,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         h0 = (r / p.tiles_w) * 8; w0 = (r % p.tiles_w) * 16;
     };
 
-    if (warp == 0) {
+    if (warp == W_APROD) {
         // ================= A producer (both CTAs): own halo patch, transactions land on the leader's barrier ====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -116,7 +155,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_BPROD) {
         // ================= B producer (both CTAs): this CTA's 64 output channels of every block, once ==========
         // one barrier per 64-channel group, so the first MMAs start after 72 KB instead of 144 KB have landed
         if (lane == 0 && pair_begin < pair_end) {
@@ -127,7 +166,100 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     tma_load_2d_2sm(sB + kb * kBHalf, &tmB, &b_full[g], 0, kb * N + (int)rank * (N / 2));
             }
         }
-    } else if (warp == 2) {
+    } else if (FUSE && warp >= W_LOAD0 && warp < W_EPI0) {
+        // ================= fused loaders (both CTAs): global -> registers -> norm affine -> swizzled shared memory ===
+        const int lw = warp - W_LOAD0;
+        const int g = lw / NL;                                    // the 64-channel group this warp serves
+        const int lt = (lw % NL) * 32 + lane;                     // index among the group's loader threads
+        const int v = lt & 7, slot = lt >> 3;                     // 16-byte chunk of the 128-byte row; pixel slot per iteration
+        constexpr int SLOTS = NL * 4, ITERS = (180 + SLOTS - 1) / SLOTS, BATCH = FUSE == 2 ? 5 : 9;   // 45 iterations = 5 x 9 = 9 x 5
+        const int C = p.n_groups * 64, c0 = g * 64 + v * 8;
+        const uint32_t sA_u = smem_u32(sA);
+        float ca[8], cb[8];
+        int cur_n = -1;
+        uint32_t seq = (uint32_t)g;                               // stages are consumed in (pair, group) order
+        if (g < p.n_groups) {
+            for (int pr = pair_begin; pr < pair_end; ++pr, seq += p.n_groups) {
+                int n, h0, w0;
+                if (lt == 0 && pr + kPrefetchPairs < pair_end) {   // keep the global reads L2 hits: TMA prefetch of a later halo
+                    tile_coords(2 * (pr + kPrefetchPairs) + (int)rank, n, h0, w0);
+                    tma_prefetch_4d(&tmA, g * 64, h0 - 1, w0 - 1, n);
+                }
+                tile_coords(2 * pr + (int)rank, n, h0, w0);
+                if (n != cur_n && n < p.B) {
+                    // the arithmetic of cin_apply_fast_kernel (halo_gemm.cu), so that fused and unfused results are identical
+                    const double inv_p = 1.0 / ((double)p.H * (double)p.WRU);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double2 st = *reinterpret_cast<const double2*>(p.fin_stats + ((long long)n * C + c0 + j) * 2);
+                        const double mean = st.x * inv_p;
+                        double var = fma(st.y, inv_p, -mean * mean);
+                        if (var < 0.0) var = 0.0;
+                        const float inv = rsqrtf((float)var + p.fin_eps), nmi = -(float)mean * inv;
+                        const float* ps = p.fin_params + n * p.fin_param_bstride;
+                        ca[j] = inv * ps[p.fin_scale_off + c0 + j];
+                        cb[j] = ps[p.fin_bias_off + c0 + j] + nmi * ps[p.fin_scale_off + c0 + j];
+                    }
+                    cur_n = n;
+                }
+                const uint32_t stage = seq % kAStages2, phase = (seq / kAStages2) & 1;
+                const uint32_t st_base = sA_u + stage * kAStage2;
+                bool waited = false;
+                const uint32_t img_base = (uint32_t)n * (uint32_t)(p.H * p.WRU);     // pixel index of the sample (tensor < 2^31 elements)
+#pragma unroll 1
+                for (int i0 = 0; i0 < ITERS; i0 += BATCH) {
+                    uint4 x[BATCH], sk[FUSE == 2 ? BATCH : 1];
+                    uint32_t okmask = 0;
+#pragma unroll
+                    for (int u = 0; u < BATCH; ++u) {
+                        const int hp = slot + SLOTS * (i0 + u);
+                        const int ww = hp / 10, hh = hp - ww * 10;
+                        const int gh = h0 - 1 + hh, gw = w0 - 1 + ww;
+                        const bool ok = hp < 180 && n < p.B && (unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.WRU;
+                        okmask |= (ok ? 1u : 0u) << u;
+                        const uint32_t off = (img_base + (uint32_t)(gh * p.WRU + gw)) * (uint32_t)C + (uint32_t)c0;
+                        x[u] = make_uint4(0, 0, 0, 0);
+                        if (ok) x[u] = ld_global_nc_16(p.fin_x + off);
+                        if (FUSE == 2) {
+                            sk[u] = make_uint4(0, 0, 0, 0);
+                            if (ok && p.fin_skip) sk[u] = ld_global_nc_16(p.fin_skip + off);
+                        }
+                    }
+                    if (!waited) { mbar_wait(&a_empty[stage], phase ^ 1); waited = true; }      // loads are in flight while we wait
+#pragma unroll
+                    for (int u = 0; u < BATCH; ++u) {
+                        const int hp = slot + SLOTS * (i0 + u);
+                        if (hp >= 180) continue;
+                        uint4 o = make_uint4(0, 0, 0, 0);                                       // 'same' padding stays zero
+                        if ((okmask >> u) & 1u) {
+                            const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x[u]);
+                            const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&sk[FUSE == 2 ? u : 0]);
+                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 xv = __bfloat1622float2(xb[j]);
+                                float o0 = fmaf(xv.x, ca[2 * j], cb[2 * j]), o1 = fmaf(xv.y, ca[2 * j + 1], cb[2 * j + 1]);
+                                if (FUSE == 1) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+                                if (FUSE == 2) { const float2 rv = __bfloat1622float2(sb[j]); o0 += rv.x; o1 += rv.y; }
+                                ob[j] = __floats2bfloat162_rn(o0, o1);
+                            }
+                            if (FUSE == 2) {
+                                const int ww = hp / 10, hh = hp - ww * 10;
+                                if (hh >= 1 && hh <= 8 && ww >= 1 && ww <= 16) {                // centre pixels: this tile owns them
+                                    const uint32_t off = (img_base + (uint32_t)((h0 - 1 + hh) * p.WRU + (w0 - 1 + ww))) * (uint32_t)C + (uint32_t)c0;
+                                    *reinterpret_cast<uint4*>(p.fin_out + off) = o;
+                                }
+                            }
+                        }
+                        st_shared_16(st_base + hp * kRowB2 + ((v ^ (hp & 7)) << 4), o);
+                    }
+                }
+                fence_proxy_async();                              // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader_release(&a_full[stage]);
+            }
+        }
+    } else if (warp == W_MMA) {
         // ================= MMA issuer: leader CTA only ==========================================================
         if (leader_cta) {
             const uint32_t idesc = make_idesc_bf16(256, N);
@@ -143,7 +275,8 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_u + cs * N;
                 for (int g = 0; g < p.n_groups; ++g) {
-                    mbar_wait(&a_full[as], aph);
+                    if (FUSE) mbar_wait_acquire_cluster(&a_full[as], aph);
+                    else mbar_wait(&a_full[as], aph);
                     if (pr == pair_begin) mbar_wait(&b_full[g], 0);      // weights of this group are resident from here on
                     tc_fence_after();
                     const uint32_t a_base16 = sA16 + as * (kAStage2 >> 4);
@@ -161,10 +294,10 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         }
-    } else {
+    } else if (warp >= W_EPI0) {
         // ================= epilogue (both CTAs): own 128 rows; two warps per lane quadrant split the columns ======
         const int q = warp & 3;
-        const int c_begin = ((warp - 3) >> 2) * (NCH / ESPLIT), c_end = c_begin + NCH / ESPLIT;
+        const int c_begin = ((warp - W_EPI0) >> 2) * (NCH / ESPLIT), c_end = c_begin + NCH / ESPLIT;
         const int row = q * 32 + lane;
         const int w_l = row >> 3, h_l = row & 7;
         float* my_sum = stat_s + q * 2 * N;
@@ -236,7 +369,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_before();
     __syncthreads();
     cluster_sync();                                           // both CTAs are done with TMEM and with remote barriers
-    if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    if (warp == W_MMA) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
 size_t halo_gemm2_smem_bytes(int n_groups) {
@@ -246,15 +379,27 @@ size_t halo_gemm2_smem_bytes(int n_groups) {
 // Weights for the 2-CTA kernel use the same packed blocks; the tensor map's box is 64 rows (one CTA's half of N).
 cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
                               cudaStream_t s) {
-    static SmemAttrCache configured;
+    static SmemAttrCache configured[3];
     const size_t smem = halo_gemm2_smem_bytes(p.n_groups);
-    if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel, smem, configured)) return e;
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int pairs = (total + 1) / 2;
     int clusters = num_sms / 2;
     if (pairs < clusters) clusters = pairs;
-    halo_gemm2_kernel<<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
+    if (p.fuse == 0) {
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<0>, smem, configured[0])) return e;
+        halo_gemm2_kernel<0><<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
+        return cudaGetLastError();
+    }
+    if (p.n_groups != 2 || !p.fin_x || !p.fin_stats || !p.fin_params || (p.fuse == 2 && !p.fin_out) || p.fuse > 2)
+        return cudaErrorInvalidValue;
+    if (p.fuse == 1) {
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1>, smem, configured[1])) return e;
+        halo_gemm2_kernel<1><<<2 * clusters, kThreads2F, smem, s>>>(tmA, tmB_half, p);
+    } else {
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<2>, smem, configured[2])) return e;
+        halo_gemm2_kernel<2><<<2 * clusters, kThreads2F, smem, s>>>(tmA, tmB_half, p);
+    }
     return cudaGetLastError();
 }
 

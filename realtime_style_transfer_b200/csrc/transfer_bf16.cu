@@ -21,6 +21,7 @@ struct HaloConv {
     HaloGemmLaunch launch;
     HaloGemmParams p;
     CUtensorMap tmA, tmB, tmB_half;
+    CUtensorMap tmA_fuse;          // fused-norm mode: the RAW tensor the loader warps read (used for its L2 prefetch)
     bool stem_2cta = false;        // SCH_STEM2 / SCH_STEM2B: cta_group::2 kernel (halo_stem2cta.cu)
     bool two_cta = false;          // 128->128 3x3 convs: cta_group::2 kernel with resident weights
     __nv_bfloat16* w_packed = nullptr;
@@ -77,9 +78,17 @@ struct HaloConv {
         return halo_gemm_plan(&launch, &p, err);
     }
 
-    cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s) {
+    // fin (optional): fused input transform of the 2-CTA trunk kernel, fields fuse / fin_* of HaloGemmParams
+    cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s, const HaloGemmParams* fin = nullptr) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
+        if (fin) {
+            if (!two_cta || y_f32) return cudaErrorInvalidValue;
+            q.fuse = fin->fuse; q.fin_x = fin->fin_x; q.fin_skip = fin->fin_skip; q.fin_out = fin->fin_out; q.fin_stats = fin->fin_stats;
+            q.fin_params = fin->fin_params; q.fin_param_bstride = fin->fin_param_bstride;
+            q.fin_scale_off = fin->fin_scale_off; q.fin_bias_off = fin->fin_bias_off;
+            return launch_halo_gemm2(tmA_fuse, tmB_half, q, num_sms, s);
+        }
 #ifdef RST_EXPERIMENTS
         if (exp_env("RST_EXP_NOSTATS")) q.stats = nullptr;     // timing experiments only (wrong results)
         if (exp_env("RST_EXP_NOSTORE")) q.H = 0;
@@ -332,6 +341,7 @@ static void setup_head8(HaloConv* c, const float* k, const float* bias, std::vec
 struct Bf16State {
     int num_sms = 148;
     bool tc_decoder = false;            // expand layers on tensor cores (standard 2-expand geometry)
+    bool fuse1 = false;                 // first norm of every residual block applied by the consuming conv's loader warps
     StemLayout stem_layout{};
     HaloConv stem, contract[4], trunk[10], e0, e1, head;
     __nv_bfloat16 *s_in = nullptr;      // packed stem input
@@ -444,6 +454,15 @@ int bf16_commit(rst_ctx* c) {
         const void* in = i == 0 ? (const void*)st->enc[c->contract.size() - 1] : (i % 2 == 0 ? (const void*)st->bx : (const void*)st->bz);
         if (i == 0 && L.ci > 32) return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: bottleneck input wider than 32 channels");
         if (!hc.bind_input(in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        if (i % 2 == 1 && hc.two_cta &&
+            !encode_halo_map(&hc.tmA_fuse, st->by, B, L.hi, L.wi, hc.in_C, hc.launch.row_bytes / 2, sched_halo_h(SCH_C3), sched_halo_w(SCH_C3), &err))
+            return fail(c, RST_ERR_CUDA, err);
+    }
+    {
+        // Fused first norm (single style: the affine is per (sample, channel); the per-pixel blend of two styles keeps the pass).
+        const char* env = ab_env("RST_FUSE_NORM");
+        st->fuse1 = g.num_styles == 1 && !(env && env[0] == '0') && (long long)B * c->bott_h * c->bott_w * F < (1LL << 31);
+        for (int i = 1; i < 10; i += 2) st->fuse1 = st->fuse1 && st->trunk[i].two_cta && st->trunk[i].p.n_groups == 2;
     }
     // ---- decoder ----
     if (st->tc_decoder) {
@@ -524,12 +543,23 @@ int bf16_transfer_forward(rst_ctx* c, const void* d_content, int content_dtype, 
         double* st1 = st->stats + (size_t)(2 * b + 1) * st->stats_stride;
         { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b].run(st->by, false, st0, batch, st->num_sms, s)); }
         record_tap(c, name + "/conv0/relu", st->by, px * F, true, s);
-        rc = norm_pass(c, st->by, false, st->bz, false, nullptr, st0, batch, PB, F, c->bott_w, d_style_params, cursor, ACT_RELU, s);
-        if (rc) return rc;
-        record_tap(c, name + "/conv0/cin", st->bz, px * F, true, s);
-        { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(st->by, false, st1, batch, st->num_sms, s)); }
-        record_tap(c, name + "/conv1/relu", st->by, px * F, true, s);
-        rc = norm_pass(c, st->by, false, st->bx, false, b == 0 ? nullptr : st->bx, st1, batch, PB, F, c->bott_w, d_style_params,
+        const __nv_bfloat16* y1 = st->by;                           // raw output of conv1
+        if (st->fuse1 && !c->keep_taps) {
+            // conv1 reads the RAW conv0 output; relu(cin(.)) happens in its loader warps (no pass, no normalised tensor)
+            HaloGemmParams fin;
+            fin.fuse = 1; fin.fin_x = st->by; fin.fin_stats = st0; fin.fin_params = d_style_params;
+            fin.fin_param_bstride = (long long)g.num_styles * c->num_style_params;
+            fin.fin_scale_off = cursor; fin.fin_bias_off = cursor + F;
+            { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(st->bz, false, st1, batch, st->num_sms, s, &fin)); }
+            y1 = st->bz;
+        } else {
+            rc = norm_pass(c, st->by, false, st->bz, false, nullptr, st0, batch, PB, F, c->bott_w, d_style_params, cursor, ACT_RELU, s);
+            if (rc) return rc;
+            record_tap(c, name + "/conv0/cin", st->bz, px * F, true, s);
+            { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(st->by, false, st1, batch, st->num_sms, s)); }
+        }
+        record_tap(c, name + "/conv1/relu", y1, px * F, true, s);
+        rc = norm_pass(c, y1, false, st->bx, false, b == 0 ? nullptr : st->bx, st1, batch, PB, F, c->bott_w, d_style_params,
                        cursor + 2 * F, ACT_NONE, s);
         if (rc) return rc;
         record_tap(c, name, st->bx, px * F, true, s);

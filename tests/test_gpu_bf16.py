@@ -149,6 +149,31 @@ def test_transfer_bf16_full_resolution(cuda_device):
     assert out.min() >= 0 and out.max() <= 1
 
 
+@pytest.mark.parametrize("h,w,batch", [(60, 100, 3), (64, 128, 2), (120, 200, 5)])
+def test_fused_first_norm_matches_the_separate_pass(cuda_device, monkeypatch, h, w, batch):
+    """The first instance norm of every residual block is applied by the loader warps of the consuming 2-CTA conv kernel
+    (halo_gemm2.cu, fuse = 1: global -> registers -> relu(a*x+b) -> swizzled shared memory) instead of a separate pass.
+    Both paths compute the same fp32 expression and round once to bf16, so they agree up to the atomics order of the
+    statistics.  Geometries: ragged tile edges (bottleneck 15x25, 30x50), an odd tile count (phantom tile of the last pair),
+    sample boundaries inside a cluster's tile range."""
+    shape_in, shape_out = (h, w, 17), (h, w, 3)
+    spec = O.TransferSpec(shape_in, shape_out, h // 4, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=5, trained_like=True)
+    content = O.synthetic_content(batch, h, w, ShapeConfig(num_channels=17).channels, seed=6, unit_depth=True)
+    params = np.random.default_rng(7).uniform(0.3, 1.2, (batch, 1, spec.num_style_parameters)).astype(np.float32)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RST_FUSE_NORM", mode)           # read when the weights are committed
+        outs[mode], _, launches = run_bf16(shape_in, shape_out, h // 4, 128, 1, weights, content, params)
+        outs[mode + "_launches"] = launches
+    assert outs["0_launches"] - outs["1_launches"] == 5     # five passes gone
+    d = np.abs(outs["1"] - outs["0"])
+    print(f"fused vs separate first norm {h}x{w} B={batch}: max diff {d.max():.3e}, identical {float((d == 0).mean()):.4f}")
+    assert d.max() < 5e-3
+    ref = O.transfer_forward(spec, weights, content, params).numpy()
+    assert rel_l2(outs["1"], ref) <= BF16_REL_TOL
+
+
 def test_transfer_bf16_full_resolution_batch8(cuda_device):
     """The benchmarked configuration itself: rst-960-120-128-17 at batch 8 (more tiles per cluster and more atomics per
     statistic than batch 2), bf16 vs the fp32 oracle on all eight frames."""
