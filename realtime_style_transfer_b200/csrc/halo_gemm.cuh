@@ -158,6 +158,7 @@ struct HaloGemmParams {
     long long fin_param_bstride = 0;
     int fin_scale_off = 0, fin_bias_off = 0;
     float fin_eps = 1e-5f;
+    int fuse_dbg = 0;                          // RST_EXPERIMENTS builds only: 1 = skip the global loads, 2 = skip the smem stores (timing)
 };
 
 constexpr int HALO_MODE_RELU = 1, HALO_MODE_POST = 2, HALO_MODE_F32 = 4, HALO_MODE_TF32 = 8;

@@ -49,8 +49,7 @@ constexpr int kThreads2 = 96 + 128 * 4;  // 3 control warps + 16 epilogue warps 
 // a TMA-landed stage in place was measured in round 1: it read and wrote every stage once more and stalled the tensor pipe).
 // Warps: 0 = B producer + L2 prefetch of later halos, 1 = MMA issuer, 2 .. 2+2*NL-1 = loaders (NL warps per 64-channel
 // group; a thread owns 8 fixed channels, so its 16 coefficients live in registers), then the 16 epilogue warps.
-constexpr int kLoadWarpsPerGroup = 1;
-constexpr int kThreads2F = 64 + 2 * kLoadWarpsPerGroup * 32 + 128 * 4;
+constexpr int threads2f(int nl) { return 64 + 2 * nl * 32 + 128 * 4; }
 
 __device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
@@ -76,10 +75,9 @@ __device__ __forceinline__ void st_shared_16(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int FUSE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? kThreads2F : kThreads2, 1)
+template <int FUSE, int NL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? threads2f(NL) : kThreads2, 1)
 halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloGemmParams p) {
-    constexpr int NL = kLoadWarpsPerGroup;
     constexpr int W_APROD = FUSE ? -1 : 0, W_BPROD = FUSE ? 0 : 1, W_MMA = FUSE ? 1 : 2;
     (void)W_APROD;
     constexpr int W_LOAD0 = 2, W_EPI0 = FUSE ? 2 + 2 * NL : 3;
@@ -172,9 +170,13 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int g = lw / NL;                                    // the 64-channel group this warp serves
         const int lt = (lw % NL) * 32 + lane;                     // index among the group's loader threads
         const int v = lt & 7, slot = lt >> 3;                     // 16-byte chunk of the 128-byte row; pixel slot per iteration
-        constexpr int SLOTS = NL * 4, ITERS = (180 + SLOTS - 1) / SLOTS, BATCH = FUSE == 2 ? 5 : 9;   // 45 iterations = 5 x 9 = 9 x 5
+        constexpr int SLOTS = NL * 4, ITERS = (180 + SLOTS - 1) / SLOTS;
+        constexpr int BATCH = 3, NBATCH = (ITERS + BATCH - 1) / BATCH;      // register double buffering: 2 x BATCH vectors in flight
+        static_assert(SLOTS == 8 || SLOTS == 4, "4 or 8 pixel slots per iteration");
         const int C = p.n_groups * 64, c0 = g * 64 + v * 8;
-        const uint32_t sA_u = smem_u32(sA);
+        const int rowC = p.WRU * C;                                // elements per image row
+        // halo pixel hp = slot + 8 i sits at shared-memory row hp; its 16-byte chunk v is swizzled by (row & 7) = slot
+        const uint32_t st_thread = smem_u32(sA) + slot * kRowB2;
         float ca[8], cb[8];
         int cur_n = -1;
         uint32_t seq = (uint32_t)g;                               // stages are consumed in (pair, group) order
@@ -203,56 +205,81 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     cur_n = n;
                 }
                 const uint32_t stage = seq % kAStages2, phase = (seq / kAStages2) & 1;
-                const uint32_t st_base = sA_u + stage * kAStage2;
-                bool waited = false;
-                const uint32_t img_base = (uint32_t)n * (uint32_t)(p.H * p.WRU);     // pixel index of the sample (tensor < 2^31 elements)
-#pragma unroll 1
-                for (int i0 = 0; i0 < ITERS; i0 += BATCH) {
-                    uint4 x[BATCH], sk[FUSE == 2 ? BATCH : 1];
-                    uint32_t okmask = 0;
+                // A ROLLED, register double-buffered loop (the fully unrolled form was 6000 instructions and thrashed the
+                // instruction cache).  Issue side walks the halo: iteration i handles row hp = slot + SLOTS*i = column ww, row hh.
+                const int hy = h0 - 1, wx = w0 - 1;
+                int hp_i = slot, hh = slot, ww = 0;                // slot < 8 < 10
+                int off = (n * p.H + (hy + hh)) * rowC + wx * C + c0;                 // element offset (tensor < 2^31 elements)
+                const bool n_ok = n < p.B;
+                int hp_c = slot;
+                uint32_t st_addr = st_thread + stage * kAStage2;
+                auto issue = [&](uint4 (&x)[BATCH], uint4 (&sk)[FUSE == 2 ? BATCH : 1], uint32_t& okmask) {
+                    okmask = 0;
 #pragma unroll
                     for (int u = 0; u < BATCH; ++u) {
-                        const int hp = slot + SLOTS * (i0 + u);
-                        const int ww = hp / 10, hh = hp - ww * 10;
-                        const int gh = h0 - 1 + hh, gw = w0 - 1 + ww;
-                        const bool ok = hp < 180 && n < p.B && (unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.WRU;
+                        const bool ok = n_ok && hp_i < 180 && (unsigned)(hy + hh) < (unsigned)p.H && (unsigned)(wx + ww) < (unsigned)p.WRU;
                         okmask |= (ok ? 1u : 0u) << u;
-                        const uint32_t off = (img_base + (uint32_t)(gh * p.WRU + gw)) * (uint32_t)C + (uint32_t)c0;
                         x[u] = make_uint4(0, 0, 0, 0);
+#ifdef RST_EXPERIMENTS
+                        if (!(p.fuse_dbg & 1))
+#endif
                         if (ok) x[u] = ld_global_nc_16(p.fin_x + off);
                         if (FUSE == 2) {
                             sk[u] = make_uint4(0, 0, 0, 0);
                             if (ok && p.fin_skip) sk[u] = ld_global_nc_16(p.fin_skip + off);
                         }
+                        hp_i += SLOTS; hh += SLOTS; off += SLOTS * rowC;               // next iteration: SLOTS rows down the halo column ...
+                        if (hh >= 10) { hh -= 10; ww += 1; off += C - 10 * rowC; }     // ... wrapping into the next column
                     }
-                    if (!waited) { mbar_wait(&a_empty[stage], phase ^ 1); waited = true; }      // loads are in flight while we wait
+                };
+                auto consume = [&](const uint4 (&x)[BATCH], const uint4 (&sk)[FUSE == 2 ? BATCH : 1], uint32_t okmask) {
 #pragma unroll
                     for (int u = 0; u < BATCH; ++u) {
-                        const int hp = slot + SLOTS * (i0 + u);
-                        if (hp >= 180) continue;
-                        uint4 o = make_uint4(0, 0, 0, 0);                                       // 'same' padding stays zero
-                        if ((okmask >> u) & 1u) {
-                            const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x[u]);
-                            const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&sk[FUSE == 2 ? u : 0]);
-                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+                        if (hp_c < 180) {                                                       // rows 180.. do not exist
+                            uint4 o = make_uint4(0, 0, 0, 0);                                   // 'same' padding stays zero
+                            if ((okmask >> u) & 1u) {
+                                const uint32_t* xw = reinterpret_cast<const uint32_t*>(&x[u]);
+                                const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&sk[FUSE == 2 ? u : 0]);
+                                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 xv = __bfloat1622float2(xb[j]);
-                                float o0 = fmaf(xv.x, ca[2 * j], cb[2 * j]), o1 = fmaf(xv.y, ca[2 * j + 1], cb[2 * j + 1]);
-                                if (FUSE == 1) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
-                                if (FUSE == 2) { const float2 rv = __bfloat1622float2(sb[j]); o0 += rv.x; o1 += rv.y; }
-                                ob[j] = __floats2bfloat162_rn(o0, o1);
-                            }
-                            if (FUSE == 2) {
-                                const int ww = hp / 10, hh = hp - ww * 10;
-                                if (hh >= 1 && hh <= 8 && ww >= 1 && ww <= 16) {                // centre pixels: this tile owns them
-                                    const uint32_t off = (img_base + (uint32_t)((h0 - 1 + hh) * p.WRU + (w0 - 1 + ww))) * (uint32_t)C + (uint32_t)c0;
-                                    *reinterpret_cast<uint4*>(p.fin_out + off) = o;
+                                for (int j = 0; j < 4; ++j) {
+                                    // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked
+                                    const float x0 = __uint_as_float(xw[j] << 16), x1 = __uint_as_float(xw[j] & 0xFFFF0000u);
+                                    const float o0 = fmaf(x0, ca[2 * j], cb[2 * j]), o1 = fmaf(x1, ca[2 * j + 1], cb[2 * j + 1]);
+                                    if (FUSE == 1) {
+                                        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(o1), "f"(o0));    // relu + pack in one
+                                    } else {
+                                        const float2 rv = __bfloat1622float2(sb[j]);
+                                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o0 + rv.x, o1 + rv.y);
+                                        ow[j] = *reinterpret_cast<uint32_t*>(&h2);
+                                    }
+                                }
+                                if (FUSE == 2) {
+                                    const int w2 = hp_c / 10, h2 = hp_c - w2 * 10;
+                                    if (h2 >= 1 && h2 <= 8 && w2 >= 1 && w2 <= 16) {            // centre pixels: this tile owns them
+                                        const int o_off = (n * p.H + (hy + h2)) * rowC + (wx + w2) * C + c0;
+                                        *reinterpret_cast<uint4*>(p.fin_out + o_off) = o;
+                                    }
                                 }
                             }
+#ifdef RST_EXPERIMENTS
+                            if (!(p.fuse_dbg & 2))
+#endif
+                            st_shared_16(st_addr + ((v ^ (hp_c & 7)) << 4), o);
                         }
-                        st_shared_16(st_base + hp * kRowB2 + ((v ^ (hp & 7)) << 4), o);
+                        hp_c += SLOTS; st_addr += SLOTS * kRowB2;
                     }
+                };
+                uint4 xa[BATCH], xb_[BATCH], ska[FUSE == 2 ? BATCH : 1], skb[FUSE == 2 ? BATCH : 1];
+                uint32_t oka, okb;
+                issue(xa, ska, oka);
+                mbar_wait(&a_empty[stage], phase ^ 1);            // the first loads are in flight while we wait for the slot
+#pragma unroll 1
+                for (int k = 0; k < NBATCH; k += 2) {              // batches past the halo's end are predicated off
+                    issue(xb_, skb, okb);
+                    consume(xa, ska, oka);
+                    issue(xa, ska, oka);
+                    consume(xb_, skb, okb);
                 }
                 fence_proxy_async();                              // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
@@ -379,7 +406,7 @@ size_t halo_gemm2_smem_bytes(int n_groups) {
 // Weights for the 2-CTA kernel use the same packed blocks; the tensor map's box is 64 rows (one CTA's half of N).
 cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
                               cudaStream_t s) {
-    static SmemAttrCache configured[3];
+    static SmemAttrCache configured[5];
     const size_t smem = halo_gemm2_smem_bytes(p.n_groups);
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
@@ -387,18 +414,25 @@ cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_hal
     int clusters = num_sms / 2;
     if (pairs < clusters) clusters = pairs;
     if (p.fuse == 0) {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<0>, smem, configured[0])) return e;
-        halo_gemm2_kernel<0><<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<0, 1>, smem, configured[0])) return e;
+        halo_gemm2_kernel<0, 1><<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
         return cudaGetLastError();
     }
     if (p.n_groups != 2 || !p.fin_x || !p.fin_stats || !p.fin_params || (p.fuse == 2 && !p.fin_out) || p.fuse > 2)
         return cudaErrorInvalidValue;
-    if (p.fuse == 1) {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1>, smem, configured[1])) return e;
-        halo_gemm2_kernel<1><<<2 * clusters, kThreads2F, smem, s>>>(tmA, tmB_half, p);
+    static const int nl = ab_env("RST_FUSE_NL") ? atoi(ab_env("RST_FUSE_NL")) : 2;     // loader warps per channel group (A/B switch)
+    if (p.fuse == 1 && nl == 1) {
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 1>, smem, configured[1])) return e;
+        halo_gemm2_kernel<1, 1><<<2 * clusters, threads2f(1), smem, s>>>(tmA, tmB_half, p);
+    } else if (p.fuse == 1) {
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 2>, smem, configured[2])) return e;
+        halo_gemm2_kernel<1, 2><<<2 * clusters, threads2f(2), smem, s>>>(tmA, tmB_half, p);
+    } else if (nl == 1) {
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<2, 1>, smem, configured[3])) return e;
+        halo_gemm2_kernel<2, 1><<<2 * clusters, threads2f(1), smem, s>>>(tmA, tmB_half, p);
     } else {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<2>, smem, configured[2])) return e;
-        halo_gemm2_kernel<2><<<2 * clusters, kThreads2F, smem, s>>>(tmA, tmB_half, p);
+        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<2, 2>, smem, configured[4])) return e;
+        halo_gemm2_kernel<2, 2><<<2 * clusters, threads2f(2), smem, s>>>(tmA, tmB_half, p);
     }
     return cudaGetLastError();
 }

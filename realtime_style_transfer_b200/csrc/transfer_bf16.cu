@@ -87,6 +87,9 @@ struct HaloConv {
             q.fuse = fin->fuse; q.fin_x = fin->fin_x; q.fin_skip = fin->fin_skip; q.fin_out = fin->fin_out; q.fin_stats = fin->fin_stats;
             q.fin_params = fin->fin_params; q.fin_param_bstride = fin->fin_param_bstride;
             q.fin_scale_off = fin->fin_scale_off; q.fin_bias_off = fin->fin_bias_off;
+#ifdef RST_EXPERIMENTS
+            if (exp_env("RST_EXP_FUSE_DBG")) q.fuse_dbg = atoi(exp_env("RST_EXP_FUSE_DBG"));
+#endif
             return launch_halo_gemm2(tmA_fuse, tmB_half, q, num_sms, s);
         }
 #ifdef RST_EXPERIMENTS

@@ -185,3 +185,86 @@ def test_bf16_emulation_mode_rounds_activations_and_bounds_the_error():
         t = taps[name]
         assert torch.equal(t, t.to(torch.bfloat16).to(t.dtype)), name
     assert not torch.equal(taps["expand_last/conv"], taps["expand_last/conv"].to(torch.bfloat16).to(torch.float64))
+
+
+# ---- second restatements (oracle/naive_np.py) of the pieces that had only one: MobileNetV3Small, training BN, RMSprop ----
+def test_mobilenet_v3_small_against_the_loop_restatement():
+    """Whole style predictor (stride-2 blocks with correct_pad on even AND odd sizes, squeeze-excite, hard-swish, residual
+    adds, the two linear heads) on a 40x72 style image: torch oracle vs the numpy loop restatement."""
+    from oracle import naive_np as NP
+    w = O.init_predictor_weights("MOBILE_NET", 50, seed=4)
+    style = np.random.default_rng(5).uniform(0, 1, (1, 40, 72, 3)).astype(np.float32)     # 40 -> 20 -> 10 -> 5 (odd) -> 3
+    ref = NP.style_predictor({k: v.astype(np.float64) for k, v in w.items()}, style)
+    import torch
+    got = O.predictor_forward("MOBILE_NET", w, style, dtype=torch.float64).numpy()
+    assert got.shape == ref.shape == (1, 50)
+    assert np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+    got32 = O.predictor_forward("MOBILE_NET", w, style).numpy()
+    assert np.abs(got32 - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_inverted_res_block_stride2_padding_cases():
+    """correct_pad: even sizes pad (k//2 - 1, k//2), odd sizes (k//2, k//2), for the 3x3 and 5x5 depthwise kernels."""
+    from oracle import naive_np as NP
+    import torch
+    assert NP.correct_pad(8, 3) == (0, 1) and NP.correct_pad(9, 3) == (1, 1)
+    assert NP.correct_pad(8, 5) == (1, 2) and NP.correct_pad(9, 5) == (2, 2)
+    for size, k in ((8, 3), (9, 3), (8, 5), (9, 5)):
+        assert O._correct_pad(size, k) == NP.correct_pad(size, k)
+        rng = np.random.default_rng(size * k)
+        x = rng.standard_normal((1, size, size + 1, 4))
+        kern = rng.standard_normal((k, k, 4, 1))
+        pt, pb = NP.correct_pad(size, k)
+        pl, pr = NP.correct_pad(size + 1, k)
+        ref = NP.depthwise_valid(NP.zero_pad(x, pt, pb, pl, pr), kern, 2)
+        got = O.depthwise_conv2d(torch.as_tensor(x), torch.as_tensor(kern), 2, (pt, pb, pl, pr)).numpy()
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-12
+
+
+def test_training_batchnorm_and_moving_statistics_against_the_loop_restatement():
+    from oracle import naive_np as NP
+    import torch
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 5, 7, 6)) * 2 + 1
+    gamma, beta = rng.uniform(0.5, 1.5, 6), rng.standard_normal(6)
+    mm, mv = rng.standard_normal(6), rng.uniform(0.5, 2, 6)
+    for momentum in (0.99, 0.999):
+        y, nm, nv = NP.batchnorm_training(x, gamma, beta, mm, mv, eps=1e-3, momentum=momentum)
+        out = []
+        got = O.batchnorm(torch.as_tensor(x), torch.as_tensor(gamma), torch.as_tensor(beta), torch.as_tensor(mm),
+                          torch.as_tensor(mv), training=True, moving_out=out, momentum=momentum).numpy()
+        assert np.abs(got - y).max() < 1e-12
+        assert np.abs(out[0][0].numpy() - nm).max() < 1e-12 and np.abs(out[0][1].numpy() - nv).max() < 1e-12
+    inf = NP.batchnorm_inference(x, gamma, beta, mm, mv)
+    got = O.batchnorm(torch.as_tensor(x), torch.as_tensor(gamma), torch.as_tensor(beta), torch.as_tensor(mm),
+                      torch.as_tensor(mv)).numpy()
+    assert np.abs(got - inf).max() < 1e-12
+
+
+def test_rmsprop_against_the_loop_restatement():
+    from oracle import naive_np as NP
+    import torch
+    rng = np.random.default_rng(1)
+    w = {"a": rng.standard_normal((3, 4)).astype(np.float32), "b": rng.standard_normal(5).astype(np.float32)}
+    slots = {k: np.zeros_like(v, np.float64) for k, v in w.items()}
+    ref_w = {k: v.astype(np.float64) for k, v in w.items()}
+    ref_s = {k: np.zeros_like(v, np.float64) for k, v in w.items()}
+    for step in range(3):
+        g = {k: rng.standard_normal(v.shape) * 10.0 ** (step - 2) for k, v in w.items()}
+        w, slots = O.rmsprop_update(w, {k: torch.as_tensor(v) for k, v in g.items()}, slots)
+        for k in ref_w:
+            ref_w[k], ref_s[k] = NP.rmsprop_step(ref_w[k], g[k], ref_s[k])
+            assert np.abs(slots[k] - ref_s[k]).max() < 1e-15
+            assert np.abs(w[k] - ref_w[k]).max() < 1e-6           # the oracle stores float32 variables, as Keras does
+            ref_w[k] = w[k].astype(np.float64)
+
+
+def test_total_variation_and_maxpool_against_the_loop_restatement():
+    from oracle import naive_np as NP
+    import torch
+    rng = np.random.default_rng(2)
+    img = rng.uniform(0, 1, (2, 6, 9, 3))
+    assert np.abs(O.total_variation(torch.as_tensor(img)).numpy() - NP.total_variation(img)).max() < 1e-12
+    x = rng.standard_normal((1, 6, 8, 5))
+    got = torch.nn.functional.max_pool2d(torch.as_tensor(x).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).numpy()
+    assert np.array_equal(got, NP.max_pool2(x))
