@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
-    while (!ok) {
+    for (;; __nanosleep(40)) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
@@ -64,7 +64,13 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (ok) break;
     }
+}
+// Waiting warps that poll hot steal issue slots from the loader warps (FUSE): back off between polls.
+template <int NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(NS);
 }
 __device__ __forceinline__ uint4 ld_global_nc_16(const void* p) {
     uint4 r;
@@ -350,7 +356,8 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int gh = h0 + h_l, gw = w0 + w_l;
             const bool valid = n < p.B && gh < p.H && gw < p.WRU;
             if (n != cur_n) { flush(); cur_n = n; }
-            mbar_wait(&acc_full[cs], cph);
+            if (FUSE) mbar_wait_backoff<200>(&acc_full[cs], cph);
+            else mbar_wait(&acc_full[cs], cph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * N;
             // Each warp owns one 32-column chunk of one lane quadrant: the accumulator stage is handed back to the MMA warp
@@ -406,7 +413,7 @@ size_t halo_gemm2_smem_bytes(int n_groups) {
 // Weights for the 2-CTA kernel use the same packed blocks; the tensor map's box is 64 rows (one CTA's half of N).
 cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloGemmParams& p, int num_sms,
                               cudaStream_t s) {
-    static SmemAttrCache configured[5];
+    static SmemAttrCache configured[2];
     const size_t smem = halo_gemm2_smem_bytes(p.n_groups);
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
@@ -418,22 +425,10 @@ cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_hal
         halo_gemm2_kernel<0, 1><<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
         return cudaGetLastError();
     }
-    if (p.n_groups != 2 || !p.fin_x || !p.fin_stats || !p.fin_params || (p.fuse == 2 && !p.fin_out) || p.fuse > 2)
-        return cudaErrorInvalidValue;
-    static const int nl = ab_env("RST_FUSE_NL") ? atoi(ab_env("RST_FUSE_NL")) : 2;     // loader warps per channel group (A/B switch)
-    if (p.fuse == 1 && nl == 1) {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 1>, smem, configured[1])) return e;
-        halo_gemm2_kernel<1, 1><<<2 * clusters, threads2f(1), smem, s>>>(tmA, tmB_half, p);
-    } else if (p.fuse == 1) {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 2>, smem, configured[2])) return e;
-        halo_gemm2_kernel<1, 2><<<2 * clusters, threads2f(2), smem, s>>>(tmA, tmB_half, p);
-    } else if (nl == 1) {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<2, 1>, smem, configured[3])) return e;
-        halo_gemm2_kernel<2, 1><<<2 * clusters, threads2f(1), smem, s>>>(tmA, tmB_half, p);
-    } else {
-        if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<2, 2>, smem, configured[4])) return e;
-        halo_gemm2_kernel<2, 2><<<2 * clusters, threads2f(2), smem, s>>>(tmA, tmB_half, p);
-    }
+    // fuse 1 only is instantiated: fuse 2 (skip add + write-back in the loader) compiles but was never profitable to finish
+    if (p.n_groups != 2 || !p.fin_x || !p.fin_stats || !p.fin_params || p.fuse != 1) return cudaErrorInvalidValue;
+    if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 2>, smem, configured[1])) return e;
+    halo_gemm2_kernel<1, 2><<<2 * clusters, threads2f(2), smem, s>>>(tmA, tmB_half, p);
     return cudaGetLastError();
 }
 

@@ -350,14 +350,13 @@ struct Bf16State {
     __nv_bfloat16 *s_in = nullptr;      // packed stem input
     __nv_bfloat16* enc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // encoder activations (enc[0] = stem output)
     __nv_bfloat16 *bx = nullptr, *by = nullptr, *bz = nullptr;   // bottleneck tensors
-    __nv_bfloat16 *ye0 = nullptr, *ze0 = nullptr, *ye1 = nullptr, *ze1 = nullptr;  // decoder tensors
+    __nv_bfloat16 *ye0 = nullptr, *ye1 = nullptr;                  // decoder tensors (normalised in place)
     float* ylast = nullptr;
     double* stats = nullptr;            // [13][max_batch][F][2]
     size_t stats_bytes = 0, stats_stride = 0;
     ~Bf16State() {
         for (auto q : enc) if (q) cudaFree(q);
-        for (void* q : {(void*)s_in, (void*)bx, (void*)by, (void*)bz, (void*)ye0, (void*)ze0, (void*)ye1,
-                        (void*)ze1, (void*)ylast, (void*)stats})
+        for (void* q : {(void*)s_in, (void*)bx, (void*)by, (void*)bz, (void*)ye0, (void*)ye1, (void*)ylast, (void*)stats})
             if (q) cudaFree(q);
     }
 };
@@ -391,9 +390,7 @@ int bf16_create(rst_ctx* c) {
     if (st->tc_decoder) {
         const size_t p1 = pb * 4, p2 = pb * 16;
         RST_CUDA(c, cudaMalloc(&st->ye0, p1 * 32 * 2));
-        RST_CUDA(c, cudaMalloc(&st->ze0, p1 * 32 * 2));
         RST_CUDA(c, cudaMalloc(&st->ye1, p2 * 16 * 2));
-        RST_CUDA(c, cudaMalloc(&st->ze1, p2 * 16 * 2));
         RST_CUDA(c, cudaMalloc(&st->ylast, p2 * 3 * 4));
     }
     st->stats_stride = B * F * 2;
@@ -454,17 +451,22 @@ int bf16_commit(rst_ctx* c) {
         setup_conv3x3(&hc, L.ci, F, k->host.data(), b->host.data(), ACT_RELU, &packed, &cb);
         RST_CUDA(c, hc.upload(packed, cb, nullptr, nullptr));
         hc.p.out_H = L.ho; hc.p.out_W = L.wo;
-        const void* in = i == 0 ? (const void*)st->enc[c->contract.size() - 1] : (i % 2 == 0 ? (const void*)st->bx : (const void*)st->bz);
+        // Both norm passes run IN PLACE on the tensor the conv just wrote (59 MB at batch 8: still in the 126 MB L2, and it stays
+        // there for the next conv's reads).  Block b: conv0 reads the block input X and writes by; norm 1 on by; conv1 reads by
+        // and writes Z; norm 2 on Z adds the skip X; Z is the next block's input.  X / Z alternate between bx and bz.
+        const int blk = i / 2;
+        const void* in = i == 0 ? (const void*)st->enc[c->contract.size() - 1]
+                       : (i % 2 == 1 ? (const void*)st->by : (blk % 2 == 1 ? (const void*)st->bz : (const void*)st->bx));
         if (i == 0 && L.ci > 32) return fail(c, RST_ERR_UNSUPPORTED, "bf16 path: bottleneck input wider than 32 channels");
         if (!hc.bind_input(in, B, L.hi, L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
-        if (i % 2 == 1 && hc.two_cta &&
-            !encode_halo_map(&hc.tmA_fuse, st->by, B, L.hi, L.wi, hc.in_C, hc.launch.row_bytes / 2, sched_halo_h(SCH_C3), sched_halo_w(SCH_C3), &err))
-            return fail(c, RST_ERR_CUDA, err);
+        hc.tmA_fuse = hc.tmA;          // fused-norm mode reads the same tensor (raw), through the loader warps
     }
     {
-        // Fused first norm (single style: the affine is per (sample, channel); the per-pixel blend of two styles keeps the pass).
+        // Fused first norm: OPT-IN (RST_FUSE_NORM=1).  Correct (tests/test_gpu_bf16.py) but slower on B200 than conv + in-place
+        // pass: 112 us against 48 + 20 us per conv at batch 8 (profiles/r02_03_fused_norm.md) -- the loader warps' instruction
+        // stream, not memory, is the limit.  Single style only (the per-pixel blend of two styles needs the weight mip).
         const char* env = ab_env("RST_FUSE_NORM");
-        st->fuse1 = g.num_styles == 1 && !(env && env[0] == '0') && (long long)B * c->bott_h * c->bott_w * F < (1LL << 31);
+        st->fuse1 = g.num_styles == 1 && env && env[0] == '1' && (long long)B * c->bott_h * c->bott_w * F < (1LL << 31);
         for (int i = 1; i < 10; i += 2) st->fuse1 = st->fuse1 && st->trunk[i].two_cta && st->trunk[i].p.n_groups == 2;
     }
     // ---- decoder ----
@@ -476,19 +478,19 @@ int bf16_commit(rst_ctx* c) {
                      c->find_weight(L0.name + "/conv/bias")->host.data(), &packed, &cb);
         RST_CUDA(c, st->e0.upload(packed, cb, nullptr, nullptr));
         st->e0.p.out_H = L0.ho; st->e0.p.out_W = L0.wo;
-        if (!st->e0.bind_input(st->bx, B, L0.hi, L0.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        if (!st->e0.bind_input(st->bz, B, L0.hi, L0.wi, &err)) return fail(c, RST_ERR_CUDA, err);   // block 4 (even) leaves its output in bz
         setup_convt2(&st->e1, L1.ci, L1.co, c->find_weight(L1.name + "/conv/kernel")->host.data(),
                      c->find_weight(L1.name + "/conv/bias")->host.data(), &packed, &cb);
         RST_CUDA(c, st->e1.upload(packed, cb, nullptr, nullptr));
         st->e1.p.out_H = L1.ho; st->e1.p.out_W = L1.wo;
-        if (!st->e1.bind_input(st->ze0, B, L1.hi, L1.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        if (!st->e1.bind_input(st->ye0, B, L1.hi, L1.wi, &err)) return fail(c, RST_ERR_CUDA, err);
         const char* env8 = ab_env("RST_HEAD8");
         const bool head8 = L2.wi % 8 == 0 && !(env8 && env8[0] == '0');
         (head8 ? setup_head8 : setup_head)(&st->head, c->find_weight(L2.name + "/conv/kernel")->host.data(),
                    c->find_weight(L2.name + "/conv/bias")->host.data(), &packed, &cb);
         RST_CUDA(c, st->head.upload(packed, cb, nullptr, nullptr));
         st->head.p.out_H = L2.ho; st->head.p.out_W = L2.wo;
-        if (!st->head.bind_input(st->ze1, B, L2.hi, L2.wi / (head8 ? 8 : 4), &err)) return fail(c, RST_ERR_CUDA, err);
+        if (!st->head.bind_input(st->ye1, B, L2.hi, L2.wi / (head8 ? 8 : 4), &err)) return fail(c, RST_ERR_CUDA, err);
     }
     return RST_OK;
 }
@@ -546,26 +548,26 @@ int bf16_transfer_forward(rst_ctx* c, const void* d_content, int content_dtype, 
         double* st1 = st->stats + (size_t)(2 * b + 1) * st->stats_stride;
         { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b].run(st->by, false, st0, batch, st->num_sms, s)); }
         record_tap(c, name + "/conv0/relu", st->by, px * F, true, s);
-        const __nv_bfloat16* y1 = st->by;                           // raw output of conv1
+        __nv_bfloat16* z = b % 2 == 0 ? st->bz : st->bx;            // conv1 output, then (in place) the block output
+        const __nv_bfloat16* skip = b % 2 == 0 ? st->bx : st->bz;   // the block input
         if (st->fuse1 && !c->keep_taps) {
             // conv1 reads the RAW conv0 output; relu(cin(.)) happens in its loader warps (no pass, no normalised tensor)
             HaloGemmParams fin;
             fin.fuse = 1; fin.fin_x = st->by; fin.fin_stats = st0; fin.fin_params = d_style_params;
             fin.fin_param_bstride = (long long)g.num_styles * c->num_style_params;
             fin.fin_scale_off = cursor; fin.fin_bias_off = cursor + F;
-            { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(st->bz, false, st1, batch, st->num_sms, s, &fin)); }
-            y1 = st->bz;
+            { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(z, false, st1, batch, st->num_sms, s, &fin)); }
         } else {
-            rc = norm_pass(c, st->by, false, st->bz, false, nullptr, st0, batch, PB, F, c->bott_w, d_style_params, cursor, ACT_RELU, s);
+            rc = norm_pass(c, st->by, false, st->by, false, nullptr, st0, batch, PB, F, c->bott_w, d_style_params, cursor, ACT_RELU, s);
             if (rc) return rc;
-            record_tap(c, name + "/conv0/cin", st->bz, px * F, true, s);
-            { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(st->by, false, st1, batch, st->num_sms, s)); }
+            record_tap(c, name + "/conv0/cin", st->by, px * F, true, s);
+            { LaunchScope ls(c, s, "conv3x3_umma"); RST_CUDA(c, st->trunk[2 * b + 1].run(z, false, st1, batch, st->num_sms, s)); }
         }
-        record_tap(c, name + "/conv1/relu", y1, px * F, true, s);
-        rc = norm_pass(c, y1, false, st->bx, false, b == 0 ? nullptr : st->bx, st1, batch, PB, F, c->bott_w, d_style_params,
+        record_tap(c, name + "/conv1/relu", z, px * F, true, s);
+        rc = norm_pass(c, z, false, z, false, b == 0 ? nullptr : skip, st1, batch, PB, F, c->bott_w, d_style_params,
                        cursor + 2 * F, ACT_NONE, s);
         if (rc) return rc;
-        record_tap(c, name, st->bx, px * F, true, s);
+        record_tap(c, name, z, px * F, true, s);
         cursor += 4 * F;
     }
 
@@ -575,7 +577,7 @@ int bf16_transfer_forward(rst_ctx* c, const void* d_content, int content_dtype, 
         float* t1 = c->act[1];
         {
             LaunchScope ls(c, s, "convert");
-            RST_CUDA(c, launch_bf16_to_f32_slice(st->bx, x, px, F, F, s));
+            RST_CUDA(c, launch_bf16_to_f32_slice(st->bz, x, px, F, F, s));
         }
         if (out_dtype != RST_DTYPE_F32)
             return fail(c, RST_ERR_UNSUPPORTED, "uint8 output needs the tensor-core decoder (2 expand blocks, 128 filters, width % 64 == 0)");
@@ -589,17 +591,17 @@ int bf16_transfer_forward(rst_ctx* c, const void* d_content, int content_dtype, 
     double* se2 = st->stats + (size_t)12 * st->stats_stride;
     { LaunchScope ls(c, s, "convt_umma"); RST_CUDA(c, st->e0.run(st->ye0, false, se0, batch, st->num_sms, s)); }
     record_tap(c, L0.name + "/conv", st->ye0, (int64_t)batch * L0.ho * L0.wo * L0.co, true, s);
-    rc = norm_pass(c, st->ye0, false, st->ze0, false, nullptr, se0, batch, L0.ho * L0.wo, L0.co, L0.wo, d_style_params, cursor,
+    rc = norm_pass(c, st->ye0, false, st->ye0, false, nullptr, se0, batch, L0.ho * L0.wo, L0.co, L0.wo, d_style_params, cursor,
                    ACT_RELU, s);
     if (rc) return rc;
-    record_tap(c, L0.name, st->ze0, (int64_t)batch * L0.ho * L0.wo * L0.co, true, s);
+    record_tap(c, L0.name, st->ye0, (int64_t)batch * L0.ho * L0.wo * L0.co, true, s);
     cursor += 2 * L0.co;
     { LaunchScope ls(c, s, "convt_umma"); RST_CUDA(c, st->e1.run(st->ye1, false, se1, batch, st->num_sms, s)); }
     record_tap(c, L1.name + "/conv", st->ye1, (int64_t)batch * L1.ho * L1.wo * L1.co, true, s);
-    rc = norm_pass(c, st->ye1, false, st->ze1, false, nullptr, se1, batch, L1.ho * L1.wo, L1.co, L1.wo, d_style_params, cursor,
+    rc = norm_pass(c, st->ye1, false, st->ye1, false, nullptr, se1, batch, L1.ho * L1.wo, L1.co, L1.wo, d_style_params, cursor,
                    ACT_RELU, s);
     if (rc) return rc;
-    record_tap(c, L1.name, st->ze1, (int64_t)batch * L1.ho * L1.wo * L1.co, true, s);
+    record_tap(c, L1.name, st->ye1, (int64_t)batch * L1.ho * L1.wo * L1.co, true, s);
     cursor += 2 * L1.co;
     { LaunchScope ls(c, s, "head_umma"); RST_CUDA(c, st->head.run(st->ylast, true, se2, batch, st->num_sms, s)); }
     record_tap(c, L2.name + "/conv", st->ylast, (int64_t)batch * L2.ho * L2.wo * 3, false, s);

@@ -151,7 +151,8 @@ def test_transfer_bf16_full_resolution(cuda_device):
 
 @pytest.mark.parametrize("h,w,batch", [(60, 100, 3), (64, 128, 2), (120, 200, 5)])
 def test_fused_first_norm_matches_the_separate_pass(cuda_device, monkeypatch, h, w, batch):
-    """The first instance norm of every residual block is applied by the loader warps of the consuming 2-CTA conv kernel
+    """Opt-in variant (RST_FUSE_NORM=1; measured slower than conv + in-place pass on B200, profiles/r02_03_fused_norm.md):
+    the first instance norm of every residual block is applied by the loader warps of the consuming 2-CTA conv kernel
     (halo_gemm2.cu, fuse = 1: global -> registers -> relu(a*x+b) -> swizzled shared memory) instead of a separate pass.
     Both paths compute the same fp32 expression and round once to bf16, so they agree up to the atomics order of the
     statistics.  Geometries: ragged tile edges (bottleneck 15x25, 30x50), an odd tile count (phantom tile of the last pair),
@@ -163,7 +164,7 @@ def test_fused_first_norm_matches_the_separate_pass(cuda_device, monkeypatch, h,
     params = np.random.default_rng(7).uniform(0.3, 1.2, (batch, 1, spec.num_style_parameters)).astype(np.float32)
     outs = {}
     for mode in ("1", "0"):
-        monkeypatch.setenv("RST_FUSE_NORM", mode)           # read when the weights are committed
+        monkeypatch.setenv("RST_FUSE_NORM", mode)           # opt-in switch, read when the weights are committed
         outs[mode], _, launches = run_bf16(shape_in, shape_out, h // 4, 128, 1, weights, content, params)
         outs[mode + "_launches"] = launches
     assert outs["0_launches"] - outs["1_launches"] == 5     # five passes gone
