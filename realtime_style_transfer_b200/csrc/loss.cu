@@ -13,6 +13,7 @@
 
 #include "rst_internal.cuh"
 #include "halo_gemm.cuh"
+#include "train_kernels.cuh"
 #include <memory>
 
 using namespace rst;
@@ -325,6 +326,21 @@ static ConvF32 vgg_conv(rst_loss* c, int i, const float* x, float* y, int batch)
     return p;
 }
 
+// Gram matrix of one style tap (styleLoss.py:11-18).  On the tensor cores (gram_tf32.cu) whenever the convolutions are: split
+// tf32 with RST_PRECISION_FP32 math, plain tf32 operands with RST_PRECISION_TF32; the scratch of the split convolutions is free
+// between two layers and large enough (2 x the largest conv input >= the tap).
+static int gram(rst_loss* c, const float* y, float* out, int B, int P, int C, cudaStream_t s) {
+    const bool split = c->math == RST_PRECISION_FP32;
+    if (c->fwd[1] && gram_tf32_supported(C) && (!split || gram_tf32_scratch_floats(B, P, C) <= c->split_scratch_floats)) {
+        std::string err;
+        cudaError_t e = launch_gram_tf32(y, out, c->split_scratch, B, P, C, split, c->num_sms, s, &err);
+        if (e != cudaSuccess) return lfail(c, RST_ERR_CUDA, "gram (tensor cores): " + (err.empty() ? std::string(cudaGetErrorString(e)) : err));
+        return RST_OK;
+    }
+    LCUDA(c, launch_gram_f32(y, out, B, P, C, s));
+    return RST_OK;
+}
+
 // Runs VGG16 on `img` (B,H,W,3 in [0,1]).  keep: write every activation into c->act/pool (prediction pass);
 // otherwise ping-pong through the scratch buffers and only hand the tap tensors to `on_tap`.
 template <typename F>
@@ -386,7 +402,7 @@ extern "C" int rst_loss_forward(rst_loss* c, const float* d_pred, const float* d
     // style image: the four Gram matrices
     rc = vgg_forward(c, d_gt_style, B, false, s, [&](int i, float* y) -> int {
         if (kVgg[i].style_idx >= 0) {
-            LCUDA(c, launch_gram_f32(y, c->gram_style[kVgg[i].style_idx], B, c->lh[i] * c->lw[i], kVgg[i].co, s));
+            if (int grc = gram(c, y, c->gram_style[kVgg[i].style_idx], B, c->lh[i] * c->lw[i], kVgg[i].co, s)) return grc;
             c->launches++;
         }
         return RST_OK;
@@ -396,7 +412,7 @@ extern "C" int rst_loss_forward(rst_loss* c, const float* d_pred, const float* d
     rc = vgg_forward(c, d_pred, B, true, s, [&](int i, float* y) -> int {
         if (kVgg[i].style_idx >= 0) {
             const int l = kVgg[i].style_idx, C = kVgg[i].co;
-            LCUDA(c, launch_gram_f32(y, c->gram_pred[l], B, c->lh[i] * c->lw[i], C, s));
+            if (int grc = gram(c, y, c->gram_pred[l], B, c->lh[i] * c->lw[i], C, s)) return grc;
             sqdiff_kernel<<<dim3(64, B), 256, 0, s>>>(c->gram_pred[l], c->gram_style[l], style4 + (size_t)l * B, (long long)C * C);
             c->launches += 2;
         }

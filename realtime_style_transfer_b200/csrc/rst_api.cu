@@ -4,6 +4,7 @@
 #include <cstring>
 #include <tuple>
 
+#include "train_kernels.cuh"
 #include "rst_ctx.h"
 #include "halo_gemm.cuh"
 
@@ -1191,6 +1192,22 @@ extern "C" int rst_op_apply_style_weights(const float* d_weights, const float* d
 
 extern "C" int rst_op_gram(const float* d_x, float* d_gram, int batch, int h, int w, int c, void* stream) {
     if (!d_x || !d_gram) return op_fail(RST_ERR_INVALID, "rst_op_gram: null tensor");
-    OP_CUDA(launch_gram_f32(d_x, d_gram, batch, h * w, c, (cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (gram_tf32_supported(c) && !ab_env("RST_GRAM_CUDA_CORE")) {
+        // tensor cores, error-compensated split tf32 (fp32-level accuracy); a stand-alone operator may allocate its scratch
+        std::string err;
+        if (!umma_init(&err)) return op_fail(RST_ERR_CUDA, err);
+        float* scratch = nullptr;
+        OP_CUDA(cudaMalloc(&scratch, gram_tf32_scratch_floats(batch, h * w, c) * sizeof(float)));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = launch_gram_tf32(d_x, d_gram, scratch, batch, h * w, c, true, sms, s, &err);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(scratch);
+        if (e != cudaSuccess) return op_fail(RST_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
+        return RST_OK;
+    }
+    OP_CUDA(launch_gram_f32(d_x, d_gram, batch, h * w, c, s));
     return RST_OK;
 }

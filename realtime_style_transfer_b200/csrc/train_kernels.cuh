@@ -21,6 +21,12 @@ cudaError_t launch_wgrad_f32(const WgradF32& p, cudaStream_t s);
 // tensor-core (kind::tf32, MN-major operands) weight gradient of a 3x3 stride-1 'same' convolution 128 -> 128 (wgrad_tf32.cu);
 // split = error-compensated (fp32-level accuracy), needs wgrad_tf32_scratch_floats() floats of scratch
 size_t wgrad_tf32_scratch_floats(int B, int H, int W);
+// tensor-core Gram matrix (gram_tf32.cu): x (B, P, C) fp32 -> gram (B, C, C) = x^T x / P per sample, C = 64 or a multiple of 128;
+// split = error-compensated tf32 (fp32-level accuracy), needs gram_tf32_scratch_floats() floats of scratch
+bool gram_tf32_supported(int C);
+size_t gram_tf32_scratch_floats(int B, int P, int C);
+cudaError_t launch_gram_tf32(const float* x, float* gram, float* lo_scratch, int B, int P, int C, bool split, int num_sms,
+                             cudaStream_t s, std::string* err);
 cudaError_t launch_wgrad_tf32(const float* x, const float* g, float* dw, float* lo_scratch, int B, int H, int W, bool split,
                               int num_sms, cudaStream_t s, std::string* err);
 

@@ -196,14 +196,41 @@ def test_op_cin(cuda_device, styles):
     assert np.abs(d_y.cpu().numpy() - ref.numpy()).max() < 2e-5
 
 
-@pytest.mark.parametrize("shape", [(2, 24, 40, 64), (1, 30, 61, 128), (2, 9, 11, 24)])
+@pytest.mark.parametrize("shape", [
+    (2, 24, 40, 64),       # block1_conv2's channel count: M = 128 with a zero-filled upper half, N = 64
+    (1, 30, 61, 128),      # ragged pixel count (1830 = 57 items + 6 pixels: the last TMA box is zero filled past the sample)
+    (2, 16, 24, 256),      # 2 x 2 channel blocks (off-diagonal blocks load two operands)
+    (1, 15, 30, 512),      # block4_conv3: 4 x 4 blocks
+    (3, 120, 240, 128),    # long reduction (28800 pixels: several accumulator flushes per CTA), three samples
+    (2, 9, 11, 24),        # not a tensor-core shape: generic CUDA-core kernel
+])
 def test_op_gram(cuda_device, shape):
-    """64-multiple channel counts take the register-tiled kernel, others the generic one; ragged pixel counts."""
-    x = np.random.default_rng(0).standard_normal(shape).astype(np.float32)
+    """get_gram_matrix_model (styleLoss.py:11-18).  Channel counts of the VGG16 style taps (64, 128, 256, 512) run on tcgen05
+    (gram_tf32.cu: MN-major kind::tf32 operands, error-compensated hi/lo split = fp32-level accuracy); post-ReLU-like inputs
+    (non-negative, so every Gram entry is a long sum of same-sign products: the worst case for truncating accumulation)."""
+    x = np.abs(np.random.default_rng(0).standard_normal(shape)).astype(np.float32)
     ref = O.gram_matrix(torch.as_tensor(x, dtype=torch.float64)).numpy()
     got = styleLoss.gram_matrix(x)
     assert got.shape == ref.shape
-    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+    rel = np.abs(got - ref).max() / np.abs(ref).max()
+    print(f"gram {shape}: max rel err {rel:.2e}")
+    assert rel < 1e-5
+    assert np.abs(got - got.transpose(0, 2, 1)).max() / np.abs(ref).max() < 1e-5
+    # second restatement (numpy einsum in fp64) on the same input
+    from oracle import naive_np as NP
+    assert np.abs(NP.gram(x) - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_op_gram_tensor_core_matches_cuda_core(cuda_device, monkeypatch):
+    """Same input through the tcgen05 kernel and through the CUDA-core kernel it replaces (RST_GRAM_CUDA_CORE=1)."""
+    x = np.abs(np.random.default_rng(1).standard_normal((2, 60, 120, 256))).astype(np.float32)
+    tc = styleLoss.gram_matrix(x)
+    monkeypatch.setenv("RST_GRAM_CUDA_CORE", "1")
+    cc = styleLoss.gram_matrix(x)
+    ref = O.gram_matrix(torch.as_tensor(x, dtype=torch.float64)).numpy()
+    e_tc, e_cc = np.abs(tc - ref).max() / np.abs(ref).max(), np.abs(cc - ref).max() / np.abs(ref).max()
+    print(f"gram 256 channels: tensor cores {e_tc:.2e}, CUDA cores {e_cc:.2e}")
+    assert e_tc < 1e-5 and e_cc < 1e-5
 
 
 # ---- whole transfer network ---------------------------------------------------------------------

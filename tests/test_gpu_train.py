@@ -438,27 +438,33 @@ def test_data_parallel_in_process_sum_of_shard_gradients(cuda_device):
     spec, tw, pw, vgg, content, style, gt = _setup("DUMMY", 4, seed=9)
     shards = [(content[:2], style[:2], gt[:2]), (content[2:], style[2:], gt[2:])]
     trainers = [_trainer(_native.EXTRACTOR_DUMMY, 2, tw, pw, vgg) for _ in shards]
-    flats = []
+    weights = {k: np.asarray(v, np.float64) for k, v in {**tw, **pw}.items() if not k.endswith(("moving_mean", "moving_variance"))}
+    flats, shard_grads = [], []
     for tr, (c, s, g) in zip(trainers, shards):
         _step(tr, cuda_device, c, s, g)
         flats.append(torch.as_tensor(_DeviceArrayView(tr.gradients_ptr(), tr.num_gradient_elements), device=cuda_device))
+        shard_grads.append({k: tr.read_gradient(k, v.shape).astype(np.float64) for k, v in weights.items()})
     total = flats[0] + flats[1]
     for f in flats:
         f.copy_(total)
     torch.cuda.synchronize()
-    weights = {k: np.asarray(v, np.float64) for k, v in {**tw, **pw}.items() if not k.endswith(("moving_mean", "moving_variance"))}
     ref_sum = None
     for c, s, g in shards:
         _, grads, _ = O.training_forward_backward(spec, tw, "DUMMY", pw, vgg, c, s, g)
         ref_sum = grads if ref_sum is None else {k: ref_sum[k] + grads[k] for k in grads}
-    # the summed native gradient is the oracle's summed gradient (end-to-end bar of this file)
+    # what both replicas now hold is the sum of the shard gradients, variable by variable ...
     for k, v in weights.items():
-        got = trainers[0].read_gradient(k, v.shape)
-        ref = ref_sum[k].numpy()
-        norm = np.sqrt((ref ** 2).sum())
-        if norm > 1e-9:
-            # end to end the loss gradient is chaotic at the 1e-2 level (module docstring); the sum must still be the sum
-            assert np.sqrt(((got - ref) ** 2).sum()) / norm < 5 * GRAD_TOL, k
+        got = trainers[1].read_gradient(k, v.shape).astype(np.float64)
+        want = shard_grads[0][k] + shard_grads[1][k]
+        assert np.abs(got - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-30), k
+    # ... and that sum is the oracle's summed gradient.  End to end the loss gradient is chaotic at the 1e-2 level per variable
+    # (module docstring), so the whole vector is compared: direction and length.
+    flat_got = np.concatenate([trainers[0].read_gradient(k, v.shape).ravel().astype(np.float64) for k, v in weights.items()])
+    flat_ref = np.concatenate([ref_sum[k].numpy().ravel() for k in weights])
+    cos = float((flat_got * flat_ref).sum() / np.sqrt((flat_got ** 2).sum() * (flat_ref ** 2).sum()))
+    ratio = float(np.sqrt((flat_got ** 2).sum() / (flat_ref ** 2).sum()))
+    print("summed gradient vs oracle: cosine", cos, "norm ratio", ratio)
+    assert cos > 0.999 and abs(ratio - 1) < 2e-2
     native_grads = {k: torch.tensor(trainers[0].read_gradient(k, v.shape)) for k, v in weights.items()}
     expect, _ = O.rmsprop_update(weights, native_grads, {k: np.zeros_like(v) for k, v in weights.items()})
     for tr in trainers:
