@@ -94,34 +94,6 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
-def bind_to_gpu_numa_node(local_rank: int):
-    """Pin this process (and the pinned host buffers it allocates next) to the NUMA node of its GPU, so that the H2D / D2H
-    copies of 8 ranks do not cross the socket interconnect.  Best effort: silently skipped when sysfs does not tell."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:                 # nvml prints an 8-digit domain, sysfs a 4-digit one
-            bus = bus[4:]
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
-        if node < 0:
-            return {"node": None}
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-        return {"node": node, "cpus": len(cpus)}
-    except Exception as e:                              # noqa: BLE001 - best effort
-        return {"node": None, "why": type(e).__name__}
-
-
 def synthetic_inputs(cfg, batch, seed):
     """Channel-wise synthetic G-buffer in ShapeConfig.channels order."""
     rng = np.random.default_rng(seed)
@@ -345,11 +317,12 @@ def main():
         run_reference(args, rank, world)
         return
 
-    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     import torch
     import torch.distributed as dist
     from realtime_style_transfer_b200 import _native, _plan
     from realtime_style_transfer_b200 import distributed as rdist
+    torch.cuda.set_device(local_rank)
+    numa = rdist.bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     from realtime_style_transfer_b200._plan import PredictorPlan, TransferPlan
     from realtime_style_transfer_b200.shape_config import ShapeConfig
 

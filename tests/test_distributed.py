@@ -92,3 +92,14 @@ def test_two_rank_gradient_allreduce_is_a_sum():
 def test_allreduce_is_a_noop_without_a_process_group():
     g = torch.ones(4)
     assert D.allreduce_sum_(g).tolist() == [1.0] * 4
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """bind_to_gpu_numa_node never raises and never leaves the process with an empty CPU set (no GPU / no NVML here)."""
+    import os
+    from realtime_style_transfer_b200 import distributed as D
+    before = os.sched_getaffinity(0)
+    info = D.bind_to_gpu_numa_node(0, measure=False)
+    assert isinstance(info, dict) and "method" in info
+    assert os.sched_getaffinity(0) and os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
