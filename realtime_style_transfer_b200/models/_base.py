@@ -137,6 +137,16 @@ class NativeModel:
     def _all_variables(self) -> Dict[str, np.ndarray]:
         return self._variables
 
+    def save(self, filepath, include_optimizer=False, save_format=None, **kwargs):
+        """Keras ``Model.save`` as the reference's export script uses it (save_using_checkpoint.py:76-103).  ``*.onnx`` writes
+        the graph + weights as ONNX (what that script produces through tf2onnx); a TensorFlow SavedModel cannot be written
+        without TensorFlow -- use ``save_weights`` for a TF2 checkpoint of the variables."""
+        path = str(filepath)
+        if path.endswith(".onnx") or save_format == "onnx":
+            from ..export import export_onnx
+            return export_onnx(self, path if path.endswith(".onnx") else path + ".onnx")
+        raise NotImplementedError("SavedModel export needs TensorFlow; supported: model.save('<name>.onnx') and save_weights()")
+
     def load_weights(self, filepath):
         """``.npz`` written by save_weights, or a TF2 object-based checkpoint prefix
         (tracing/checkpoint.py:37 writes those); returns a status object like TF's."""
