@@ -311,3 +311,23 @@ def test_inference_model_uploads_once_and_never_runs_stale(monkeypatch):
     n = _StubCtx.uploads
     models.inference.predict(x)
     assert _StubCtx.uploads == n
+
+
+def test_half_exr_planes_stay_float16_for_the_reduced_byte_ingest(tmp_path):
+    """load_unreal_hdr_screenshot(dtype=float16): HALF planes are returned as stored (same values as the float32 path, half the
+    bytes) -- the array the float16 entry points upload; FLOAT planes are narrowed only on request."""
+    from realtime_style_transfer_b200.dataloaders import exr, hdrScreenshots
+    rng = np.random.default_rng(3)
+    h, w = 20, 36
+    cfg = ShapeConfig(hdr=True, num_styles=1, num_channels=17)
+    for name, n in cfg.channels:
+        data = rng.uniform(0, 4, (h, w, n)).astype(np.float32)
+        exr.save(tmp_path / f"shot_{name}.exr", {c: data[..., i] for i, c in enumerate("RGB"[:n])}, "ZIP", "HALF")
+    (tmp_path / "shot.png").write_bytes(b"")
+    f32, _ = hdrScreenshots.load_unreal_hdr_screenshot(tmp_path / "shot.png", cfg.channels)
+    f16, _ = hdrScreenshots.load_unreal_hdr_screenshot(tmp_path / "shot.png", cfg.channels, dtype=np.float16)
+    assert f32.dtype == np.float32 and f16.dtype == np.float16 and f16.shape == f32.shape == (h, w, 17)
+    assert np.array_equal(f16.astype(np.float32), f32)             # HALF -> float32 is exact: identical values
+    assert exr.load(tmp_path / "shot_FinalImage.exr", keep_half=True).channel("R").dtype == np.float16
+    batches = list(hdrScreenshots.iter_unreal_hdr_screenshots(tmp_path, cfg.channels, batch=2, dtype=np.float16))
+    assert len(batches) == 1 and batches[0].shape == (1, h, w, 17) and batches[0].dtype == np.float16
