@@ -390,3 +390,44 @@ def test_inference_model_through_reference_surface(cuda_device, styles):
     with pytest.raises(ValueError):
         models.transfer.predict({"content": element["content"][:, :32], "style_params": sp})
     models.inference.close(); models.transfer.close(); models.style_predictor.close()
+
+
+def test_reference_inference_model_test_at_its_own_size(cuda_device, tmp_path):
+    """realtime_style_transfer/models/styleTransferInferenceModelTest.py at the reference's OWN sizes (the largest geometry the
+    reference exercises): content (480,960,3), output (1920,3840,3) = four expand blocks, two styles with a (1920,3840,1) weight
+    map, DUMMY predictor.  test_output_shape_matches, test_inference (all-zero element, as the reference feeds it) and
+    test_save_transfer_model (here: the ONNX file of export.py); plus what the reference could not check -- the numbers,
+    against the oracle on a random element."""
+    num_styles = 2
+    in_shape, out_shape = (480, 960, 3), (1920, 3840, 3)
+    models = styleTransferInferenceModel.make_style_transfer_inference_model(
+        num_styles=num_styles,
+        style_transfer_factory_func=lambda: styleTransfer.create_style_transfer_model(
+            input_shape=in_shape, output_shape=out_shape, bottleneck_res_y=120, bottleneck_num_filters=128,
+            num_styles=num_styles, name="StyleTransferTestModel"),
+        style_predictor_factory_func=lambda n: stylePrediction.create_style_prediction_model(
+            in_shape, stylePrediction.StyleFeatureExtractor.DUMMY, n),
+        name="StyleTransferInferenceTestModel")
+    models.inference.compile()
+    assert models.inference.output_shape == (None,) + out_shape                       # test_output_shape_matches
+    shapes = {"style": (num_styles,) + in_shape, "style_weights": (1920, 3840, num_styles - 1), "content": in_shape}
+    y = models.inference.predict({name: np.zeros((1,) + shape, np.float32) for name, shape in shapes.items()})
+    assert y.shape == (1,) + out_shape and np.isfinite(y).all()                       # test_inference
+    path = models.transfer.save(str(tmp_path / "transfer.onnx"))                      # test_save_transfer_model
+    assert (tmp_path / "transfer.onnx").stat().st_size > 1_000_000 and path.endswith(".onnx")
+    # numbers: random element against the oracle (fp32 path, 1e-4)
+    spec = O.TransferSpec(in_shape, out_shape, 120, 128, num_styles)
+    assert (spec.n_contract, spec.n_expand) == (2, 4)
+    tw = O.init_transfer_weights(spec, seed=8)
+    pw = O.init_predictor_weights("DUMMY", spec.num_style_parameters, seed=9)
+    models.transfer.set_weights(tw)
+    models.style_predictor.set_weights(pw)
+    rng = np.random.default_rng(10)
+    element = {"content": rng.uniform(0, 1, (1,) + in_shape).astype(np.float32),
+               "style": rng.uniform(0, 1, (1, num_styles) + in_shape).astype(np.float32),
+               "style_weights": O.synthetic_style_weights(1, 1920, 3840)}
+    ref = O.inference_forward(spec, tw, "DUMMY", pw, element["content"], element["style"], element["style_weights"]).numpy()
+    got = models.inference.predict(element)
+    print("reference test geometry 480x960x3 -> 1920x3840x3, 2 styles: max abs err", float(np.abs(got - ref).max()))
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= FP32_TOL
+    models.inference.close(); models.transfer.close(); models.style_predictor.close()

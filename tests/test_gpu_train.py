@@ -477,3 +477,52 @@ def test_data_parallel_in_process_sum_of_shard_gradients(cuda_device):
         assert np.abs(a - v).max() < 2e-6 * max(1.0, np.abs(v).max()), k
     for tr in trainers:
         tr.close()
+
+
+def test_reference_training_model_test_at_its_own_size(cuda_device):
+    """realtime_style_transfer/models/styleTransferTrainingModelTest.py::test_training at the reference's own sizes: content
+    (240,480,3), output (480,960,3), bottleneck_res_y 30 (3 contract / 4 expand blocks), 4 bottleneck filters, DUMMY predictor,
+    two all-zero samples batched by 2, one `fit`.  (The reference's StyleLossModelDummy is a test double; the loss model here is
+    the VGG16 one train_network.py uses, without the MiDaS depth term.)  Then the same step against the oracle on random data."""
+    from realtime_style_transfer_b200 import optimizers
+    from realtime_style_transfer_b200.models import styleLoss, stylePrediction, styleTransfer, styleTransferTrainingModel
+    in_shape, out_shape, res_y, filters = (240, 480, 3), (480, 960, 3), 30, 4
+    loss_model = styleLoss.StyleLossModelVGG(out_shape, seed=3)
+    m = styleTransferTrainingModel.make_style_transfer_training_model(
+        style_transfer_factory_func=lambda: styleTransfer.create_style_transfer_model(
+            in_shape, out_shape, res_y, filters, num_styles=1, name="StyleTransferTestModel"),
+        style_predictor_factory_func=lambda n: stylePrediction.create_style_prediction_model(
+            out_shape, stylePrediction.StyleFeatureExtractor.DUMMY, n),
+        style_loss_func_factory_func=lambda: styleLoss.make_style_loss_function(loss_model, out_shape, 1, with_depth_loss=False),
+        name="StyleTransferTrainingTestModel")
+    assert (m.transfer.plan.num_contract_blocks, m.transfer.plan.num_expand_blocks) == (3, 4)
+    m.training.compile(run_eagerly=False, optimizer=optimizers.RMSprop())
+    zeros = ({"content": np.zeros((2,) + in_shape, np.float32), "style": np.zeros((2, 1) + out_shape, np.float32)},
+             {"content": np.zeros((2,) + out_shape, np.float32), "style": np.zeros((2, 1) + out_shape, np.float32)})
+    history = m.training.fit([zeros], verbose=0)
+    assert np.isfinite(history.history["loss"][0])
+    # numbers at this geometry: one step on random data against the oracle's forward (prediction 1e-4, losses 1e-3)
+    spec = O.TransferSpec(in_shape, out_shape, res_y, filters, 1)
+    tw = O.init_transfer_weights(spec, seed=41, trained_like=True)
+    pw = O.init_predictor_weights("DUMMY", spec.num_style_parameters, seed=42)
+    vgg = O.init_vgg16_weights(seed=3)
+    rng = np.random.default_rng(43)
+    content = rng.uniform(0, 1, (2,) + in_shape).astype(np.float32)
+    style = rng.uniform(0, 1, (2,) + out_shape).astype(np.float32)
+    gt = rng.uniform(0, 1, (2,) + out_shape).astype(np.float32)
+    with torch.no_grad():
+        W = {k: torch.as_tensor(v) for k, v in {**tw, **pw}.items()}
+        params = O._predictor_forward_t("DUMMY", W, torch.as_tensor(style), training=True)[:, None, :]
+        ref_pred = O._transfer_forward_t(spec, W, torch.as_tensor(content), params, training=True)
+        ref_losses = O.style_loss_vgg(vgg, ref_pred, gt, torch.as_tensor(style), dtype=torch.float32)
+    tr = _native.NativeTrainer(in_shape=in_shape, out_shape=out_shape, bottleneck_res_y=res_y, bottleneck_num_filters=filters,
+                               max_batch=2, extractor=_native.EXTRACTOR_DUMMY, style_shape=out_shape[:2])
+    tr.model.set_weights({**tw, **pw})
+    tr.loss.set_weights(vgg)
+    losses = _step(tr, cuda_device, content, style, gt)
+    assert np.abs(tr.read_prediction(2) - ref_pred.numpy()).max() <= 1e-4
+    for i, key in enumerate(("loss", "feature_loss", "style_loss", "total_variation_loss")):
+        r = ref_losses[key].numpy()
+        assert np.abs(losses[:, i] - r).max() / np.abs(r).max() <= 1e-3, key
+    tr.close()
+    m.training.close()
