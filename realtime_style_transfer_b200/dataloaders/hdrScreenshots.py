@@ -48,3 +48,37 @@ def iter_unreal_hdr_screenshots(content_image_dir, expected_channels, batch: int
             chunk = []
     if chunk:
         yield np.stack(chunk)
+
+
+def get_unreal_hdr_screenshot_dataset(content_image_dir, expected_channels, shape, **kwargs):
+    """hdrScreenshots.py:32-34: every ``*.png`` stem of the directory."""
+    screenshot_pngs = list(Path(content_image_dir).glob('*.png'))
+    return get_unreal_hdr_screenshot_dataset_from_filepaths(screenshot_pngs, expected_channels, shape, **kwargs)
+
+
+def get_unreal_hdr_screenshot_dataset_from_filepaths(screenshot_png_paths, expected_channels, shape, **kwargs):
+    """hdrScreenshots.py:37-70 without tf.data: a re-iterable of G-buffer frames resized / centre-cropped to ``shape``
+    (``common.preprocess_numpy_image``), shuffled once with ``seed`` if given, unreadable screenshots skipped with a warning.
+    ``dtype=np.float16`` keeps HALF planes narrow when no resize is needed.  (The reference's ``output_shape`` variant also
+    yields the 8-bit screenshot as ground truth; decoding PNG needs an image library that is not part of this package.)"""
+    import logging
+    from .common import FrameDataset, preprocess_numpy_image
+    log = logging.getLogger(__name__)
+    paths = list(screenshot_png_paths)
+    if "seed" in kwargs:
+        import random
+        random.Random(kwargs["seed"]).shuffle(paths)
+    if "output_shape" in kwargs:
+        raise NotImplementedError("ground-truth PNG decoding is outside the accelerated path")
+    dtype = kwargs.get("dtype", np.float32)
+
+    def frames():
+        for png in paths:
+            try:
+                channels, _ = load_unreal_hdr_screenshot(png, expected_channels, dtype)
+                out = preprocess_numpy_image(channels, shape)
+                yield out if out.dtype == np.dtype(dtype) else out.astype(np.float32)
+            except Exception as e:                      # noqa: BLE001 - the reference skips unreadable screenshots too
+                log.warning(f"Skipping f{png} due to an error: {e}")
+
+    return FrameDataset(frames, len(paths))

@@ -331,3 +331,36 @@ def test_half_exr_planes_stay_float16_for_the_reduced_byte_ingest(tmp_path):
     assert exr.load(tmp_path / "shot_FinalImage.exr", keep_half=True).channel("R").dtype == np.float16
     batches = list(hdrScreenshots.iter_unreal_hdr_screenshots(tmp_path, cfg.channels, batch=2, dtype=np.float16))
     assert len(batches) == 1 and batches[0].shape == (1, h, w, 17) and batches[0].dtype == np.float16
+
+
+def test_preprocess_numpy_image_and_screenshot_dataset(tmp_path):
+    """common.preprocess_numpy_image (common.py:45-58): bilinear resize with half-pixel centres + centred crop, against torch's
+    interpolate (same sampling rule); and the dataset factory names of hdrScreenshots.py:32-70."""
+    import torch
+    from realtime_style_transfer_b200.dataloaders import common, exr, hdrScreenshots
+    rng = np.random.default_rng(4)
+    img = rng.uniform(0, 4, (30, 50, 5)).astype(np.float32)
+    for size in ((60, 100), (45, 80), (17, 23), (30, 50)):
+        got = common.resize_bilinear(img, size)
+        ref = torch.nn.functional.interpolate(torch.as_tensor(img).permute(2, 0, 1)[None], size=size, mode="bilinear",
+                                              align_corners=False, antialias=False)[0].permute(1, 2, 0).numpy()
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-5
+    assert np.array_equal(common.preprocess_numpy_image(img, (30, 50, 5)), img)              # already the target shape
+    out = common.preprocess_numpy_image(img, (24, 48, 5))                                     # wider target: scale rows, crop columns
+    assert out.shape == (24, 48, 5)
+    padded = common.resize_with_crop_or_pad(img, 34, 40)
+    assert padded.shape == (34, 40, 5) and np.array_equal(padded[2:32], img[:, 5:45]) and not padded[:2].any()
+    cfg = ShapeConfig(hdr=True, num_styles=1, num_channels=17)
+    for stem in ("a", "b", "c"):
+        for name, n in cfg.channels:
+            data = rng.uniform(0, 1, (20, 40, n)).astype(np.float32)
+            exr.save(tmp_path / f"{stem}_{name}.exr", {c: data[..., i] for i, c in enumerate("RGB"[:n])}, "ZIP", "HALF")
+        (tmp_path / f"{stem}.png").write_bytes(b"")
+    ds = hdrScreenshots.get_unreal_hdr_screenshot_dataset(tmp_path, cfg.channels, (20, 40, 17), seed=1)
+    assert ds.num_samples == 3
+    frames = list(ds.prefetch(5))
+    assert len(frames) == 3 and frames[0].shape == (20, 40, 17) and frames[0].dtype == np.float32
+    batches = list(ds.batch(2))
+    assert [b.shape[0] for b in batches] == [2, 1] and len(list(ds)) == 3                      # re-iterable
+    small = list(hdrScreenshots.get_unreal_hdr_screenshot_dataset(tmp_path, cfg.channels, (10, 20, 17)))
+    assert small[0].shape == (10, 20, 17)
