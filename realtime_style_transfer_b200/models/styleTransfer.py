@@ -188,18 +188,28 @@ class StyleTransferModel(NativeModel):
         return np.concatenate(outs, axis=0) if len(outs) > 1 else outs[0]
 
 
+def _pinned_view(x):
+    """A pinned torch CPU tensor (float32 / float16, contiguous) -> its numpy view, else None."""
+    if hasattr(x, "is_pinned") and x.is_pinned() and x.is_contiguous() and str(x.dtype) in ("torch.float32", "torch.float16"):
+        return x.numpy()
+    return None
+
+
 def _predict_frames(self, batches, pinned: bool = True, output_dtype=np.float32):
     """Streaming variant of the reference's video loop (predict_video_using_checkpoint.py:90-98): yields one
     stylised numpy batch per input dict, with the host<->device copies of neighbouring batches overlapping the forward.
-    Inputs are staged through two pinned buffers.  float16 'content' arrays cross PCIe as float16 and
-    output_dtype=np.uint8 returns trunc(255 * y) (what the reference's loop computes from the float result at :98):
-    together 136 MB instead of 295 MB per batch of 8 frames of rst-960-120-128-17."""
+    numpy inputs are staged through two pinned buffers (one host copy per batch); a 'content' given as a PINNED torch CPU
+    tensor is handed to the DMA engine as it is (no host copy -- the caller must not modify it until its result has been
+    yielded).  float16 'content' crosses PCIe as float16 and output_dtype=np.uint8 returns trunc(255 * y) (what the reference's
+    loop computes from the float result at :98): together 136 MB instead of 295 MB per batch of 8 frames of rst-960-120-128-17."""
     import torch
     slots, pending = [], []
     ctx = None
     for k, element in enumerate(batches):
         content, params, weights = self._check_inputs(element)
-        content, params = as_content(content), as_numpy(params)
+        direct = _pinned_view(content)
+        content = direct if direct is not None else as_content(content)
+        params = as_numpy(params)
         weights = as_numpy(weights) if weights is not None else None
         b = content.shape[0]
         if ctx is None:
@@ -215,18 +225,21 @@ def _predict_frames(self, batches, pinned: bool = True, output_dtype=np.float32)
                               "weights": mk((ctx.cfg.max_batch,) + self.plan.output_shape[:2] + (max(self.plan.num_styles - 1, 1),)),
                               "out": mk((ctx.cfg.max_batch,) + self.plan.output_shape, output_dtype)})
         if len(pending) == 2:
-            t, sl, n = pending.pop(0)
+            t, sl, n, _keep = pending.pop(0)
             ctx.transfer_wait(t)
             yield sl["out"][:n].copy()
         sl = slots[k % 2]
-        sl["content"][:b] = content
+        if direct is None or content.dtype != sl["content"].dtype:
+            sl["content"][:b] = content
+            src = sl["content"][:b]
+        else:
+            src = content
         sl["params"][:b] = params
         if weights is not None:
             sl["weights"][:b] = weights
-        ticket = ctx.transfer_submit_host(sl["content"][:b], sl["params"][:b], sl["weights"][:b] if weights is not None else None,
-                                          sl["out"][:b])
-        pending.append((ticket, sl, b))
-    for t, sl, n in pending:
+        ticket = ctx.transfer_submit_host(src, sl["params"][:b], sl["weights"][:b] if weights is not None else None, sl["out"][:b])
+        pending.append((ticket, sl, b, element))          # the element keeps a directly-used pinned tensor alive
+    for t, sl, n, _keep in pending:
         ctx.transfer_wait(t)
         yield sl["out"][:n].copy()
 

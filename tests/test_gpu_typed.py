@@ -163,3 +163,25 @@ def test_full_resolution_batch8_typed_round_trip(cuda_device):
     e = np.abs(outs[0][[0, 3]].astype(int) - ref)
     print(f"full-res B=8 fp16->uint8: mean |d|={e.mean():.3f} levels, p99={np.quantile(e, 0.99):.0f}, max={e.max()}")
     assert np.quantile(e, 0.99) <= 6 and np.quantile(e, 0.999) <= 14
+
+
+def test_streaming_takes_pinned_torch_tensors_without_a_host_copy(cuda_device):
+    """predict_frames with 'content' as pinned torch CPU tensors (float16): the DMA reads the caller's buffer directly."""
+    mixed_precision.set_global_policy("mixed_bfloat16")
+    try:
+        model, p = styleTransfer.create_style_transfer_model((64, 128, 17), (64, 128, 3), 16, 128, 1)
+        rng = np.random.default_rng(1)
+        batches, plain = [], []
+        for k in range(4):
+            c = O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=17).channels, seed=10 + k).astype(np.float16)
+            sp = rng.uniform(0.3, 1.2, (2, 1, p)).astype(np.float32)
+            batches.append({"content": torch.from_numpy(c).pin_memory(), "style_params": sp})
+            plain.append({"content": c, "style_params": sp})
+        got = list(model.predict_frames(iter(batches), output_dtype=np.uint8))
+        want = list(model.predict_frames(iter(plain), output_dtype=np.uint8))
+        assert len(got) == 4
+        for g, w in zip(got, want):
+            assert np.abs(g.astype(int) - w.astype(int)).max() <= 2
+        model.close()
+    finally:
+        mixed_precision.set_global_policy("float32")
