@@ -563,6 +563,17 @@ def main():
                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": BATCH * 2 * 120 * 240 * 128 * 2,
                     "peak_source": pk["source"] + ", burst figure (kernel timed alone between events)",
                     "avg_launch_ms": g_ms / g_n, "launches": g_n, "share_of_step": shares.get("conv3x3_umma")}
+        # HBM-bound passes: algorithmic bytes (each tensor read / written once) over the event-timed group
+        px = 120 * 240 * 128 * 2 * BATCH                          # one bottleneck tensor, bytes
+        norm_bytes = 5 * 2 * px + 2 * px + 4 * 3 * px + 2 * px + 2 * (2 * px) + BATCH * 480 * 960 * 3 * (4 + 1)
+        pack_bytes = BATCH * 480 * 960 * (17 * 2 + 32 * 2)
+        hbm = {}
+        for grp, nbytes, what in (("cin_apply_bf16", norm_bytes, "13 conditional-instance-norm passes (style affine, ReLU, skip add, sigmoid / uint8 head)"),
+                                 ("pack_input", pack_bytes, "float16 NHWC-17 -> packed bf16 stem rows")):
+            if grp in groups and groups[grp][0] > 0:
+                gbs = nbytes * args.steps / (groups[grp][0] / 1e3) / 1e9
+                hbm[grp] = {"what": what, "algorithmic_bytes_per_step": int(nbytes), "ms_per_step": groups[grp][0] / args.steps,
+                            "achieved_gbs": gbs, "peak_gbs": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"]}
         tflops = fps * GFLOP_PER_FRAME / 1e3 / world
         whole = {"achieved_tflops": tflops, "regime": f"burst ({ms_max / 1e3:.3f} s timed region)", "peak_burst": pk["bf16_tflops"],
                  "frac_of_burst_bf16": tflops / pk["bf16_tflops"]}
@@ -582,6 +593,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": sampler_main if sampler_main["samples"] else sampler.summary(),
             "roofline": roof,
+            "roofline_hbm_passes": hbm,
             "whole_net": whole,
             "kernel_shares": shares,
             "sum_kernel_ms_per_step": total_group_ms / args.steps,
