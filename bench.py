@@ -408,6 +408,23 @@ def main():
         sustained = {"steps": n_sus, "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / n_sus,
                      "clocks": sampler.summary(t_s0 + 0.5, t_s1)}
 
+    # ---- frame latency at smaller batches (the reference is a per-frame renderer: predict_video_using_checkpoint.py runs
+    # batch_size=1): same context, same device buffers, first b frames ----
+    batch_sweep = {}
+    if not args.no_extras:
+        for b in (1, 2, 4):
+            if b >= BATCH:
+                continue
+
+            def step_b(b=b):
+                ctx.transfer_forward_device(d_content16.data_ptr(), d_params.data_ptr(), None, d_out8.data_ptr(), b, stream.cuda_stream,
+                                            content_dtype=_native.DTYPE_F16, out_dtype=_native.DTYPE_U8)
+            for _ in range(2 + 3):
+                step_b()
+            ms_b = timed_replays(torch, stream, step_b, args.steps, sync_all)
+            ms_b = rdist.max_over_ranks([ms_b], device=dev)[0]
+            batch_sweep[f"batch_{b}"] = {"ms_per_forward": ms_b / args.steps, "frames_per_s": world * b * args.steps / (ms_b / 1e3)}
+
     # ---- end-to-end: HOST buffers through the public streaming entry point (rst_transfer_submit_host_typed / _wait): every
     # step copies its float16 G-buffer batch H2D and its uint8 stylised frames D2H inside the timed region; the copies of
     # neighbouring steps overlap the forward (two staging slots), as in a video loop with prefetch.
@@ -614,6 +631,8 @@ def main():
                                "h2d_bytes_per_step": fp32_io["h2d"], "d2h_bytes_per_step": fp32_io["d2h"],
                                "api": "rst_transfer_forward / rst_transfer_submit_host (float32 in, float32 out: the drop-in default)",
                                "uint8_path_vs_trunc255_of_float_path_max_levels": fp32_io["uint8_vs_float_levels_max"]}
+        if batch_sweep:
+            line["batch_sweep"] = batch_sweep
         if config_recs:
             line["configs"] = config_recs
         if training:
