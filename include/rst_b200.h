@@ -77,6 +77,11 @@ int rst_destroy(rst_ctx* ctx);
 /* ctx may be NULL: returns the message of the last failed rst_create on this thread. */
 const char* rst_last_error(const rst_ctx* ctx);
 
+/* Host utility: crc32c (Castagnoli) of a host buffer, the checksum of TensorFlow's tensor bundles (un-vendored third party:
+ * tensorflow/core/lib/hash/crc32c; callers mask it as LevelDB does).  Used by checkpoint.py, which reads and writes the
+ * reference's checkpoint format (tracing/checkpoint.py:18-37) without TensorFlow. */
+uint32_t rst_host_crc32c(const void* h_data, uint64_t num_bytes);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 /* num_style_parameters returned by create_style_transfer_model (styleTransfer.py:278-279, :332). */
 int rst_num_style_params(const rst_ctx* ctx);

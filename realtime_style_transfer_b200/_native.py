@@ -62,6 +62,7 @@ _vp = C.c_void_p
 # name -> (restype, argtypes); every symbol include/rst_b200.h declares
 SIGNATURES = {
     "rst_version": (C.c_char_p, []),
+    "rst_host_crc32c": (C.c_uint32, [_vp, C.c_uint64]),
     "rst_create": (C.c_int, [C.POINTER(RstConfig), C.c_int, C.POINTER(_vp)]),
     "rst_destroy": (C.c_int, [_vp]),
     "rst_last_error": (C.c_char_p, [_vp]),

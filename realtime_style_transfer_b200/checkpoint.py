@@ -12,8 +12,13 @@ is a *tensor bundle*:
                                  (e.g. ``layer_with_weights-3/.../kernel/.ATTRIBUTES/VARIABLE_VALUE``)
 
 Both the SSTable and the two protos are parsed by hand here (a few dozen lines each; TF's bundle writer never compresses).
-``write_checkpoint`` produces the same format and is what the tests use to build bundles (no checkpoint of the reference
-is available offline): parity with a real TensorFlow-written file is therefore unpinned.
+``write_checkpoint`` produces the same container: every tensor carries its masked crc32c (``rst_host_crc32c``), the object
+graph has children edges (root -> ``layer_with_weights-i`` -> ``v``) that spell the keys and the Keras ``full_name`` of every
+variable.  What it can NOT reproduce without Keras is the reference model's own trackable object tree (nested functional
+models), so a bundle written here is meant for this package's ``load_weights`` and for name-based readers
+(``tf.train.load_checkpoint(prefix).get_tensor(key)``), not for Keras' object-based ``model.load_weights``.
+No checkpoint of the reference is available offline (SURVEY.md F6): parity with a real TensorFlow-written file is unpinned;
+the reader is additionally tested against a bundle assembled by an independent encoder (tests/test_checkpoint.py).
 """
 from __future__ import annotations
 
@@ -86,6 +91,10 @@ def _field(fn: int, wt: int, payload: bytes) -> bytes:
     return _put_varint((fn << 3) | wt) + payload
 
 
+def _len_delimited(payload: bytes) -> bytes:
+    return _put_varint(len(payload)) + payload
+
+
 # ---- crc32c (Castagnoli), masked as LevelDB / TF do -----------------------------------------------------------------
 _CRC_TABLE = []
 for _i in range(256):
@@ -95,11 +104,29 @@ for _i in range(256):
     _CRC_TABLE.append(_c)
 
 
-def crc32c(data: bytes) -> int:
+def _crc32c_python(data: bytes) -> int:
     c = 0xFFFFFFFF
     for b in data:
         c = _CRC_TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
+
+
+def crc32c(data) -> int:
+    """bytes / bytearray / memoryview / contiguous ndarray.  Large buffers go through the library's slicing-by-8 routine
+    (rst_host_crc32c, host code: needs no GPU); the table loop above is the fallback and the cross-check."""
+    if isinstance(data, np.ndarray):
+        data = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    n = len(data)
+    if n >= 4096:
+        try:
+            from ._native import load_library
+            import ctypes as C
+            lib = load_library()
+            buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+            return int(lib.rst_host_crc32c(buf.ctypes.data_as(C.c_void_p), n))
+        except Exception:                               # noqa: BLE001 - library not built: fall back to the Python loop
+            pass
+    return _crc32c_python(bytes(data))
 
 
 def _mask(crc: int) -> int:
@@ -167,7 +194,7 @@ def read_index(prefix: str) -> Dict[str, dict]:
     for k, v in table.items():
         if k == b"":
             continue                                    # BundleHeaderProto
-        e = {"dtype": 0, "shape": (), "shard": 0, "offset": 0, "size": 0}
+        e = {"dtype": 0, "shape": (), "shard": 0, "offset": 0, "size": 0, "crc32c": 0}
         for fn, _wt, val in _parse_fields(v):
             if fn == 1:
                 e["dtype"] = val
@@ -179,6 +206,8 @@ def read_index(prefix: str) -> Dict[str, dict]:
                 e["offset"] = val
             elif fn == 5:
                 e["size"] = val
+            elif fn == 6:
+                e["crc32c"] = val
         out[k.decode()] = e
     return out
 
@@ -205,8 +234,9 @@ def _parse_object_graph(buf: bytes) -> Dict[str, str]:
     return out
 
 
-def read_checkpoint_variables(prefix: str) -> Dict[str, dict]:
-    """Reads every numeric variable of a TF2 checkpoint: checkpoint_key -> {'value': ndarray, 'full_name': str}."""
+def read_checkpoint_variables(prefix: str, verify_tensors: bool = False) -> Dict[str, dict]:
+    """Reads every numeric variable of a TF2 checkpoint: checkpoint_key -> {'value': ndarray, 'full_name': str}.
+    verify_tensors: also check every tensor against the masked crc32c of its BundleEntryProto (as TensorFlow's reader does)."""
     prefix = str(prefix)
     if prefix.endswith(".index"):
         prefix = prefix[:-6]
@@ -242,7 +272,10 @@ def read_checkpoint_variables(prefix: str) -> Dict[str, dict]:
             continue
         dt = np.dtype(_DTYPES[e["dtype"]])
         buf = shard_bytes(e["shard"])[e["offset"]:e["offset"] + e["size"]]
-        out[key] = {"value": np.frombuffer(bytes(buf), dtype=dt).reshape(e["shape"]).copy(), "full_name": names.get(key, "")}
+        value = np.frombuffer(bytes(buf), dtype=dt).reshape(e["shape"]).copy()
+        if verify_tensors and _mask(crc32c(value)) != e["crc32c"]:
+            raise ValueError(f"checkpoint tensor {key} fails its crc32c check")
+        out[key] = {"value": value, "full_name": names.get(key, "")}
     return out
 
 
@@ -363,7 +396,8 @@ def write_checkpoint(prefix: str, variables: Dict[str, np.ndarray], extra: Dict[
     bn_index: Dict[str, int] = {}
     data = bytearray()
     entries: Dict[bytes, bytes] = {}
-    graph_nodes = [b""]                                         # node 0: the root object (no attributes)
+    graph_nodes = [b""]                                         # node 0: the root object, its children are filled in below
+    root_children: List[bytes] = []
 
     def add_tensor(key: str, arr: np.ndarray, dtype_code: int):
         raw = arr.tobytes()
@@ -371,10 +405,7 @@ def write_checkpoint(prefix: str, variables: Dict[str, np.ndarray], extra: Dict[
                          (_field(1, 0, _put_varint(int(s))) for s in arr.shape))
         entry = (_field(1, 0, _put_varint(dtype_code)) + _field(2, 2, _put_varint(len(shape)) + shape) +
                  _field(4, 0, _put_varint(len(data))) + _field(5, 0, _put_varint(len(raw))) +
-                 # per-tensor crc32c: computed for tensors up to 1 MiB (pure-Python CRC), 0 above (this reader does not
-                 # verify tensor CRCs; TensorFlow itself would reject such an entry, so this writer is a fixture / exchange
-                 # format for this package, not an exporter)
-                 _field(6, 5, struct.pack("<I", _mask(crc32c(raw)) if len(raw) <= (1 << 20) else 0)))
+                 _field(6, 5, struct.pack("<I", _mask(crc32c(raw)))))         # masked crc32c of the tensor bytes, every tensor
         entries[key.encode()] = entry
         data.extend(raw)
 
@@ -384,9 +415,15 @@ def write_checkpoint(prefix: str, variables: Dict[str, np.ndarray], extra: Dict[
         add_tensor(key, np.ascontiguousarray(arr, np.float32), _DT_FLOAT)
         attr = (_field(1, 2, _put_varint(14) + b"VARIABLE_VALUE") + _field(2, 2, _put_varint(len(full)) + full.encode()) +
                 _field(3, 2, _put_varint(len(key)) + key.encode()))
+        # object graph: root --layer_with_weights-i--> holder --v--> variable node (children edges as TensorFlow writes them,
+        # so the key is the path of edge names from the root followed by the attribute suffix)
+        holder, variable = len(graph_nodes), len(graph_nodes) + 1
+        root_children.append(_field(1, 2, _len_delimited(_field(1, 0, _put_varint(holder)) + _field(2, 2, _len_delimited(f"layer_with_weights-{i}".encode())))))
+        graph_nodes.append(_field(1, 2, _len_delimited(_field(1, 0, _put_varint(variable)) + _field(2, 2, _len_delimited(b"v")))))
         graph_nodes.append(_field(2, 2, _put_varint(len(attr)) + attr))
     for key, arr in (extra or {}).items():
         add_tensor(key, np.ascontiguousarray(arr, np.float32), _DT_FLOAT)
+    graph_nodes[0] = b"".join(root_children)
     graph = b"".join(_field(1, 2, _put_varint(len(n)) + n) for n in graph_nodes)
     # scalar DT_STRING tensor: [varint length][masked crc32c of the length bytes][bytes]
     length = _put_varint(len(graph))

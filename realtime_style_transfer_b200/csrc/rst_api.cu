@@ -211,7 +211,36 @@ static int build_plan(rst_ctx* c) {
 // ------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------
-extern "C" const char* rst_version(void) { return "rst_b200 0.1 (sm_100a)"; }
+extern "C" const char* rst_version(void) { return "rst_b200 0.2 (sm_100a)"; }
+
+// crc32c (Castagnoli, reflected 0x82F63B78) of a host buffer, slicing-by-8: the checksum of TensorFlow's tensor bundles
+// (tensorflow/core/lib/hash/crc32c) for the checkpoint reader / writer, whose pure-Python loop is too slow for 100 MB shards.
+extern "C" uint32_t rst_host_crc32c(const void* data, uint64_t n) {
+    static uint32_t T[8][256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+            T[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFF];
+        ready = true;
+    }
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint32_t c = 0xFFFFFFFFu;
+    while (n >= 8) {
+        uint32_t lo, hi;
+        memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4);
+        lo ^= c;
+        c = T[7][lo & 0xFF] ^ T[6][(lo >> 8) & 0xFF] ^ T[5][(lo >> 16) & 0xFF] ^ T[4][lo >> 24] ^
+            T[3][hi & 0xFF] ^ T[2][(hi >> 8) & 0xFF] ^ T[1][(hi >> 16) & 0xFF] ^ T[0][hi >> 24];
+        p += 8; n -= 8;
+    }
+    while (n--) c = T[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
 
 static void free_ctx(rst_ctx* c) {
     if (!c) return;

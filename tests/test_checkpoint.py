@@ -212,3 +212,39 @@ def test_reads_a_hand_assembled_tf2_bundle(tmp_path):
     np.testing.assert_array_equal(model.weights["contract_start/bn/gamma"], gamma)
     assert sorted(status.matched) == ["contract_start/bn/gamma", "contract_start/conv/bias", "contract_start/conv/kernel"]
     assert any("OPTIMIZER_SLOT" in k for k in status.unused) or all("rms" not in m for m in status.matched)
+
+
+def test_native_crc32c_and_tensor_verification(tmp_path):
+    """rst_host_crc32c (slicing-by-8 in the library, host code) against the RFC 3720 vectors and the Python table loop; every
+    tensor of a written bundle carries its masked crc32c (also above 1 MiB) and read_checkpoint_variables(verify_tensors=True)
+    checks it; the object graph has children edges whose names spell the checkpoint keys."""
+    rng = np.random.default_rng(0)
+    blob = rng.integers(0, 256, 100_003, dtype=np.uint8).tobytes()
+    assert ck.crc32c(blob) == ck._crc32c_python(blob)
+    assert ck.crc32c(b"123456789" * 1000) == ck._crc32c_python(b"123456789" * 1000)
+    big = rng.standard_normal((3, 3, 256, 256)).astype(np.float32)              # 2.4 MB
+    variables = {"residual_block_1/conv0/kernel": big, "residual_block_1/conv0/bias": rng.standard_normal(256).astype(np.float32)}
+    prefix = ck.write_checkpoint(str(tmp_path / "ckpt-1"), variables)
+    index = ck.read_index(prefix)
+    key = "layer_with_weights-0/v/.ATTRIBUTES/VARIABLE_VALUE"
+    assert index[key]["crc32c"] == ck._mask(ck._crc32c_python(big.tobytes())) != 0
+    got = ck.read_checkpoint_variables(prefix, verify_tensors=True)
+    np.testing.assert_array_equal(got[key]["value"], big)
+    # corrupt one byte of the big tensor in the data shard
+    data_path = prefix + ".data-00000-of-00001"
+    raw = bytearray(open(data_path, "rb").read())
+    raw[index[key]["offset"] + 12345] ^= 0x40
+    open(data_path, "wb").write(raw)
+    with pytest.raises(ValueError):
+        ck.read_checkpoint_variables(prefix, verify_tensors=True)
+    ck.read_checkpoint_variables(prefix)                                          # unverified read still returns the bytes
+    # children edges: root -> layer_with_weights-i -> v
+    e = index["_CHECKPOINTABLE_OBJECT_GRAPH"]
+    shard = open(data_path, "rb").read()[e["offset"]:e["offset"] + e["size"]]
+    n, pos = ck._get_varint(shard, 0)
+    nodes = [v for fn, _wt, v in ck._parse_fields(shard[pos + 4:pos + 4 + n]) if fn == 1]
+    root_children = [dict((f2, v2) for f2, _w, v2 in ck._parse_fields(v)) for fn, _wt, v in ck._parse_fields(nodes[0]) if fn == 1]
+    assert [c[2] for c in root_children] == [b"layer_with_weights-0", b"layer_with_weights-1"]
+    holder = nodes[root_children[0][1]]
+    child = dict((f2, v2) for f2, _w, v2 in ck._parse_fields([v for fn, _wt, v in ck._parse_fields(holder) if fn == 1][0]))
+    assert child[2] == b"v" and any(fn == 2 for fn, _wt, _v in ck._parse_fields(nodes[child[1]]))
