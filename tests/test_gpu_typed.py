@@ -185,3 +185,27 @@ def test_streaming_takes_pinned_torch_tensors_without_a_host_copy(cuda_device):
         model.close()
     finally:
         mixed_precision.set_global_policy("float32")
+
+
+def test_typed_edge_cases_empty_batch_and_partial_batch(cuda_device):
+    """batch 0 is a no-op (the reference's predict on an empty array returns an empty array), a call with fewer frames than
+    max_batch touches only its frames, and every frame of a short batch equals the same frame inside a full batch."""
+    spec, weights, content, params, _, res_y = make_case(64, 128, 17, 1, 4, seed=7)
+    ctx = _native.NativeContext(in_shape=spec.input_shape, out_shape=spec.output_shape, bottleneck_res_y=res_y,
+                                bottleneck_num_filters=128, num_styles=1, max_batch=4, precision=_native.PRECISION_BF16)
+    ctx.set_weights(weights)
+    c16 = content.astype(np.float16)
+    empty = ctx.transfer_forward_host(c16[:0], params[:0], out_dtype=np.uint8)
+    assert empty.shape == (0, 64, 128, 3) and empty.dtype == np.uint8
+    full = ctx.transfer_forward_host(c16, params, out_dtype=np.uint8)
+    for n in (1, 3):
+        part = ctx.transfer_forward_host(c16[:n], params[:n], out_dtype=np.uint8)
+        assert part.shape[0] == n and np.abs(part.astype(int) - full[:n].astype(int)).max() <= 2
+    with pytest.raises(_native.RstError):
+        ctx.transfer_forward_host(np.concatenate([c16, c16]), np.concatenate([params, params]))      # exceeds max_batch
+    ctx.close()
+    model, p = styleTransfer.create_style_transfer_model((64, 128, 17), (64, 128, 3), 16, 128, 1)
+    out = model.predict({"content": np.zeros((0, 64, 128, 17), np.float32), "style_params": np.zeros((0, 1, p), np.float32)},
+                        output_dtype=np.uint8)
+    assert out.shape == (0, 64, 128, 3) and out.dtype == np.uint8
+    model.close()
