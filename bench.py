@@ -594,6 +594,12 @@ def main():
         tflops = fps * GFLOP_PER_FRAME / 1e3 / world
         whole = {"achieved_tflops": tflops, "regime": f"burst ({ms_max / 1e3:.3f} s timed region)", "peak_burst": pk["bf16_tflops"],
                  "frac_of_burst_bf16": tflops / pk["bf16_tflops"]}
+        # north_star's "conv path": the convolution kernels alone (every *_umma group of the eager, event-timed pass), i.e. the
+        # step without the norm / blend and pack passes
+        conv_ms = sum(v[0] for k, v in groups.items() if k.endswith("_umma")) / args.steps
+        conv_tflops = BATCH * GFLOP_PER_FRAME / conv_ms if conv_ms > 0 else 0.0          # GFLOP / ms = TFLOP/s
+        whole["conv_path"] = {"ms_per_step": conv_ms, "achieved_tflops": conv_tflops, "frac_of_burst_bf16": conv_tflops / pk["bf16_tflops"],
+                              "frac_of_sustained_bf16": conv_tflops / pk["bf16_tflops_sustained"]}
         line = {
             "metric": "frames/sec rst-960-120-128-17", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

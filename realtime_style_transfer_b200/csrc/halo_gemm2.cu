@@ -39,6 +39,7 @@ constexpr int kHalo2 = 10 * 18 * kRowB2;
 constexpr int kAStage2 = (kHalo2 + 1023) & ~1023;
 constexpr int kAStages2 = 3;
 constexpr int kTail2 = 6400;
+constexpr int kMaxBBlocks2 = 18;          // 2 channel groups x 9 taps
 constexpr int kPrefetchPairs = 3;         // L2 prefetch distance of the A producer, in tile pairs
 
 constexpr int kThreads2 = 96 + 128 * 4;  // 3 control warps + 16 epilogue warps (one per lane quadrant and 32-column chunk)
@@ -97,8 +98,8 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* tail = sB + nblocks * kBHalf;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 4;
-    uint64_t* b_full = a_empty + 4;
-    uint64_t* acc_full = b_full + 2;
+    uint64_t* b_full = a_empty + 4;                          // one per weight block (tap x 64 input channels): kMaxBBlocks2
+    uint64_t* acc_full = b_full + kMaxBBlocks2;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* bias_s = reinterpret_cast<float*>(tail + 256);
@@ -118,7 +119,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 0) {
         // FUSE: every loader warp of both CTAs that fills a stage arrives once on the leader's full barrier
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], FUSE ? 2 * NL : 1); mbar_init(&a_empty[i], 1); }
-        mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1);
+        for (int i = 0; i < kMaxBBlocks2; ++i) mbar_init(&b_full[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 4 * ESPLIT); }
         fence_barrier_init();
     }
@@ -161,13 +162,15 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == W_BPROD) {
         // ================= B producer (both CTAs): this CTA's 64 output channels of every block, once ==========
-        // one barrier per 64-channel group, so the first MMAs start after 72 KB instead of 144 KB have landed
         if (lane == 0 && pair_begin < pair_end) {
             const int per_group = kKS2 / 4;
             for (int g = 0; g < p.n_groups; ++g) {
-                if (leader_cta) mbar_expect_tx(&b_full[g], 2 * per_group * kBHalf);
-                for (int kb = g * per_group; kb < (g + 1) * per_group; ++kb)
-                    tma_load_2d_2sm(sB + kb * kBHalf, &tmB, &b_full[g], 0, kb * N + (int)rank * (N / 2));
+                // one barrier per block (8 KB per CTA), in the order the MMAs consume them: the first tile pair's MMAs start
+                // as soon as the first tap has landed and the other 136 KB stream in behind them
+                for (int kb = g * per_group; kb < (g + 1) * per_group; ++kb) {
+                    if (leader_cta) mbar_expect_tx(&b_full[kb], 2 * kBHalf);
+                    tma_load_2d_2sm(sB + kb * kBHalf, &tmB, &b_full[kb], 0, kb * N + (int)rank * (N / 2));
+                }
             }
         }
     } else if (FUSE && warp >= W_LOAD0 && warp < W_EPI0) {
@@ -310,12 +313,13 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int g = 0; g < p.n_groups; ++g) {
                     if (FUSE) mbar_wait_acquire_cluster(&a_full[as], aph);
                     else mbar_wait(&a_full[as], aph);
-                    if (pr == pair_begin) mbar_wait(&b_full[g], 0);      // weights of this group are resident from here on
+                    const bool first_pair = pr == pair_begin;          // weights are resident after the first tile pair
                     tc_fence_after();
                     const uint32_t a_base16 = sA16 + as * (kAStage2 >> 4);
                     const uint32_t b_base16 = sB16 + g * (kKS2 / 4) * (kBHalf >> 4);
 #pragma unroll
                     for (int ks = 0; ks < kKS2; ++ks) {
+                        if (first_pair && (ks & 3) == 0) { mbar_wait(&b_full[g * (kKS2 / 4) + ks / 4], 0); tc_fence_after(); }
                         const uint64_t da = da_const | (uint64_t)(a_base16 + (uint32_t)(sched_off(SCH_C3, kRowB2, ks) >> 4));
                         const uint64_t db = db_const | (uint64_t)(b_base16 + (ks / 4) * (kBHalf >> 4) + (ks & 3) * 2);
                         if (issuer) mma_f16_ss_2sm(tmem_d, da, db, idesc, ks == 0 ? (uint32_t)(g != 0) : 1u);
