@@ -219,7 +219,7 @@ def e2e_loop(ctx, content, params, weights, outs, n):
     ctx.transfer_wait(prev)
 
 
-def bench_training(torch, dist, _native, _plan, rdist, dev, local_rank, rank, world, steps=3, warmup=2):
+def bench_training(torch, dist, _native, _plan, rdist, dev, local_rank, rank, world, steps=3, warmup=2, tf32_math=False):
     """BASELINE config 4: predictor + transfer net forward/backward in training mode, VGG16 Gram/content loss (x3 forward,
     x1 backward), gradient all-reduce (SUM) over NCCL, RMSprop; 8 samples per GPU at 480x960, 17 channels, 128 filters."""
     b, h, w, f = 8, 480, 960, 128
@@ -231,6 +231,8 @@ def bench_training(torch, dist, _native, _plan, rdist, dev, local_rank, rank, wo
     weights.update(pplan.initial_weights(rng))
     tr = _native.NativeTrainer(in_shape=in_shape, out_shape=out_shape, bottleneck_res_y=h // 4, bottleneck_num_filters=f,
                                max_batch=b, extractor=_native.EXTRACTOR_MOBILE_NET, style_shape=out_shape[:2], device=local_rank)
+    if tf32_math:
+        tr.set_math(_native.PRECISION_TF32)       # plain tf32 operands: TensorFlow's own default for float32 models on Ampere and later
     tr.model.set_weights(weights)
     vgg, cin = {}, 3
     for blk, n, co in (("block1", 2, 64), ("block2", 2, 128), ("block3", 3, 256), ("block4", 3, 512), ("block5", 3, 512)):
@@ -292,7 +294,8 @@ def bench_training(torch, dist, _native, _plan, rdist, dev, local_rank, rank, wo
         "allreduce_ms": ar_max, "allreduce_elements": int(tr.num_gradient_elements),
         "collective": "NCCL all-reduce (SUM) of the flat fp32 gradient buffer" if world > 1 else "none (single process)",
         "achieved_tflops_per_gpu": TRAIN_TFLOP_PER_SAMPLE * b / (per_step / 1e3),
-        "math": "fp32-accurate (error-compensated split tf32 on tcgen05 for the trunk and VGG convolutions, fp32 elsewhere)",
+        "math": "plain tf32 operands on tcgen05 for the trunk and VGG convolutions (rst_train_set_math(TF32)), fp32 elsewhere" if tf32_math else
+                "fp32-accurate (error-compensated split tf32 on tcgen05 for the trunk and VGG convolutions, fp32 elsewhere)",
         "timing": "CUDA events on the trainer's stream around the timed steps, max over ranks",
         "loss_mean": float(loss_rows[:, 0].mean()), "style_loss_mean": float(loss_rows[:, 2].mean()),
         "gpu_launches_per_step": launches,
@@ -552,6 +555,8 @@ def main():
     if not args.no_training:
         torch.cuda.set_stream(torch.cuda.default_stream(dev))
         training = bench_training(torch, dist, _native, _plan, rdist, dev, local_rank, rank, world)
+        fast = bench_training(torch, dist, _native, _plan, rdist, dev, local_rank, rank, world, tf32_math=True)
+        training["tf32_math"] = {k: fast[k] for k in ("samples_per_s", "ms_per_step", "allreduce_ms", "achieved_tflops_per_gpu", "math", "loss_mean")}
 
     # multi-GPU timing rule: every rank did the same number of frames; report against the slowest rank
     vals = [ms, e2e_s * 1e3, e2e_sync_s * 1e3, sustained["seconds"] * 1e3 if sustained else 0.0,
