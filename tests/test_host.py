@@ -364,3 +364,49 @@ def test_preprocess_numpy_image_and_screenshot_dataset(tmp_path):
     assert [b.shape[0] for b in batches] == [2, 1] and len(list(ds)) == 3                      # re-iterable
     small = list(hdrScreenshots.get_unreal_hdr_screenshot_dataset(tmp_path, cfg.channels, (10, 20, 17)))
     assert small[0].shape == (10, 20, 17)
+
+
+def test_header_compiles_as_c_and_links_from_plain_c(tmp_path):
+    """include/rst_b200.h is a C header (no C++ / CUDA / torch types) and the shared library links from a plain C program: the
+    drop-in boundary any host language binds.  Without a GPU rst_create must fail cleanly with a message, not crash."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    header_dir = os.path.join(ROOT, "include")
+    lib_dir = os.path.join(ROOT, "realtime_style_transfer_b200", "csrc")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                           os.path.join(header_dir, "rst_b200.h")])
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "rst_b200.h"
+int main(void) {
+    rst_config cfg;
+    rst_ctx* ctx = NULL;
+    const unsigned char digits[9] = {'1','2','3','4','5','6','7','8','9'};
+    memset(&cfg, 0, sizeof cfg);
+    cfg.in_h = 64; cfg.in_w = 128; cfg.in_c = 17; cfg.out_h = 64; cfg.out_w = 128; cfg.bottleneck_res_y = 16;
+    cfg.bottleneck_num_filters = 128; cfg.num_styles = 1; cfg.max_batch = 1; cfg.precision = RST_PRECISION_BF16;
+    printf("%s\n", rst_version());
+    printf("crc %08x\n", (unsigned)rst_host_crc32c(digits, 9));
+    printf("dtype %d %d %d\n", RST_DTYPE_F32, RST_DTYPE_F16, RST_DTYPE_U8);
+    int rc = rst_create(&cfg, 0, &ctx);
+    printf("create rc=%d msg=%s\n", rc, rc ? rst_last_error(NULL) : "ok");
+    if (!rc) rst_destroy(ctx);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-I", header_dir, str(src), "-o", str(exe), "-L", lib_dir, "-lrst_sm100",
+                           f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith("rst_b200") and lines[1] == "crc e3069283" and lines[2] == "dtype 0 1 2"
+    assert lines[3].startswith("create rc=")
+    import torch
+    if not torch.cuda.is_available():
+        assert "rc=0" not in lines[3] and "no CUDA device" in lines[3]
