@@ -77,6 +77,11 @@ int rst_destroy(rst_ctx* ctx);
 /* ctx may be NULL: returns the message of the last failed rst_create on this thread. */
 const char* rst_last_error(const rst_ctx* ctx);
 
+/* Page-locked host buffers for the frames / images given to the *_host entry points (what tf.data's prefetch buffers are to the
+ * reference's loop, predict_video_using_checkpoint.py:90-93): asynchronous copies need pinned memory.  write_combined != 0 for
+ * buffers the host only writes (G-buffers on their way to the GPU).  rst_last_error(NULL) gives the message of a failure. */
+int rst_host_alloc(void** h_ptr, uint64_t num_bytes, int write_combined);
+int rst_host_free(void* h_ptr);
 /* Host utility: crc32c (Castagnoli) of a host buffer, the checksum of TensorFlow's tensor bundles (un-vendored third party:
  * tensorflow/core/lib/hash/crc32c; callers mask it as LevelDB does).  Used by checkpoint.py, which reads and writes the
  * reference's checkpoint format (tracing/checkpoint.py:18-37) without TensorFlow. */

@@ -63,6 +63,8 @@ _vp = C.c_void_p
 SIGNATURES = {
     "rst_version": (C.c_char_p, []),
     "rst_host_crc32c": (C.c_uint32, [_vp, C.c_uint64]),
+    "rst_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64, C.c_int]),
+    "rst_host_free": (C.c_int, [_vp]),
     "rst_create": (C.c_int, [C.POINTER(RstConfig), C.c_int, C.POINTER(_vp)]),
     "rst_destroy": (C.c_int, [_vp]),
     "rst_last_error": (C.c_char_p, [_vp]),
@@ -164,6 +166,35 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(_vp)
     return _vp(int(a))
+
+
+class PinnedArray:
+    """A page-locked host array from rst_host_alloc (numpy view in ``.array``); free() or garbage collection releases it.
+    write_combined=True for frame buffers the host only writes before they are uploaded."""
+
+    def __init__(self, shape, dtype=np.float32, write_combined: bool = False):
+        self.lib = load_library()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = _vp()
+        rc = self.lib.rst_host_alloc(C.byref(ptr), n, int(write_combined))
+        if rc != 0:
+            raise RstError(rc, (self.lib.rst_last_error(None) or b"").decode())
+        self.ptr = ptr
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.rst_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class NativeContext:

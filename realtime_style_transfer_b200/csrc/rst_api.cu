@@ -213,6 +213,20 @@ static int build_plan(rst_ctx* c) {
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* rst_version(void) { return "rst_b200 0.2 (sm_100a)"; }
 
+// Page-locked host memory for frame / image buffers handed to the *_host entry points (asynchronous DMA needs it).
+// write_combined: uncached on the CPU side -- right for buffers the host only WRITES (captured G-buffers on their way to the GPU).
+extern "C" int rst_host_alloc(void** h_ptr, uint64_t bytes, int write_combined) {
+    if (!h_ptr) return RST_ERR_INVALID;
+    *h_ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(h_ptr, bytes ? bytes : 16, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (e != cudaSuccess) { g_create_error = std::string("rst_host_alloc: ") + cudaGetErrorString(e); return RST_ERR_CUDA; }
+    return RST_OK;
+}
+extern "C" int rst_host_free(void* h_ptr) {
+    if (!h_ptr) return RST_OK;
+    return cudaFreeHost(h_ptr) == cudaSuccess ? RST_OK : RST_ERR_CUDA;
+}
+
 // crc32c (Castagnoli, reflected 0x82F63B78) of a host buffer, slicing-by-8: the checksum of TensorFlow's tensor bundles
 // (tensorflow/core/lib/hash/crc32c) for the checkpoint reader / writer, whose pure-Python loop is too slow for 100 MB shards.
 extern "C" uint32_t rst_host_crc32c(const void* data, uint64_t n) {

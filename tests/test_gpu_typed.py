@@ -209,3 +209,24 @@ def test_typed_edge_cases_empty_batch_and_partial_batch(cuda_device):
                         output_dtype=np.uint8)
     assert out.shape == (0, 64, 128, 3) and out.dtype == np.uint8
     model.close()
+
+
+def test_library_pinned_buffers_feed_the_streaming_entry_point(cuda_device):
+    """rst_host_alloc / rst_host_free (page-locked frame buffers for hosts that do not link the CUDA runtime themselves) used as
+    the source and destination of rst_transfer_submit_host_typed."""
+    spec, weights, content, params, _, res_y = make_case(64, 128, 17, 1, 2, seed=11)
+    ctx = _native.NativeContext(in_shape=spec.input_shape, out_shape=spec.output_shape, bottleneck_res_y=res_y,
+                                bottleneck_num_filters=128, num_styles=1, max_batch=2, precision=_native.PRECISION_BF16)
+    ctx.set_weights(weights)
+    frames = _native.PinnedArray(content.shape, np.float16, write_combined=True)
+    image = _native.PinnedArray((2, 64, 128, 3), np.uint8)
+    sp = _native.PinnedArray(params.shape, np.float32)
+    frames.array[...] = content.astype(np.float16)
+    sp.array[...] = params
+    ticket = ctx.transfer_submit_host(frames.array, sp.array, None, image.array)
+    ctx.transfer_wait(ticket)
+    want = ctx.transfer_forward_host(content.astype(np.float16), params, out_dtype=np.uint8)
+    assert np.abs(image.array.astype(int) - want.astype(int)).max() <= 2
+    ctx.close()
+    for a in (frames, image, sp):
+        a.free()
