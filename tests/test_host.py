@@ -410,3 +410,80 @@ int main(void) {
     import torch
     if not torch.cuda.is_available():
         assert "rc=0" not in lines[3] and "no CUDA device" in lines[3]
+
+
+def test_reads_hand_assembled_exr_files(tmp_path):
+    """EXR files assembled byte by byte in this test from the OpenEXR file-layout description (scan-line, single part) by an
+    encoder that shares no code with dataloaders/exr.py: an uncompressed file with a HALF and a FLOAT channel and a data
+    window that does not start at (0, 0), and a ZIP file (16-line blocks, byte interleave + delta predictor written as explicit
+    Python loops, the last block short).  The Unreal capture writes such files; none is available offline."""
+    import struct
+    import zlib
+    from realtime_style_transfer_b200.dataloaders import exr
+
+    def attr(name, typ, payload):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(payload)) + payload
+
+    def build(path, planes, types, compression, window):
+        x0, y0, x1, y1 = window
+        w, h = x1 - x0 + 1, y1 - y0 + 1
+        names = sorted(planes)                                            # channels are stored in alphabetical order
+        chlist = b""
+        for n in names:
+            chlist += n.encode() + b"\0" + struct.pack("<iB3xii", {"HALF": 1, "FLOAT": 2}[types[n]], 0, 1, 1)
+        chlist += b"\0"
+        header = struct.pack("<iI", 20000630, 2)
+        header += attr("channels", "chlist", chlist)
+        header += attr("compression", "compression", bytes([compression]))
+        header += attr("dataWindow", "box2i", struct.pack("<iiii", x0, y0, x1, y1))
+        header += attr("displayWindow", "box2i", struct.pack("<iiii", 0, 0, x1, y1))
+        header += attr("lineOrder", "lineOrder", b"\0")
+        header += attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+        header += attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0))
+        header += attr("screenWindowWidth", "float", struct.pack("<f", 1.0))
+        header += b"\0"
+        lines = 16 if compression == 3 else 1
+        blocks = []
+        for by in range(0, h, lines):
+            raw = b""
+            for yy in range(by, min(by + lines, h)):
+                for n in names:                                           # per scan line: every channel's row, one after the other
+                    dt = "<f2" if types[n] == "HALF" else "<f4"
+                    raw += planes[n][yy].astype(dt).tobytes()
+            if compression == 3:
+                half = (len(raw) + 1) // 2
+                re = bytearray(len(raw))
+                for i, b in enumerate(raw):                               # even bytes first, odd bytes second
+                    re[(i // 2) if i % 2 == 0 else half + i // 2] = b
+                enc = bytearray(len(re))
+                prev = 0
+                for i, b in enumerate(re):                                # delta predictor: d[i] = t[i] - t[i-1] + 128 (mod 256)
+                    enc[i] = b if i == 0 else (b - prev + 128 + 256) & 0xFF
+                    prev = b
+                packed = zlib.compress(bytes(enc))
+                payload = packed if len(packed) < len(raw) else raw      # a block is stored raw when compression does not help
+            else:
+                payload = raw
+            blocks.append(struct.pack("<ii", y0 + by, len(payload)) + payload)
+        table_pos = len(header)
+        offsets, pos = [], table_pos + 8 * len(blocks)
+        for b in blocks:
+            offsets.append(pos)
+            pos += len(b)
+        path.write_bytes(header + struct.pack(f"<{len(blocks)}Q", *offsets) + b"".join(blocks))
+
+    rng = np.random.default_rng(5)
+    h, w = 21, 30                                                          # 21 rows: the second ZIP block has 5 lines
+    half_vals = rng.uniform(0, 4, (h, w)).astype(np.float16).astype(np.float32)
+    float_vals = rng.uniform(10, 1e4, (h, w)).astype(np.float32)
+    build(tmp_path / "plain.exr", {"R": half_vals, "Z": float_vals}, {"R": "HALF", "Z": "FLOAT"}, 0, (3, 2, 3 + w - 1, 2 + h - 1))
+    img = exr.load(tmp_path / "plain.exr")
+    assert img.shape == (h, w) and list(img.channels()) == ["R", "Z"]
+    assert np.array_equal(img.channel("R"), half_vals) and np.array_equal(img.channel("Z"), float_vals)
+    smooth = np.tile(np.linspace(0, 1, w, dtype=np.float32), (h, 1)).astype(np.float16).astype(np.float32)
+    build(tmp_path / "zip.exr", {"B": smooth * 0.5, "G": smooth, "R": half_vals}, {"B": "HALF", "G": "HALF", "R": "HALF"}, 3,
+          (0, 0, w - 1, h - 1))
+    img = exr.load(tmp_path / "zip.exr", keep_half=True)
+    assert img.header["compression"] == "ZIP" and img.channel("G").dtype == np.float16
+    assert np.array_equal(img.channel("R").astype(np.float32), half_vals)
+    assert np.array_equal(img.channel("G").astype(np.float32), smooth) and np.array_equal(img.channel("B").astype(np.float32), smooth * 0.5)
