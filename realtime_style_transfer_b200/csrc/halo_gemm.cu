@@ -1034,11 +1034,14 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
         a0[j] = inv * ps[p.scale_off + c];
         b0[j] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
         if (BLEND) {
+            // the weight map of this path is always (1 - w, w) (styleTransfer.py:297-302 and its average-pooled mips), so
+            // w0*p0 + w1*p1 = p0 + w1*(p1 - p0): the differences are kept, one fma per coefficient and pixel instead of two ops
             const float* p1 = ps + p.param_sstride;
-            a1[j] = inv * p1[p.scale_off + c];
-            b1[j] = p1[p.bias_off + c] + nmi * p1[p.scale_off + c];
+            a1[j] = inv * p1[p.scale_off + c] - a0[j];
+            b1[j] = (p1[p.bias_off + c] + nmi * p1[p.scale_off + c]) - b0[j];
         }
     }
+    const int vpp_shift = 31 - __clz(vec_per_pix);            // C in {16, 32, 64, 128}: a power of two
     const long long base = (long long)n * p.P * vec_per_pix;
     const long long v0 = (long long)blockIdx.x * pix_per_block * vec_per_pix;
     const long long v1 = min((long long)p.P * vec_per_pix, v0 + (long long)pix_per_block * vec_per_pix);
@@ -1057,8 +1060,8 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
             const float2 xv = __bfloat1622float2(xb[j]);
             float aa0 = a0[2 * j], bb0 = b0[2 * j], aa1 = a0[2 * j + 1], bb1 = b0[2 * j + 1];
             if (BLEND) {
-                aa0 = aa0 * w.x + a1[2 * j] * w.y;         bb0 = bb0 * w.x + b1[2 * j] * w.y;
-                aa1 = aa1 * w.x + a1[2 * j + 1] * w.y;     bb1 = bb1 * w.x + b1[2 * j + 1] * w.y;
+                aa0 = fmaf(w.y, a1[2 * j], aa0);           bb0 = fmaf(w.y, b1[2 * j], bb0);
+                aa1 = fmaf(w.y, a1[2 * j + 1], aa1);       bb1 = fmaf(w.y, b1[2 * j + 1], bb1);
             }
             float o0 = fmaf(xv.x, aa0, bb0), o1 = fmaf(xv.y, aa1, bb1);
             if (act == ACT_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
@@ -1077,13 +1080,13 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
         for (int u = 0; u < 4; ++u) {
             xi[u] = x4[v + u * stride];
             ri[u] = RES ? r4[v + u * stride] : z;
-            wi[u] = BLEND ? w2[(v + u * stride) / vec_per_pix] : make_float2(1.f, 0.f);
+            wi[u] = BLEND ? w2[(v + u * stride) >> vpp_shift] : make_float2(1.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) y4[v + u * stride] = one(xi[u], ri[u], wi[u]);
     }
     for (; v < v1; v += stride)
-        y4[v] = one(x4[v], RES ? r4[v] : z, BLEND ? w2[v / vec_per_pix] : make_float2(1.f, 0.f));
+        y4[v] = one(x4[v], RES ? r4[v] : z, BLEND ? w2[v >> vpp_shift] : make_float2(1.f, 0.f));
 }
 
 // fp32 -> fp32 with 3 channels (the image head): 4 consecutive floats per thread, sigmoid.

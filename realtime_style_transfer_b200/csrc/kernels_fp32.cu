@@ -633,6 +633,55 @@ __global__ void weights_concat_kernel(const float* __restrict__ w_in, float* __r
     }
     w_out[i * (sm1 + 1)] = 1.f - sum;
 }
+// Two styles: the concat [1 - w, w] (styleTransfer.py:297-302) and its first two AvgPool2D(2) levels (:335-345) in ONE pass.
+// A thread owns a 4 x 4 block of the weight map: four float4 loads, then 16 + 4 + 1 two-channel pixels out (the pooled levels
+// are averages of averages, as the reference's chained pooling layers compute them).
+__global__ void weights_pyramid3_kernel(const float* __restrict__ w_in, float* __restrict__ l0, float* __restrict__ l1,
+                                        float* __restrict__ l2, int H, int W, long long blocks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= blocks) return;
+    const int bw = W / 4, bh = H / 4;
+    const int bx = (int)(i % bw);
+    const long long t = i / bw;
+    const int by = (int)(t % bh);
+    const long long n = t / bh;
+    float4 r[4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) r[y] = *reinterpret_cast<const float4*>(w_in + ((n * H + 4 * by + y) * W + 4 * bx));
+    float m1[2][2][2];                                    // [row][col][channel] of level 1
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        const float w1[4] = {r[y].x, r[y].y, r[y].z, r[y].w};
+        float4* o = reinterpret_cast<float4*>(l0 + ((n * H + 4 * by + y) * W + 4 * bx) * 2);
+        o[0] = make_float4(1.f - w1[0], w1[0], 1.f - w1[1], w1[1]);
+        o[1] = make_float4(1.f - w1[2], w1[2], 1.f - w1[3], w1[3]);
+    }
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx) {
+            const float a[4] = {xx ? r[2 * yy].z : r[2 * yy].x, xx ? r[2 * yy].w : r[2 * yy].y,
+                                xx ? r[2 * yy + 1].z : r[2 * yy + 1].x, xx ? r[2 * yy + 1].w : r[2 * yy + 1].y};
+            // the same summation order as the generic 2x2 pooling kernel: top-left + top-right + bottom-left + bottom-right
+            m1[yy][xx][0] = ((1.f - a[0]) + (1.f - a[1]) + (1.f - a[2]) + (1.f - a[3])) * 0.25f;
+            m1[yy][xx][1] = (a[0] + a[1] + a[2] + a[3]) * 0.25f;
+        }
+    const int H1 = H / 2, W1 = W / 2;
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy)
+        *reinterpret_cast<float4*>(l1 + ((n * H1 + 2 * by + yy) * W1 + 2 * bx) * 2) =
+            make_float4(m1[yy][0][0], m1[yy][0][1], m1[yy][1][0], m1[yy][1][1]);
+    *reinterpret_cast<float2*>(l2 + ((n * (H / 4) + by) * (W / 4) + bx) * 2) =
+        make_float2((m1[0][0][0] + m1[0][1][0] + m1[1][0][0] + m1[1][1][0]) * 0.25f,
+                    (m1[0][0][1] + m1[0][1][1] + m1[1][0][1] + m1[1][1][1]) * 0.25f);
+}
+cudaError_t launch_weights_pyramid3(const float* w_in, float* l0, float* l1, float* l2, int B, int H, int W, cudaStream_t s) {
+    const long long blocks = (long long)B * (H / 4) * (W / 4);
+    if (blocks == 0) return cudaSuccess;
+    weights_pyramid3_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, s>>>(w_in, l0, l1, l2, H, W, blocks);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_weights_concat(const float* w_in, float* w_out, long long pixels, int sm1, cudaStream_t s) {
     if (pixels == 0) return cudaSuccess;
     weights_concat_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, s>>>(w_in, w_out, pixels, sm1);

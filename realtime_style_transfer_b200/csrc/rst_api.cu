@@ -464,12 +464,28 @@ int build_mips(rst_ctx* c, const float* d_style_weights, int batch, cudaStream_t
     if (!d_style_weights) return fail(c, RST_ERR_INVALID, "style_weights required when num_styles > 1");
     int h = c->cfg.out_h, w = c->cfg.out_w;
     float* cur = c->w_pyramid;
-    {
-        LaunchScope ls(c, s, "weights_pyramid");
-        RST_CUDA(c, launch_weights_concat(d_style_weights, cur, (long long)batch * h * w, c->cfg.num_styles - 1, s));
+    int first = 0;
+    if (c->cfg.num_styles == 2 && h % 4 == 0 && w % 4 == 0 && c->n_expand + 1 >= 2 &&
+        (reinterpret_cast<uintptr_t>(d_style_weights) & 15) == 0) {
+        // the three levels the network reads (widths W, W/2, W/4) in one pass
+        float* l1 = cur + (size_t)batch * h * w * 2;
+        float* l2 = l1 + (size_t)batch * (h / 2) * (w / 2) * 2;
+        {
+            LaunchScope ls(c, s, "weights_pyramid");
+            RST_CUDA(c, launch_weights_pyramid3(d_style_weights, cur, l1, l2, batch, h, w, s));
+        }
+        c->mips.emplace_back(w, cur);
+        c->mips.emplace_back(w / 2, l1);
+        c->mips.emplace_back(w / 4, l2);
+        cur = l2; h /= 4; w /= 4; first = 2;
+    } else {
+        {
+            LaunchScope ls(c, s, "weights_pyramid");
+            RST_CUDA(c, launch_weights_concat(d_style_weights, cur, (long long)batch * h * w, c->cfg.num_styles - 1, s));
+        }
+        c->mips.emplace_back(w, cur);
     }
-    c->mips.emplace_back(w, cur);
-    for (int i = 0; i < c->n_expand + 1; ++i) {
+    for (int i = first; i < c->n_expand + 1; ++i) {
         if (h < 2 || w < 2) break;
         float* nxt = cur + (size_t)batch * h * w * 2;
         LaunchScope ls(c, s, "weights_pyramid");

@@ -113,6 +113,8 @@ cudaError_t launch_cin_apply(const CinApply& p, cudaStream_t s);
 
 // style-weight pyramid (styleTransfer.py:297-303, :335-345)
 cudaError_t launch_weights_concat(const float* w_in, float* w_out, long long pixels, int sm1, cudaStream_t s);
+// two styles, H % 4 == 0, W % 4 == 0: concat level and the first two pooled levels in one kernel
+cudaError_t launch_weights_pyramid3(const float* w_in, float* l0, float* l1, float* l2, int B, int H, int W, cudaStream_t s);
 cudaError_t launch_avgpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s);
 cudaError_t launch_maxpool2_f32(const float* x, float* y, int B, int Hi, int Wi, int C, cudaStream_t s);
 cudaError_t launch_scale_channels(const float* x, const float* z, float* y, int B, int P, int C, cudaStream_t s);
