@@ -526,3 +526,28 @@ def test_reference_training_model_test_at_its_own_size(cuda_device):
         assert np.abs(losses[:, i] - r).max() / np.abs(r).max() <= 1e-3, key
     tr.close()
     m.training.close()
+
+
+def test_checkpoint_right_after_train_step_holds_the_trained_values(cuda_device, tmp_path):
+    """A custom loop over train_step (no fit): weights / get_weights / trainable_variables / save_weights must see the values the
+    native trainer holds after the step, not the host copies from before it."""
+    from realtime_style_transfer_b200 import optimizers
+    models = _python_training_model()
+    models.training.compile(optimizer=optimizers.RMSprop())
+    before = {k: v.copy() for k, v in models.training.weights.items()}
+    models.training.train_step(_dataset(1, 2, seed=21)[0])
+    after = models.training.weights                                   # no fit(), no explicit sync_to_host()
+    changed = [k for k in before if not np.array_equal(before[k], after[k])]
+    assert len(changed) > len(before) // 2, "weights property returned the stale host copies"
+    assert all(not np.array_equal(a, b) for a, b in zip(models.training.get_weights(), before.values()) if a.size > 8) or changed
+    path = models.training.save_weights(str(tmp_path / "after_one_step"))
+    fresh = _python_training_model()
+    fresh.training.load_weights(path).assert_existing_objects_matched()
+    for k, v in after.items():
+        assert np.array_equal(fresh.training.weights[k], v), k
+    # and the trainer was not re-uploaded with stale values: a second step continues from the trained state
+    tr = models.training._trainer
+    dev_kernel = tr.model.get_weight("residual_block_2/conv1/kernel", after["residual_block_2/conv1/kernel"].shape)
+    tr.sync_weights()
+    assert np.array_equal(dev_kernel, after["residual_block_2/conv1/kernel"])
+    models.training.close(); fresh.training.close()
