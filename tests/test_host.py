@@ -487,3 +487,29 @@ def test_reads_hand_assembled_exr_files(tmp_path):
     assert img.header["compression"] == "ZIP" and img.channel("G").dtype == np.float16
     assert np.array_equal(img.channel("R").astype(np.float32), half_vals)
     assert np.array_equal(img.channel("G").astype(np.float32), smooth) and np.array_equal(img.channel("B").astype(np.float32), smooth * 0.5)
+
+
+def test_predictor_bottleneck_width_other_than_the_reference_default_is_rejected_early():
+    """create_style_prediction_model(..., num_style_parameters=N): the native head has the reference default (100,
+    stylePrediction.py:26) built in; another width must fail at construction, not with a shape error at the first forward."""
+    stylePrediction.create_style_prediction_model((64, 128, 3), "DUMMY", 742, num_style_parameters=100)
+    with pytest.raises(NotImplementedError):
+        stylePrediction.create_style_prediction_model((64, 128, 3), "DUMMY", 742, num_style_parameters=64)
+    with pytest.raises(NotImplementedError):
+        PredictorPlan((64, 128, 3), "MOBILE_NET", 742, 128)
+
+
+def test_checkpoint_duplicate_keras_names_prefer_the_inference_model(tmp_path):
+    """A training checkpoint of the reference can hold two variables with the same Keras name (the frozen loss model's MobileNet
+    next to the predictor's): entries below `loss_model` must never be loaded into the inference variables."""
+    from realtime_style_transfer_b200 import checkpoint as ck
+    model = stylePrediction.create_style_prediction_model((64, 128, 3), "MOBILE_NET", 50)
+    good = np.full((3, 3, 3, 16), 2.0, np.float32)
+    bad = np.full((3, 3, 3, 16), -7.0, np.float32)
+    for order in (("loss_model/x", "inference_model/y"), ("a_loss_model/x", "z_inference/y")):
+        ckpt = {
+            f"{order[0] if 'loss' in order[0] else order[1]}/kernel/.ATTRIBUTES/VARIABLE_VALUE": {"value": bad, "full_name": "Conv/kernel"},
+            f"{order[1] if 'loss' in order[0] else order[0]}/kernel/.ATTRIBUTES/VARIABLE_VALUE": {"value": good, "full_name": "Conv/kernel"},
+        }
+        assignment, _missing, _unused = ck.match_checkpoint_to_model(ckpt, model)
+        assert np.array_equal(assignment["mobilenet/Conv/kernel"], good)
