@@ -105,6 +105,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    pdl_wait();                                        // everything below may touch what the previous kernel wrote / still reads
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         bias_s[i] = p.bias ? p.bias[i] : 0.f;
         scale_s[i] = p.post_scale ? p.post_scale[i] : 1.f;
@@ -488,7 +489,7 @@ static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, con
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES><<<grid, halo_threads(N), l.smem_bytes, s>>>(tmA, tmB, p);
+    if (cudaError_t e = launch_pdl(halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES>, dim3(grid), dim3(halo_threads(N)), l.smem_bytes, s, tmA, tmB, p)) return e;
     return cudaGetLastError();
 }
 
@@ -677,6 +678,8 @@ __device__ __forceinline__ float4 ld_quad(const __half* base, int i) {
 template <typename TIn>
 __global__ void pack_stem_input_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C,
                                        int n_real, int row_elems, int pair_window, long long total_slots) {
+    pdl_wait();
+    pdl_trigger();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_slots) return;
     const int slots = row_elems / 8;
@@ -713,6 +716,8 @@ __global__ void pack_stem_input_kernel(const TIn* __restrict__ x, __nv_bfloat16*
 // 18-channel pair layout (SCH_STEM2B), any even W: one thread per (pixel pair, 8-element group of the 64-element pair row).
 template <typename TIn>
 __global__ void pack_stem_pairs18_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int W, long long total_groups) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int C = 18;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_groups) return;
@@ -744,6 +749,8 @@ __global__ void pack_stem_pairs18_kernel(const TIn* __restrict__ x, __nv_bfloat1
 template <typename TIn>
 __global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
                                                                     long long total_segments) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int C = 18, NF4 = 18 * C;                                // 72 pixels x 18 floats
     extern __shared__ float4 pack_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -796,6 +803,8 @@ __global__ void __launch_bounds__(256) pack_stem_pair_rows18_kernel(const TIn* _
 template <int NV, bool PAIRW, typename TIn>
 __global__ void __launch_bounds__(256) pack_stem_rows_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int W,
                                                              long long total_segments) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int C = 16 + NV, ROW = NV <= 1 ? 32 : 64, NF4 = 18 * C;
     extern __shared__ float4 pack_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -886,9 +895,9 @@ static cudaError_t launch_pack_stem_input_t(const TIn* x, __nv_bfloat16* y, int 
         if (row_elems != 32) return cudaErrorInvalidValue;
         if (W % 64 == 0 && aligned) {
             const long long segments = (long long)B * H * (W / 64);
-            pack_stem_pair_rows18_kernel<TIn><<<(unsigned)((segments + 7) / 8), 256, (size_t)8 * 18 * 18 * sizeof(float4), s>>>(x, y, W, segments);
+            (void)launch_pdl(pack_stem_pair_rows18_kernel<TIn>, dim3((unsigned)((segments + 7) / 8)), dim3(256), (size_t)8 * 18 * 18 * sizeof(float4), s, x, y, W, segments);
         } else {
-            pack_stem_pairs18_kernel<TIn><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, W, total);
+            (void)launch_pdl(pack_stem_pairs18_kernel<TIn>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, x, y, W, total);
         }
         return cudaGetLastError();
     }
@@ -896,12 +905,12 @@ static cudaError_t launch_pack_stem_input_t(const TIn* x, __nv_bfloat16* y, int 
         const long long segments = (long long)B * H * (W / 64);
         const unsigned blocks = (unsigned)((segments + 7) / 8);
         const size_t smem = (size_t)8 * 18 * C * sizeof(float4);
-        if (nv == 1 && pair_window) pack_stem_rows_kernel<1, true, TIn><<<blocks, 256, smem, s>>>(x, y, W, segments);
-        else if (nv == 1) pack_stem_rows_kernel<1, false, TIn><<<blocks, 256, smem, s>>>(x, y, W, segments);
-        else pack_stem_rows_kernel<2, false, TIn><<<blocks, 256, smem, s>>>(x, y, W, segments);
+        if (nv == 1 && pair_window) (void)launch_pdl(pack_stem_rows_kernel<1, true, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
+        else if (nv == 1) (void)launch_pdl(pack_stem_rows_kernel<1, false, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
+        else (void)launch_pdl(pack_stem_rows_kernel<2, false, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
         return cudaGetLastError();
     }
-    pack_stem_input_kernel<TIn><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, H, W, C, n_real, row_elems, pair_window, total);
+    (void)launch_pdl(pack_stem_input_kernel<TIn>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, x, y, H, W, C, n_real, row_elems, pair_window, total);
     return cudaGetLastError();
 }
 
@@ -914,6 +923,8 @@ cudaError_t launch_pack_stem_input(const void* x, int x_f16, __nv_bfloat16* y, i
 // Instance-norm apply, VEC channels per thread-iteration (8 for bf16 input, 4 or fewer for fp32 input).
 template <bool XF32, bool YF32>
 __global__ void __launch_bounds__(256) cin_apply_v_kernel(const CinApplyV p, int pix_per_block) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float smf[];
     const int C = p.C;
     float* s_inv = smf;
@@ -1017,6 +1028,8 @@ __global__ void __launch_bounds__(256) cin_apply_v_kernel(const CinApplyV p, int
 // fused coefficients y = x*a + b in registers and streams 4 independent 16-byte vectors per iteration.
 template <bool BLEND, bool RES>
 __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, int pix_per_block) {
+    pdl_wait();
+    pdl_trigger();
     const int C = p.C, n = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int c0 = (threadIdx.x % vec_per_pix) * 8;
@@ -1089,11 +1102,151 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
         y4[v] = one(x4[v], RES ? r4[v] : z, BLEND ? w2[v >> vpp_shift] : make_float2(1.f, 0.f));
 }
 
+// Same arithmetic, operands staged by the bulk-copy engine: a producer warp streams 16-byte-vector chunks of x (and of the skip
+// tensor) into a ring of shared-memory stages with cp.async.bulk + mbarrier transaction counts, eight consumer warps read their
+// vectors from shared memory and store the result straight to global memory.  The loads in flight no longer live in registers
+// (stages x chunk bytes per CTA instead of 4 vectors per thread), which is what the register version is short of when the
+// tensors sit in L2 (profiles/r02_00_summary.md: 35 % warps active, issue 30 %, ~6 TB/s of a ~12 TB/s L2).
+// In place (y == x) is safe: a chunk is stored only after its own bulk load completed, other chunks are other addresses.
+constexpr int kBulkMaxStages = 8;
+constexpr int kBulkConsumers = 256;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     umma::smem_u32(dst_smem)),
+                 "l"((uint64_t)__cvta_generic_to_global(src)), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+
+template <bool BLEND, bool RES>
+__global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(const CinApplyV p, int pix_per_block, int stages,
+                                                                             int chunk_vecs) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ uint64_t full[kBulkMaxStages], empty[kBulkMaxStages];
+    const int C = p.C, n = blockIdx.y, tid = threadIdx.x;
+    const int vec_per_pix = C >> 3;
+    const long long base = (long long)n * p.P * vec_per_pix;
+    const long long v0 = (long long)blockIdx.x * pix_per_block * vec_per_pix;
+    const long long v1 = min((long long)p.P * vec_per_pix, v0 + (long long)pix_per_block * vec_per_pix);
+    const int nchunks = (int)((v1 - v0 + chunk_vecs - 1) / chunk_vecs);
+    uint4* xs = reinterpret_cast<uint4*>(bulk_smem);
+    uint4* rs = xs + (size_t)stages * chunk_vecs;
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], kBulkConsumers / 32); }
+        umma::fence_barrier_init();
+    }
+    pdl_wait();
+    pdl_trigger();
+    __syncthreads();
+    if (tid >= kBulkConsumers) {                                   // ---- producer warp
+        if (tid == kBulkConsumers) {
+            const uint4* x4 = reinterpret_cast<const uint4*>(p.x) + base;
+            const uint4* r4 = RES ? reinterpret_cast<const uint4*>(p.residual) + base : nullptr;
+            for (int k = 0; k < nchunks; ++k) {
+                const int st = k % stages;
+                if (k >= stages) umma::mbar_wait(&empty[st], ((k / stages) - 1) & 1);
+                const long long v = v0 + (long long)k * chunk_vecs;
+                const uint32_t bytes = (uint32_t)min((long long)chunk_vecs, v1 - v) * 16u;
+                umma::mbar_expect_tx(&full[st], RES ? 2 * bytes : bytes);
+                bulk_load_1d(xs + (size_t)st * chunk_vecs, x4 + v, bytes, &full[st]);
+                if (RES) bulk_load_1d(rs + (size_t)st * chunk_vecs, r4 + v, bytes, &full[st]);
+            }
+        }
+        return;
+    }
+    // ---- consumers: fixed group of 8 channels per thread (kBulkConsumers % vec_per_pix == 0)
+    const int c0 = (tid % vec_per_pix) * 8;
+    const double inv_p = 1.0 / (double)p.P;
+    float a0[8], b0[8], a1[8], b1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const double2 st = *reinterpret_cast<const double2*>(p.stats + ((long long)n * C + c) * 2);
+        const double mean = st.x * inv_p;
+        double var = fma(st.y, inv_p, -mean * mean);
+        if (var < 0.0) var = 0.0;
+        const float inv = rsqrtf((float)var + p.eps), nmi = -(float)mean * inv;
+        const float* ps = p.params + n * p.param_bstride;
+        a0[j] = inv * ps[p.scale_off + c];
+        b0[j] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
+        if (BLEND) {
+            const float* p1 = ps + p.param_sstride;
+            a1[j] = inv * p1[p.scale_off + c] - a0[j];
+            b1[j] = (p1[p.bias_off + c] + nmi * p1[p.scale_off + c]) - b0[j];
+        }
+    }
+    const int vpp_shift = 31 - __clz(vec_per_pix);
+    uint4* y4 = reinterpret_cast<uint4*>(p.y) + base;
+    const float2* w2 = BLEND ? reinterpret_cast<const float2*>(p.weights) + (long long)n * p.P : nullptr;
+    const int act = p.act;
+    const int vpt = chunk_vecs / kBulkConsumers;                   // vectors per thread and chunk (launcher: 1..8)
+    for (int k = 0; k < nchunks; ++k) {
+        const int st = k % stages;
+        const long long v = v0 + (long long)k * chunk_vecs;
+        const int nv = (int)min((long long)chunk_vecs, v1 - v);
+        float wy[8];
+        if (BLEND) {                                               // weight map: plain loads issued before the wait
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (u < vpt) { const int i = tid + u * kBulkConsumers; wy[u] = i < nv ? w2[(v + i) >> vpp_shift].y : 0.f; }
+        }
+        umma::mbar_wait(&full[st], (k / stages) & 1);
+        const uint4* xc = xs + (size_t)st * chunk_vecs;
+        const uint4* rc = rs + (size_t)st * chunk_vecs;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (u >= vpt) break;
+            const int i = tid + u * kBulkConsumers;
+            if (i < nv) {
+                const uint4 xin = xc[i];
+                uint4 rin = make_uint4(0, 0, 0, 0);
+                if (RES) rin = rc[i];
+                const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xin);
+                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rin);
+                uint4 outv;
+                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 xv = __bfloat1622float2(xb[j]);
+                    float aa0 = a0[2 * j], bb0 = b0[2 * j], aa1 = a0[2 * j + 1], bb1 = b0[2 * j + 1];
+                    if (BLEND) {
+                        aa0 = fmaf(wy[u], a1[2 * j], aa0);           bb0 = fmaf(wy[u], b1[2 * j], bb0);
+                        aa1 = fmaf(wy[u], a1[2 * j + 1], aa1);       bb1 = fmaf(wy[u], b1[2 * j + 1], bb1);
+                    }
+                    float o0 = fmaf(xv.x, aa0, bb0), o1 = fmaf(xv.y, aa1, bb1);
+                    if (act == ACT_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+                    if (RES) { const float2 rv = __bfloat1622float2(rb[j]); o0 += rv.x; o1 += rv.y; }
+                    ob[j] = __floats2bfloat162_rn(o0, o1);
+                }
+                y4[v + i] = outv;
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) umma::mbar_arrive(&empty[st]);        // this warp no longer reads the stage
+    }
+}
+
+template <bool BLEND, bool RES>
+static cudaError_t launch_cin_apply_bulk(const CinApplyV& p, int pix_per_block, int stages, int chunk_vecs, cudaStream_t s) {
+    const size_t smem = (size_t)stages * chunk_vecs * 16 * (RES ? 2 : 1);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(cin_apply_bulk_kernel<BLEND, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
+    (void)launch_pdl(cin_apply_bulk_kernel<BLEND, RES>, dim3(grid), dim3(kBulkConsumers + 32), smem, s, p, pix_per_block, stages, chunk_vecs);
+    return cudaGetLastError();
+}
+
 // fp32 -> fp32 with 3 channels (the image head): 4 consecutive floats per thread, sigmoid.
 // YU8: the image leaves as uint8 = trunc(255 * y), the quantisation the reference's callers apply to the prediction
 // (predict_using_checkpoint.py:99 `np.uint8(... * 255)`, predict_video_using_checkpoint.py:98 `(... * 255).astype(int)`).
 template <bool BLEND, bool YU8>
 __global__ void __launch_bounds__(256) cin_apply_c3_kernel(const CinApplyV p) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sa[2][3], sb[2][3];
     const int n = blockIdx.y;
     if (threadIdx.x < 3) {
@@ -1178,13 +1331,41 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
     if (p.x_f32 && p.residual) return cudaErrorInvalidValue;
     const bool blend = p.num_styles == 2 && p.weights != nullptr;
     if (!p.x_f32 && !p.y_f32 && p.act != ACT_SIGMOID && (p.C == 16 || p.C == 32 || p.C == 64 || p.C == 128)) {
-        static const int ppb_scale = ab_env("RST_NORM_PPB") ? atoi(ab_env("RST_NORM_PPB")) : 65536;
-        const int pix_per_block = max(64, ppb_scale / p.C);       // swept on B200 (profiles/r01_03_experiments.md): ~3 CTAs per SM is the optimum
+        // Tensors of the batch-8 trunk / decoder size go through the bulk-copy kernel, one wave of ~2 CTAs per SM, each streaming
+        // a whole number of chunks (B200, profiles/r02_04_pdl_and_bulk_norm.md); small ones keep the register kernel, whose short CTAs
+        // start faster.  RST_NORM_BULK=0/1 forces one of them, RST_NORM_PPB the elements per CTA (A/B runs).
+        static const int bulk_mode = ab_env("RST_NORM_BULK") ? atoi(ab_env("RST_NORM_BULK")) : -1;
+        static const int ppb_env = ab_env("RST_NORM_PPB") ? atoi(ab_env("RST_NORM_PPB")) : 0;
+        const long long tensor_bytes = (long long)p.B * p.P * p.C * 2;
+        const bool bulk = bulk_mode < 0 ? tensor_bytes >= (24ll << 20) : bulk_mode != 0;
+        if (bulk) {
+            static const int stages_x = ab_env("RST_NORM_STAGES") ? atoi(ab_env("RST_NORM_STAGES")) : 4;
+            static const int stages_r = ab_env("RST_NORM_STAGES_RES") ? atoi(ab_env("RST_NORM_STAGES_RES")) : 3;
+            static const int chunk_vecs = ab_env("RST_NORM_CHUNK") ? atoi(ab_env("RST_NORM_CHUNK")) : 1024;
+            const int stages = p.residual ? stages_r : stages_x;
+            if (stages < 1 || stages > kBulkMaxStages || chunk_vecs % kBulkConsumers || chunk_vecs < kBulkConsumers ||
+                chunk_vecs > 8 * kBulkConsumers || (size_t)stages * chunk_vecs * 32 > 200 * 1024)
+                return cudaErrorInvalidValue;
+            static int num_sms = 0;
+            if (!num_sms) {
+                int dev = 0;
+                if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+                    num_sms = 148;
+            }
+            const int chunk_pix = chunk_vecs / (p.C >> 3);
+            int pix_per_block = ppb_env ? max(chunk_pix, ppb_env / p.C)
+                                        : ceil_div(ceil_div(p.P, max(1, 2 * num_sms / p.B)), chunk_pix) * chunk_pix;
+            if (blend && p.residual) return launch_cin_apply_bulk<true, true>(p, pix_per_block, stages, chunk_vecs, s);
+            if (blend) return launch_cin_apply_bulk<true, false>(p, pix_per_block, stages, chunk_vecs, s);
+            if (p.residual) return launch_cin_apply_bulk<false, true>(p, pix_per_block, stages, chunk_vecs, s);
+            return launch_cin_apply_bulk<false, false>(p, pix_per_block, stages, chunk_vecs, s);
+        }
+        const int pix_per_block = max(64, (ppb_env ? ppb_env : 65536) / p.C);       // swept on B200 (profiles/r01_03_experiments.md): ~3 CTAs per SM is the optimum
         dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
-        if (blend && p.residual) cin_apply_fast_kernel<true, true><<<grid, 256, 0, s>>>(p, pix_per_block);
-        else if (blend) cin_apply_fast_kernel<true, false><<<grid, 256, 0, s>>>(p, pix_per_block);
-        else if (p.residual) cin_apply_fast_kernel<false, true><<<grid, 256, 0, s>>>(p, pix_per_block);
-        else cin_apply_fast_kernel<false, false><<<grid, 256, 0, s>>>(p, pix_per_block);
+        if (blend && p.residual) (void)launch_pdl(cin_apply_fast_kernel<true, true>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        else if (blend) (void)launch_pdl(cin_apply_fast_kernel<true, false>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        else if (p.residual) (void)launch_pdl(cin_apply_fast_kernel<false, true>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        else (void)launch_pdl(cin_apply_fast_kernel<false, false>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
         return cudaGetLastError();
     }
     if (p.y_u8 && !(p.x_f32 && p.C == 3 && p.P % 4 == 0)) return cudaErrorInvalidValue;   // uint8 only for the 3-channel image head
@@ -1192,19 +1373,19 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
         const long long want = ((long long)p.P / 4 + 255) / 256;
         const long long per_sample = max(1, 148 * 4 / p.B);          // ~4 CTAs per SM in total, each streaming a long run
         dim3 grid((unsigned)(want < per_sample ? want : per_sample), (unsigned)p.B);
-        if (blend && p.y_u8) cin_apply_c3_kernel<true, true><<<grid, 256, 0, s>>>(p);
-        else if (blend) cin_apply_c3_kernel<true, false><<<grid, 256, 0, s>>>(p);
-        else if (p.y_u8) cin_apply_c3_kernel<false, true><<<grid, 256, 0, s>>>(p);
-        else cin_apply_c3_kernel<false, false><<<grid, 256, 0, s>>>(p);
+        if (blend && p.y_u8) (void)launch_pdl(cin_apply_c3_kernel<true, true>, dim3(grid), dim3(256), 0, s, p);
+        else if (blend) (void)launch_pdl(cin_apply_c3_kernel<true, false>, dim3(grid), dim3(256), 0, s, p);
+        else if (p.y_u8) (void)launch_pdl(cin_apply_c3_kernel<false, true>, dim3(grid), dim3(256), 0, s, p);
+        else (void)launch_pdl(cin_apply_c3_kernel<false, false>, dim3(grid), dim3(256), 0, s, p);
         return cudaGetLastError();
     }
     int pix_per_block = max(1, 32768 / p.C);
     dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
     size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
-    if (p.x_f32 && p.y_f32) cin_apply_v_kernel<true, true><<<grid, 256, smem, s>>>(p, pix_per_block);
-    else if (p.x_f32) cin_apply_v_kernel<true, false><<<grid, 256, smem, s>>>(p, pix_per_block);
-    else if (p.y_f32) cin_apply_v_kernel<false, true><<<grid, 256, smem, s>>>(p, pix_per_block);
-    else cin_apply_v_kernel<false, false><<<grid, 256, smem, s>>>(p, pix_per_block);
+    if (p.x_f32 && p.y_f32) (void)launch_pdl(cin_apply_v_kernel<true, true>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    else if (p.x_f32) (void)launch_pdl(cin_apply_v_kernel<true, false>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    else if (p.y_f32) (void)launch_pdl(cin_apply_v_kernel<false, true>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    else (void)launch_pdl(cin_apply_v_kernel<false, false>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,12 @@ constexpr int kThreads2 = 96 + 128 * 4;  // 3 control warps + 16 epilogue warps 
 // Warps: 0 = B producer + L2 prefetch of later halos, 1 = MMA issuer, 2 .. 2+2*NL-1 = loaders (NL warps per 64-channel
 // group; a thread owns 8 fixed channels, so its 16 coefficients live in registers), then the 16 epilogue warps.
 constexpr int threads2f(int nl) { return 64 + 2 * nl * 32 + 128 * 4; }
+#ifndef RST_TRUNK_REG_BOUND
+#define RST_TRUNK_REG_BOUND kThreads2
+#endif
+// The launch bound the compiler sizes the register budget of the unfused kernel for (65536 / bound, rounded down to 8): the
+// kernel is launched with kThreads2 threads whatever this is.  768 -> 80 registers, which leaves 16 K registers of the SM free.
+constexpr int kTrunkRegBound = RST_TRUNK_REG_BOUND;
 
 __device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
@@ -83,7 +89,7 @@ __device__ __forceinline__ void st_shared_16(uint32_t addr, uint4 v) {
 }
 
 template <int FUSE, int NL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? threads2f(NL) : kThreads2, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FUSE ? threads2f(NL) : kTrunkRegBound, 1)
 halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloGemmParams p) {
     constexpr int W_APROD = FUSE ? -1 : 0, W_BPROD = FUSE ? 0 : 1, W_MMA = FUSE ? 1 : 2;
     (void)W_APROD;
@@ -133,6 +139,8 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the weight producer only reads constants: it runs ahead of the previous kernel's completion; everyone else waits here
+    if (warp != W_BPROD) pdl_wait();
 
     auto tile_coords = [&](int t, int& n, int& h0, int& w0) {
         if (t >= total_tiles) { n = p.B; h0 = 0; w0 = 0; return; }     // phantom tile: out of bounds everywhere -> zeros
@@ -426,13 +434,13 @@ cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_hal
     if (pairs < clusters) clusters = pairs;
     if (p.fuse == 0) {
         if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<0, 1>, smem, configured[0])) return e;
-        halo_gemm2_kernel<0, 1><<<2 * clusters, kThreads2, smem, s>>>(tmA, tmB_half, p);
+        if (cudaError_t e = launch_pdl(halo_gemm2_kernel<0, 1>, dim3(2 * clusters), dim3(kThreads2), smem, s, tmA, tmB_half, p)) return e;
         return cudaGetLastError();
     }
     // fuse 1 only is instantiated: fuse 2 (skip add + write-back in the loader) compiles but was never profitable to finish
     if (p.n_groups != 2 || !p.fin_x || !p.fin_stats || !p.fin_params || p.fuse != 1) return cudaErrorInvalidValue;
     if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 2>, smem, configured[1])) return e;
-    halo_gemm2_kernel<1, 2><<<2 * clusters, threads2f(2), smem, s>>>(tmA, tmB_half, p);
+    if (cudaError_t e = launch_pdl(halo_gemm2_kernel<1, 2>, dim3(2 * clusters), dim3(threads2f(2)), smem, s, tmA, tmB_half, p)) return e;
     return cudaGetLastError();
 }
 

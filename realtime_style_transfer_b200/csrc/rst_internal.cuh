@@ -32,6 +32,36 @@ inline const char* exp_env(const char* name) {
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------------
+// The kernels of the inference forward are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Every such kernel
+// executes pdl_wait() in every thread that reads or writes anything a predecessor touches, before it does so (the wait returns
+// when the predecessor grid has completed and its memory is visible; without the launch attribute it is a no-op).  The
+// HBM-bound pass kernels (norm apply, input packing) also execute pdl_trigger() right after their wait: the convolution that
+// follows is then staged while the pass runs, and its CTAs allocate TMEM and pull their weights into shared memory as soon as
+// an SM drains.  The convolution kernels do NOT trigger: pass CTAs parked in their wait next to running convolution CTAs cost
+// 6 % of the step on B200 (profiles/r02_04_pdl_and_bulk_norm.md); their successor starts when they complete (the implicit trigger), which
+// still hides the launch latency.  Triggering only after the wait keeps the look-ahead at one kernel, so "predecessor complete"
+// stays transitive along the chain.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = !(ab_env("RST_PDL") && atoi(ab_env("RST_PDL")) == 0);
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // TF 'SAME' padding for one spatial dim: returns output size, writes pad_before.
 inline int tf_same(int size, int k, int s, int* pad_before) {
     int out = (size + s - 1) / s;
