@@ -32,7 +32,10 @@ enum rst_status {
 };
 
 enum rst_precision {
-    RST_PRECISION_FP32 = 0,  /* CUDA-core fp32 path, bar: max abs err <= 1e-4 vs the oracle */
+    RST_PRECISION_FP32 = 0,  /* fp32-accurate path, bar: max abs err <= 1e-4 vs the oracle.  The residual blocks' 3x3 convolutions
+                              * run on tcgen05 as error-compensated split tf32 (the RST_PRECISION_TF32X3 arithmetic, fp32
+                              * accumulation) when their channel counts are multiples of 32; the 9x9, strided and transposed
+                              * layers and the style predictor are CUDA-core fp32 kernels */
     RST_PRECISION_BF16 = 1,  /* tcgen05 bf16 path (fp32 accumulate), bar: <= 2e-2 relative */
     RST_PRECISION_TF32 = 2,  /* tcgen05 tf32 operands on fp32 tensors (what TensorFlow itself does with fp32 convolutions on
                               * Ampere and later GPUs); operator level, the loss model and the training step only, see

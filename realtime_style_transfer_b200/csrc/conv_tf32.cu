@@ -77,11 +77,12 @@ bool Tf32Conv3x3::setup_shape(int ci_layer_, int co_layer_, bool relu_, bool inp
     ci = (input_gradient ? co_layer : ci_layer) * (split ? 3 : 1);
     co = input_gradient ? ci_layer : co_layer;
     relu = relu_;
-    if (ci % 32 != 0 || co % 64 != 0) {
-        if (err) *err = "tf32 conv: needs Cin % 32 == 0 and Cout % 64 == 0";
+    // blocks of 32 output channels exist for the forward conv with ReLU only (the 32-filter bottleneck of the fp32 inference path)
+    if (ci % 32 != 0 || (co % 64 != 0 && !(co == 32 && relu && !input_gradient))) {
+        if (err) *err = "tf32 conv: needs Cin % 32 == 0 and Cout % 64 == 0 (or Cout == 32 for a forward conv with ReLU)";
         return false;
     }
-    nb = co % 128 == 0 ? 128 : 64;
+    nb = co % 128 == 0 ? 128 : co % 64 == 0 ? 64 : 32;
     nblk = co / nb;
     const int n_groups = ci / 32, blocks = n_groups * 9;
     if (w_packed) { cudaFree(w_packed); w_packed = nullptr; }

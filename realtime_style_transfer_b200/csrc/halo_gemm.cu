@@ -105,7 +105,6 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
-    pdl_wait();                                        // everything below may touch what the previous kernel wrote / still reads
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         bias_s[i] = p.bias ? p.bias[i] : 0.f;
         scale_s[i] = p.post_scale ? p.post_scale[i] : 1.f;
@@ -116,6 +115,8 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything but the weights (warp 1 streams constants only) may be something the previous kernel wrote or still reads
+    if (warp != 1) pdl_wait();
 
     if (warp == 0) {
         // ================= A producer: one halo patch per (tile, channel group) =================
@@ -489,7 +490,7 @@ static cudaError_t launch_t(const HaloGemmLaunch& l, const CUtensorMap& tmA, con
     const int total = p.B * p.tiles_h * p.tiles_w;
     if (total == 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    if (cudaError_t e = launch_pdl(halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES>, dim3(grid), dim3(halo_threads(N)), l.smem_bytes, s, tmA, tmB, p)) return e;
+    if (cudaError_t e = launch_pdl(p.pdl != 0, halo_gemm_kernel<N, ROWB, EPI, MODE, SCH, BRES>, dim3(grid), dim3(halo_threads(N)), l.smem_bytes, s, tmA, tmB, p)) return e;
     return cudaGetLastError();
 }
 
@@ -518,6 +519,7 @@ cudaError_t launch_halo_gemm(const HaloGemmLaunch& l, const CUtensorMap& tmA, co
     RST_HALO_CASE(32, 128, EPI_OCT3, MODE_F32, SCH_HEAD8, true)             // expand_last: 8 pixels x 3 (+1) channels
     RST_HALO_CASE(128, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)   // tf32 3x3 convs (VGG16 loss model)
     RST_HALO_CASE(64, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)
+    RST_HALO_CASE(32, 128, EPI_NHWC, MODE_RELU | MODE_F32 | MODE_TF32, SCH_C3, false)    // 32-filter bottleneck (rst-960-120-32-3), fp32 inference
     RST_HALO_CASE(128, 128, EPI_NHWC, MODE_F32 | MODE_TF32, SCH_C3, false)               // ... and their input gradients
     RST_HALO_CASE(64, 128, EPI_NHWC, MODE_F32 | MODE_TF32, SCH_C3, false)
 #undef RST_HALO_CASE
@@ -895,9 +897,9 @@ static cudaError_t launch_pack_stem_input_t(const TIn* x, __nv_bfloat16* y, int 
         if (row_elems != 32) return cudaErrorInvalidValue;
         if (W % 64 == 0 && aligned) {
             const long long segments = (long long)B * H * (W / 64);
-            (void)launch_pdl(pack_stem_pair_rows18_kernel<TIn>, dim3((unsigned)((segments + 7) / 8)), dim3(256), (size_t)8 * 18 * 18 * sizeof(float4), s, x, y, W, segments);
+            (void)launch_pdl(true, pack_stem_pair_rows18_kernel<TIn>, dim3((unsigned)((segments + 7) / 8)), dim3(256), (size_t)8 * 18 * 18 * sizeof(float4), s, x, y, W, segments);
         } else {
-            (void)launch_pdl(pack_stem_pairs18_kernel<TIn>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, x, y, W, total);
+            (void)launch_pdl(true, pack_stem_pairs18_kernel<TIn>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, x, y, W, total);
         }
         return cudaGetLastError();
     }
@@ -905,12 +907,12 @@ static cudaError_t launch_pack_stem_input_t(const TIn* x, __nv_bfloat16* y, int 
         const long long segments = (long long)B * H * (W / 64);
         const unsigned blocks = (unsigned)((segments + 7) / 8);
         const size_t smem = (size_t)8 * 18 * C * sizeof(float4);
-        if (nv == 1 && pair_window) (void)launch_pdl(pack_stem_rows_kernel<1, true, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
-        else if (nv == 1) (void)launch_pdl(pack_stem_rows_kernel<1, false, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
-        else (void)launch_pdl(pack_stem_rows_kernel<2, false, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
+        if (nv == 1 && pair_window) (void)launch_pdl(true, pack_stem_rows_kernel<1, true, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
+        else if (nv == 1) (void)launch_pdl(true, pack_stem_rows_kernel<1, false, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
+        else (void)launch_pdl(true, pack_stem_rows_kernel<2, false, TIn>, dim3(blocks), dim3(256), smem, s, x, y, W, segments);
         return cudaGetLastError();
     }
-    (void)launch_pdl(pack_stem_input_kernel<TIn>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, x, y, H, W, C, n_real, row_elems, pair_window, total);
+    (void)launch_pdl(true, pack_stem_input_kernel<TIn>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, x, y, H, W, C, n_real, row_elems, pair_window, total);
     return cudaGetLastError();
 }
 
@@ -1236,7 +1238,7 @@ static cudaError_t launch_cin_apply_bulk(const CinApplyV& p, int pix_per_block, 
         attr_done = true;
     }
     dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
-    (void)launch_pdl(cin_apply_bulk_kernel<BLEND, RES>, dim3(grid), dim3(kBulkConsumers + 32), smem, s, p, pix_per_block, stages, chunk_vecs);
+    (void)launch_pdl(true, cin_apply_bulk_kernel<BLEND, RES>, dim3(grid), dim3(kBulkConsumers + 32), smem, s, p, pix_per_block, stages, chunk_vecs);
     return cudaGetLastError();
 }
 
@@ -1362,10 +1364,10 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
         }
         const int pix_per_block = max(64, (ppb_env ? ppb_env : 65536) / p.C);       // swept on B200 (profiles/r01_03_experiments.md): ~3 CTAs per SM is the optimum
         dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
-        if (blend && p.residual) (void)launch_pdl(cin_apply_fast_kernel<true, true>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
-        else if (blend) (void)launch_pdl(cin_apply_fast_kernel<true, false>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
-        else if (p.residual) (void)launch_pdl(cin_apply_fast_kernel<false, true>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
-        else (void)launch_pdl(cin_apply_fast_kernel<false, false>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        if (blend && p.residual) (void)launch_pdl(true, cin_apply_fast_kernel<true, true>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        else if (blend) (void)launch_pdl(true, cin_apply_fast_kernel<true, false>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        else if (p.residual) (void)launch_pdl(true, cin_apply_fast_kernel<false, true>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
+        else (void)launch_pdl(true, cin_apply_fast_kernel<false, false>, dim3(grid), dim3(256), 0, s, p, pix_per_block);
         return cudaGetLastError();
     }
     if (p.y_u8 && !(p.x_f32 && p.C == 3 && p.P % 4 == 0)) return cudaErrorInvalidValue;   // uint8 only for the 3-channel image head
@@ -1373,19 +1375,19 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
         const long long want = ((long long)p.P / 4 + 255) / 256;
         const long long per_sample = max(1, 148 * 4 / p.B);          // ~4 CTAs per SM in total, each streaming a long run
         dim3 grid((unsigned)(want < per_sample ? want : per_sample), (unsigned)p.B);
-        if (blend && p.y_u8) (void)launch_pdl(cin_apply_c3_kernel<true, true>, dim3(grid), dim3(256), 0, s, p);
-        else if (blend) (void)launch_pdl(cin_apply_c3_kernel<true, false>, dim3(grid), dim3(256), 0, s, p);
-        else if (p.y_u8) (void)launch_pdl(cin_apply_c3_kernel<false, true>, dim3(grid), dim3(256), 0, s, p);
-        else (void)launch_pdl(cin_apply_c3_kernel<false, false>, dim3(grid), dim3(256), 0, s, p);
+        if (blend && p.y_u8) (void)launch_pdl(true, cin_apply_c3_kernel<true, true>, dim3(grid), dim3(256), 0, s, p);
+        else if (blend) (void)launch_pdl(true, cin_apply_c3_kernel<true, false>, dim3(grid), dim3(256), 0, s, p);
+        else if (p.y_u8) (void)launch_pdl(true, cin_apply_c3_kernel<false, true>, dim3(grid), dim3(256), 0, s, p);
+        else (void)launch_pdl(true, cin_apply_c3_kernel<false, false>, dim3(grid), dim3(256), 0, s, p);
         return cudaGetLastError();
     }
     int pix_per_block = max(1, 32768 / p.C);
     dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
     size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
-    if (p.x_f32 && p.y_f32) (void)launch_pdl(cin_apply_v_kernel<true, true>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
-    else if (p.x_f32) (void)launch_pdl(cin_apply_v_kernel<true, false>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
-    else if (p.y_f32) (void)launch_pdl(cin_apply_v_kernel<false, true>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
-    else (void)launch_pdl(cin_apply_v_kernel<false, false>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    if (p.x_f32 && p.y_f32) (void)launch_pdl(true, cin_apply_v_kernel<true, true>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    else if (p.x_f32) (void)launch_pdl(true, cin_apply_v_kernel<true, false>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    else if (p.y_f32) (void)launch_pdl(true, cin_apply_v_kernel<false, true>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
+    else (void)launch_pdl(true, cin_apply_v_kernel<false, false>, dim3(grid), dim3(256), smem, s, p, pix_per_block);
     return cudaGetLastError();
 }
 

@@ -434,13 +434,13 @@ cudaError_t launch_halo_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB_hal
     if (pairs < clusters) clusters = pairs;
     if (p.fuse == 0) {
         if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<0, 1>, smem, configured[0])) return e;
-        if (cudaError_t e = launch_pdl(halo_gemm2_kernel<0, 1>, dim3(2 * clusters), dim3(kThreads2), smem, s, tmA, tmB_half, p)) return e;
+        if (cudaError_t e = launch_pdl(p.pdl != 0, halo_gemm2_kernel<0, 1>, dim3(2 * clusters), dim3(kThreads2), smem, s, tmA, tmB_half, p)) return e;
         return cudaGetLastError();
     }
     // fuse 1 only is instantiated: fuse 2 (skip add + write-back in the loader) compiles but was never profitable to finish
     if (p.n_groups != 2 || !p.fin_x || !p.fin_stats || !p.fin_params || p.fuse != 1) return cudaErrorInvalidValue;
     if (cudaError_t e = ensure_dynamic_smem(halo_gemm2_kernel<1, 2>, smem, configured[1])) return e;
-    if (cudaError_t e = launch_pdl(halo_gemm2_kernel<1, 2>, dim3(2 * clusters), dim3(threads2f(2)), smem, s, tmA, tmB_half, p)) return e;
+    if (cudaError_t e = launch_pdl(p.pdl != 0, halo_gemm2_kernel<1, 2>, dim3(2 * clusters), dim3(threads2f(2)), smem, s, tmA, tmB_half, p)) return e;
     return cudaGetLastError();
 }
 

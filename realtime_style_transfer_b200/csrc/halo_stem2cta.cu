@@ -70,7 +70,7 @@ halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
+    if (warp != 1) pdl_wait();                                // the weight producer reads constants only
 
     auto tile_coords = [&](int t, int& n, int& h0, int& w0) {
         if (t >= total_tiles) { n = p.B; h0 = 0; w0 = 0; return; }     // phantom tile: out of bounds everywhere -> zeros
@@ -186,7 +186,7 @@ static cudaError_t launch_stem2cta(const CUtensorMap& tmA, const CUtensorMap& tm
     const int pairs = (total + 1) / 2;
     int clusters = num_sms / 2;
     if (pairs < clusters) clusters = pairs;
-    if (cudaError_t e = launch_pdl(halo_stem2cta_kernel<SCH>, dim3(2 * clusters), dim3(kSThreads), smem, s, tmA, tmB_units, p)) return e;
+    if (cudaError_t e = launch_pdl(p.pdl != 0, halo_stem2cta_kernel<SCH>, dim3(2 * clusters), dim3(kSThreads), smem, s, tmA, tmB_units, p)) return e;
     return cudaGetLastError();
 }
 

@@ -267,6 +267,8 @@ static void free_ctx(rst_ctx* c) {
     for (auto& a : c->pvec) if (a) cudaFree(a);
     if (c->stats) cudaFree(c->stats);
     if (c->w_pyramid) cudaFree(c->w_pyramid);
+    c->res_tf32.clear();
+    if (c->tf32_scratch) cudaFree(c->tf32_scratch);
     for (float* p : {c->st_content, c->st_params, c->st_weights, c->st_out, c->st_style, c->cvt_content, c->cvt_out}) if (p) cudaFree(p);
     for (auto& kv : c->taps) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -422,6 +424,38 @@ static int fold_bn(rst_ctx* c, const std::string& prefix, int ch, float eps) {
     return RST_OK;
 }
 
+// RST_PRECISION_FP32 inference: the residual blocks' 3x3 convolutions (62 % of the FLOPs of rst-960-120-128-17, 28 % of
+// rst-960-120-32-3) run on the tensor cores as error-compensated split-tf32 GEMMs -- x = x_hi + x_lo, w = w_hi + w_lo on the tf32
+// grid, y = x_hi w_hi + x_lo w_hi + x_hi w_lo accumulated in fp32: the arithmetic of RST_PRECISION_TF32X3 in rst_op_conv2d, <= 7e-7
+// relative per conv (tests/test_gpu_fp32.py) -- the 9x9, strided and transposed layers keep the fp32 CUDA-core kernels.
+// RST_FP32_TENSOR=0 selects the CUDA-core kernels for the residual blocks as well (A/B).
+static int fp32_tensor_commit(rst_ctx* c) {
+    c->res_tf32.clear();
+    const char* env = ab_env("RST_FP32_TENSOR");
+    if (env && env[0] == '0') return RST_OK;
+    int max_ci = 0;
+    for (auto& L : c->residual) {
+        if (L.k != 3 || L.stride != 1 || L.transposed || L.ci % 32 != 0 || (L.co % 64 != 0 && L.co != 32)) return RST_OK;
+        max_ci = std::max(max_ci, L.ci);
+    }
+    std::string err;
+    if (!umma_init(&err)) return RST_OK;                       // no tensor-map encoder in this driver: keep the CUDA-core path
+    if (!c->num_sms) RST_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
+    std::vector<std::shared_ptr<Tf32Conv3x3>> convs;
+    for (auto& L : c->residual) {
+        auto t = std::make_shared<Tf32Conv3x3>();
+        if (!t->setup_shape(L.ci, L.co, /*relu=*/true, /*input_gradient=*/false, &err, /*split=*/true))
+            return fail(c, RST_ERR_CUDA, "fp32 tensor-core path: " + err);
+        RST_CUDA(c, t->repack(c->wdev(L.name + "/kernel"), c->wdev(L.name + "/bias"), nullptr));
+        convs.push_back(t);
+    }
+    RST_CUDA(c, cudaDeviceSynchronize());
+    if (!c->tf32_scratch)
+        RST_CUDA(c, cudaMalloc(&c->tf32_scratch, (size_t)c->cfg.max_batch * c->bott_h * c->bott_w * max_ci * 2 * sizeof(float)));
+    c->res_tf32 = std::move(convs);
+    return RST_OK;
+}
+
 extern "C" int rst_commit_weights(rst_ctx* ctx) {
     if (!ctx) return RST_ERR_INVALID;
     cudaSetDevice(ctx->device);
@@ -446,6 +480,10 @@ extern "C" int rst_commit_weights(rst_ctx* ctx) {
     }
     if (ctx->cfg.precision == RST_PRECISION_BF16 && ctx->cfg.in_h != 0) {
         int rc = bf16_commit(ctx);
+        if (rc) return rc;
+    }
+    if (ctx->cfg.precision == RST_PRECISION_FP32 && ctx->cfg.in_h != 0 && !ctx->weight_arena) {
+        int rc = fp32_tensor_commit(ctx);
         if (rc) return rc;
     }
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);     // captured graphs hold the old operands
@@ -601,19 +639,32 @@ static int fp32_transfer_forward(rst_ctx* c, const float* d_content, const float
     const int F = c->cfg.bottleneck_num_filters;
     const int P = c->bott_h * c->bott_w;
     int cursor = 0;
+    const bool tensor = c->res_tf32.size() == c->residual.size() && !c->res_tf32.empty();
     for (int b = 0; b < 5; ++b) {                                          // residual_block, :144-185
         const LayerDesc& L0 = c->residual[2 * b];
         const LayerDesc& L1 = c->residual[2 * b + 1];
-        ConvF32 p0 = conv_params(c, L0, x, t1, batch, L0.name + "/kernel", L0.name + "/bias");
-        p0.act1 = ACT_RELU;
-        { LaunchScope ls(c, s, "conv_fp32"); RST_CUDA(c, launch_conv_f32(p0, s)); }
+        if (tensor) {
+            LaunchScope ls(c, s, "conv_tf32x3", 2);
+            RST_CUDA(c, c->res_tf32[2 * b]->run_split(x, c->tf32_scratch, t1, batch, c->bott_h, c->bott_w, c->num_sms, s, &c->err));
+        } else {
+            ConvF32 p0 = conv_params(c, L0, x, t1, batch, L0.name + "/kernel", L0.name + "/bias");
+            p0.act1 = ACT_RELU;
+            LaunchScope ls(c, s, "conv_fp32");
+            RST_CUDA(c, launch_conv_f32(p0, s));
+        }
         record_tap(c, L0.name + "/relu", t1, (int64_t)batch * P * F, false, s);
         rc = cin_layer(c, t1, t1, nullptr, batch, P, F, c->bott_w, d_style_params, cursor, ACT_RELU, s);
         if (rc) return rc;
         record_tap(c, L0.name + "/cin", t1, (int64_t)batch * P * F, false, s);
-        ConvF32 p1 = conv_params(c, L1, t1, t2, batch, L1.name + "/kernel", L1.name + "/bias");
-        p1.act1 = ACT_RELU;
-        { LaunchScope ls(c, s, "conv_fp32"); RST_CUDA(c, launch_conv_f32(p1, s)); }
+        if (tensor) {
+            LaunchScope ls(c, s, "conv_tf32x3", 2);
+            RST_CUDA(c, c->res_tf32[2 * b + 1]->run_split(t1, c->tf32_scratch, t2, batch, c->bott_h, c->bott_w, c->num_sms, s, &c->err));
+        } else {
+            ConvF32 p1 = conv_params(c, L1, t1, t2, batch, L1.name + "/kernel", L1.name + "/bias");
+            p1.act1 = ACT_RELU;
+            LaunchScope ls(c, s, "conv_fp32");
+            RST_CUDA(c, launch_conv_f32(p1, s));
+        }
         record_tap(c, L1.name + "/relu", t2, (int64_t)batch * P * F, false, s);
         rc = cin_layer(c, t2, t2, b == 0 ? nullptr : x, batch, P, F, c->bott_w, d_style_params, cursor + 2 * F,
                        ACT_NONE, s);

@@ -44,6 +44,7 @@ struct ProfileGroup {
 };
 
 struct Bf16State;           // defined in transfer_bf16.cu
+struct Tf32Conv3x3;         // halo_gemm.cuh
 
 }  // namespace rst
 
@@ -92,6 +93,11 @@ struct rst_ctx {
         bool busy[2] = {false, false};
         int64_t next = 0;
     } pipe;
+
+    // ---- fp32 path: the residual 3x3 convolutions as error-compensated split-tf32 tcgen05 GEMMs (conv_tf32.cu) ----
+    std::vector<std::shared_ptr<rst::Tf32Conv3x3>> res_tf32;   // one per residual conv; empty = CUDA-core kernels
+    float* tf32_scratch = nullptr;                              // [x_hi | x_lo] expansion of one conv input
+    int num_sms = 0;
 
     // ---- bf16 tensor-core path ----
     std::shared_ptr<rst::Bf16State> bf16;

@@ -82,6 +82,7 @@ struct HaloConv {
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s, const HaloGemmParams* fin = nullptr) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
+        q.pdl = 1;                      // inference: weights / bias / folded BN were packed at commit time, long before this launch
         if (fin) {
             if (!two_cta || y_f32) return cudaErrorInvalidValue;
             q.fuse = fin->fuse; q.fin_x = fin->fin_x; q.fin_skip = fin->fin_skip; q.fin_out = fin->fin_out; q.fin_stats = fin->fin_stats;

@@ -315,6 +315,33 @@ def test_config1_rst_960_120_32_3_fp32(cuda_device):
     assert out.min() > 0 and out.max() < 1
 
 
+@pytest.mark.parametrize("filters", [32, 128])
+def test_fp32_residual_blocks_run_on_the_tensor_cores(cuda_device, monkeypatch, filters):
+    """RST_PRECISION_FP32: the residual 3x3 convolutions are split-tf32 tcgen05 GEMMs (rst_api.cu::fp32_tensor_commit); the
+    CUDA-core kernels (RST_FP32_TENSOR=0) give the same image to fp32 rounding, and both meet the fp32 bar against the oracle."""
+    shape_in, shape_out = (64, 128, 17), (64, 128, 3)
+    spec = O.TransferSpec(shape_in, shape_out, 16, filters, 1)
+    weights = O.init_transfer_weights(spec, seed=1, trained_like=True)
+    content = O.synthetic_content(2, 64, 128, ShapeConfig(num_channels=17).channels, seed=5, unit_depth=True)
+    params = np.random.default_rng(2).uniform(0.3, 1.2, (2, 1, spec.num_style_parameters)).astype(np.float32)
+    ref = O.transfer_forward(spec, weights, content, params).numpy()
+    outs, groups = {}, {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RST_FP32_TENSOR", mode)
+        ctx = _native.NativeContext(in_shape=shape_in, out_shape=shape_out, bottleneck_res_y=16, bottleneck_num_filters=filters,
+                                    num_styles=1, max_batch=2)
+        ctx.set_weights(weights)
+        ctx.profile(True)
+        outs[mode] = ctx.transfer_forward_host(content, params)
+        groups[mode] = ctx.profile_groups()
+        ctx.close()
+    assert groups["1"]["conv_tf32x3"][1] == 10 and "conv_tf32x3" not in groups["0"]        # ten residual convs
+    assert groups["1"]["conv_fp32"][1] == groups["0"]["conv_fp32"][1] - 10                 # stem / strided / transposed layers stay
+    print("fp32 tensor vs CUDA-core max abs", np.abs(outs["1"] - outs["0"]).max(), "vs oracle", np.abs(outs["1"] - ref).max())
+    assert np.abs(outs["1"] - outs["0"]).max() <= 2e-5
+    assert np.abs(outs["1"] - ref).max() <= FP32_TOL and np.abs(outs["0"] - ref).max() <= FP32_TOL
+
+
 def test_frames_are_independent_and_deterministic(cuda_device):
     """Size-independent properties: instance norm is per sample, so a batch equals its frames run alone."""
     shape_in, shape_out = (64, 128, 17), (64, 128, 3)
