@@ -605,8 +605,89 @@ __global__ void cin_apply_kernel(const CinApply p, int pix_per_block) {
     }
 }
 
+// fp32 -> fp32 with P * C % 4 == 0: one float4 (four consecutive elements, possibly across a pixel boundary: C = 3) per thread
+// and iteration, 32-bit index arithmetic; per element the same operations in the same order as cin_apply_kernel above
+// (results are bit-identical).
+__global__ void __launch_bounds__(256) cin_apply_f32x4_kernel(const CinApply p, int vec_per_block) {
+    extern __shared__ float smf[];
+    const int C = p.C;
+    float* s_inv = smf;
+    float* s_nmi = smf + C;
+    float* s_scale = smf + 2 * C;
+    float* s_bias = s_scale + p.num_styles * C;
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sum = p.stats[((long long)n * C + c) * 2 + 0];
+        double sq = p.stats[((long long)n * C + c) * 2 + 1];
+        double mean = sum / (double)p.P;
+        double var = sq / (double)p.P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float inv = rsqrtf((float)var + p.eps);
+        s_inv[c] = inv;
+        s_nmi[c] = -(float)mean * inv;
+        for (int st = 0; st < p.num_styles; ++st) {
+            const float* ps = p.params + n * p.param_bstride + st * p.param_sstride;
+            s_scale[st * C + c] = ps[p.scale_off + c];
+            s_bias[st * C + c] = ps[p.bias_off + c];
+        }
+    }
+    __syncthreads();
+    const long long base4 = (long long)n * p.P * C / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(p.x) + base4;
+    const float4* r4 = p.residual ? reinterpret_cast<const float4*>(p.residual) + base4 : nullptr;
+    float4* y4 = reinterpret_cast<float4*>(p.y) + base4;
+    const int total4 = (int)((long long)p.P * C / 4);               // P * C < 2^31 (checked by the launcher)
+    const int v0 = blockIdx.x * vec_per_block, v1 = min(total4, v0 + vec_per_block);
+    const bool blend = p.num_styles == 2 && p.weights != nullptr;
+    const float2* w2 = blend ? reinterpret_cast<const float2*>(p.weights) + (long long)n * p.P : nullptr;
+    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        int pix = (4 * v) / C, c = 4 * v - pix * C;
+        const float4 xv = x4[v];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r4) { const float4 rv = r4[v]; rs[0] = rv.x; rs[1] = rv.y; rs[2] = rv.z; rs[3] = rv.w; }
+        float2 w = make_float2(0.f, 0.f);
+        if (blend) w = __ldg(w2 + pix);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float scale, bias;
+            if (blend) {
+                scale = s_scale[c] * w.x + s_scale[C + c] * w.y;
+                bias = s_bias[c] * w.x + s_bias[C + c] * w.y;
+            } else {
+                scale = s_scale[c];
+                bias = s_bias[c];
+            }
+            const float xh = xs[j] * s_inv[c] + s_nmi[c];
+            float t = bias + xh * scale;
+            t = apply_act(t, p.act);
+            if (r4) t += rs[j];
+            o[j] = t;
+            if (++c == C) {                                          // next pixel
+                c = 0; ++pix;
+                if (blend && j < 3 && pix < p.P) w = __ldg(w2 + pix);
+            }
+        }
+        y4[v] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 cudaError_t launch_cin_apply(const CinApply& p, cudaStream_t s) {
     if (p.B == 0 || p.P == 0) return cudaSuccess;
+    if (!p.x_bf16 && !p.y_bf16 && ((long long)p.P * p.C) % 4 == 0 && (long long)p.P * p.C < (1ll << 31) &&
+        (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
+        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
+        // 128 KB read per CTA on large tensors; small ones (batch 1 at the bottleneck: 3.7 MB) are cut into ~4 CTAs per SM so that
+        // the pass is not a serial chain of load -> store round trips on a fifth of the SMs
+        const long long total4 = (long long)p.P * p.C / 4;
+        int vec_per_block = (int)(total4 * p.B / (4 * 148));
+        vec_per_block = vec_per_block < 512 ? 512 : vec_per_block > 8192 ? 8192 : (vec_per_block + 255) / 256 * 256;
+        dim3 grid((unsigned)ceil_div((int)((long long)p.P * p.C / 4), vec_per_block), (unsigned)p.B);
+        size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
+        cin_apply_f32x4_kernel<<<grid, 256, smem, s>>>(p, vec_per_block);
+        return cudaGetLastError();
+    }
     int pix_per_block = max(1, 16384 / p.C);
     dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
     size_t smem = (size_t)(2 + 2 * p.num_styles) * p.C * sizeof(float);
