@@ -533,7 +533,8 @@ def main():
         torch.cuda.synchronize(dev)
         e1s = time.perf_counter() - t0
         config_recs["config1_fp32_b1"] = {
-            "workload": "rst-960-120-32-3, one style, batch 1, fp32 path (max abs error <= 1e-4), float32 in / out",
+            "workload": "rst-960-120-32-3, one style, batch 1, fp32 path (max abs error <= 1e-4; residual 3x3 convolutions as split-tf32 "
+                        "tcgen05 GEMMs, the 9x9 / strided / transposed layers on CUDA cores), float32 in / out",
             "frames_per_s": world * args.steps / (ms1 / 1e3), "ms_per_frame": ms1 / args.steps,
             "e2e_frames_per_s": world * args.steps / e1s,
             "achieved_tflops_per_gpu": args.steps / (ms1 / 1e3) * GFLOP_PER_FRAME_32_3 / 1e3,
