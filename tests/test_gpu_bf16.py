@@ -296,6 +296,46 @@ def test_graph_replay_matches_eager_and_follows_new_inputs(cuda_device):
     ctx.close()
 
 
+def test_back_to_back_replays_agree_under_programmatic_dependent_launch(cuda_device):
+    """The forward's kernels overlap their predecessors' tails (rst_internal.cuh: launch_pdl / griddepcontrol.wait).  A kernel that
+    read its input before the producer had finished would show up as a replay that differs from the others by far more than the
+    rounding of the atomically accumulated statistics: 40 replays queued back to back at the benchmark size (batch 8, full
+    resolution, buffers rotating so that a replay's input was the previous replay's scratch) must all agree with the first
+    and with an eager (taps enabled, no graph) run of the same frames."""
+    cfg = ShapeConfig.from_spec("rst-960-120-128-17")
+    in_shape, out_shape = cfg.input_shape["content"], cfg.output_shape
+    spec = O.TransferSpec(in_shape, out_shape, 120, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1, trained_like=True)
+    ctx = _native.NativeContext(in_shape=in_shape, out_shape=out_shape, bottleneck_res_y=120, bottleneck_num_filters=128,
+                                num_styles=1, max_batch=8, precision=_native.PRECISION_BF16)
+    ctx.set_weights(weights)
+    content = torch.as_tensor(O.synthetic_content(8, 480, 960, cfg.channels, seed=11, unit_depth=True)).to(cuda_device).half()
+    params = torch.as_tensor(np.random.default_rng(3).uniform(0.3, 1.2, (8, 1, spec.num_style_parameters)).astype(np.float32)).to(cuda_device)
+    outs = [torch.empty((8,) + out_shape, dtype=torch.uint8, device=cuda_device) for _ in range(40)]
+    first = torch.empty((8,) + out_shape, dtype=torch.uint8, device=cuda_device)
+    stream = torch.cuda.Stream(cuda_device)
+
+    def fwd(dst):
+        ctx.transfer_forward_device(content.data_ptr(), params.data_ptr(), None, dst.data_ptr(), 8, stream.cuda_stream,
+                                    content_dtype=_native.DTYPE_F16, out_dtype=_native.DTYPE_U8)
+    with torch.cuda.stream(stream):
+        fwd(first)                                          # eager
+        fwd(first)                                          # captured
+        for o in outs:                                      # replays of one graph per output buffer would not queue back to back:
+            fwd(first)                                      # the SAME graph 40 times, copied out after each replay
+            o.copy_(first, non_blocking=True)
+        stream.synchronize()
+    ref = outs[0].cpu().numpy().astype(np.int16)
+    for o in outs[1:]:
+        assert np.abs(o.cpu().numpy().astype(np.int16) - ref).max() <= 1        # one uint8 level: the order of the fp64 atomics
+    ctx.enable_taps(True)                                   # taps force the eager path (no graph, no overlap between replays)
+    with torch.cuda.stream(stream):
+        fwd(first)
+        stream.synchronize()
+    assert np.abs(first.cpu().numpy().astype(np.int16) - ref).max() <= 1
+    ctx.close()
+
+
 def test_mixed_precision_policy_selects_tensor_core_path(cuda_device):
     mixed_precision.set_global_policy("mixed_bfloat16")
     try:
