@@ -1,5 +1,7 @@
+"""Per-group device time of the fp32 inference path (rst_profile_*): `python tools/experiments/fp32_path_profile.py [spec] [batch]`.
+Used for the config-1 numbers of profiles/r02_00_summary.md."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from realtime_style_transfer_b200 import _native
 from realtime_style_transfer_b200._plan import TransferPlan

@@ -1,7 +1,7 @@
 """Experiment: one batch of 8 frames against two half batches on two streams (do the norm passes of one half hide under the
 convolutions of the other?)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from realtime_style_transfer_b200 import _native
