@@ -116,7 +116,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // everything but the weights (warp 1 streams constants only) may be something the previous kernel wrote or still reads
-    if (warp != 1) pdl_wait();
+    if (warp != 1) { pdl_wait(); if (p.pdl_trigger) pdl_trigger(); }
 
     if (warp == 0) {
         // ================= A producer: one halo patch per (tile, channel group) =================
@@ -1137,6 +1137,17 @@ __global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(con
         for (int i = 0; i < stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], kBulkConsumers / 32); }
         umma::fence_barrier_init();
     }
+    // the style parameters are inputs of the forward (written long before this kernel's predecessor): fetched ahead of the wait
+    const int c0 = (tid % vec_per_pix) * 8;
+    float sc0[8], bi0[8], sc1[BLEND ? 8 : 1], bi1[BLEND ? 8 : 1];
+    {
+        const float* ps = p.params + n * p.param_bstride;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc0[j] = ps[p.scale_off + c0 + j]; bi0[j] = ps[p.bias_off + c0 + j];
+            if (BLEND) { sc1[j] = ps[p.param_sstride + p.scale_off + c0 + j]; bi1[j] = ps[p.param_sstride + p.bias_off + c0 + j]; }
+        }
+    }
     pdl_wait();
     pdl_trigger();
     __syncthreads();
@@ -1157,7 +1168,6 @@ __global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(con
         return;
     }
     // ---- consumers: fixed group of 8 channels per thread (kBulkConsumers % vec_per_pix == 0)
-    const int c0 = (tid % vec_per_pix) * 8;
     const double inv_p = 1.0 / (double)p.P;
     float a0[8], b0[8], a1[8], b1[8];
 #pragma unroll
@@ -1168,13 +1178,11 @@ __global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(con
         double var = fma(st.y, inv_p, -mean * mean);
         if (var < 0.0) var = 0.0;
         const float inv = rsqrtf((float)var + p.eps), nmi = -(float)mean * inv;
-        const float* ps = p.params + n * p.param_bstride;
-        a0[j] = inv * ps[p.scale_off + c];
-        b0[j] = ps[p.bias_off + c] + nmi * ps[p.scale_off + c];
+        a0[j] = inv * sc0[j];
+        b0[j] = bi0[j] + nmi * sc0[j];
         if (BLEND) {
-            const float* p1 = ps + p.param_sstride;
-            a1[j] = inv * p1[p.scale_off + c] - a0[j];
-            b1[j] = (p1[p.bias_off + c] + nmi * p1[p.scale_off + c]) - b0[j];
+            a1[j] = inv * sc1[j] - a0[j];
+            b1[j] = (bi1[j] + nmi * sc1[j]) - b0[j];
         }
     }
     const int vpp_shift = 31 - __clz(vec_per_pix);

@@ -158,6 +158,8 @@ struct HaloGemmParams {
     long long fin_param_bstride = 0;
     int fin_scale_off = 0, fin_bias_off = 0;
     float fin_eps = 1e-5f;
+    int pdl_trigger = 0;                       // pdl only: let the successor be staged early (set when the successor is another
+                                               // convolution: its CTAs cannot park beside this kernel's, they need the shared memory)
     int pdl = 0;                               // launch with the programmatic-dependent-launch attribute (rst_internal.cuh): the weights,
                                                // bias and folded BN constants must not be written by the kernel launched just before
     int fuse_dbg = 0;                          // RST_EXPERIMENTS builds only: 1 = skip the global loads, 2 = skip the smem stores (timing)

@@ -70,7 +70,7 @@ halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp != 1) pdl_wait();                                // the weight producer reads constants only
+    if (warp != 1) { pdl_wait(); if (p.pdl_trigger) pdl_trigger(); }     // the weight producer reads constants only
 
     auto tile_coords = [&](int t, int& n, int& h0, int& w0) {
         if (t >= total_tiles) { n = p.B; h0 = 0; w0 = 0; return; }     // phantom tile: out of bounds everywhere -> zeros

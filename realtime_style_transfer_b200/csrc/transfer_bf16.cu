@@ -78,11 +78,13 @@ struct HaloConv {
         return halo_gemm_plan(&launch, &p, err);
     }
 
+    bool next_is_conv = false;      // the kernel launched after this one in the forward is a convolution (HaloGemmParams::pdl_trigger)
     // fin (optional): fused input transform of the 2-CTA trunk kernel, fields fuse / fin_* of HaloGemmParams
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s, const HaloGemmParams* fin = nullptr) {
         HaloGemmParams q = p;
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
         q.pdl = 1;                      // inference: weights / bias / folded BN were packed at commit time, long before this launch
+        q.pdl_trigger = next_is_conv ? 1 : 0;
         if (fin) {
             if (!two_cta || y_f32) return cudaErrorInvalidValue;
             q.fuse = fin->fuse; q.fin_x = fin->fin_x; q.fin_skip = fin->fin_skip; q.fin_out = fin->fin_out; q.fin_stats = fin->fin_stats;
@@ -428,6 +430,7 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, st->stem.upload(packed, cb, &cs, &csh));
         st->stem.p.out_H = L.ho; st->stem.p.out_W = pairs ? L.wo / 2 : L.wo;
         if (!st->stem.bind_input(st->s_in, B, L.hi, pairs ? L.wi / 2 : L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        st->stem.next_is_conv = true;                            // contract_0 follows
     }
     // ---- strided encoder convs ----
     for (size_t i = 1; i < c->contract.size(); ++i) {
@@ -442,6 +445,7 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, hc.upload(packed, cb, &cs, &csh));
         hc.p.out_H = L.ho; hc.p.out_W = L.wo;
         if (!hc.bind_input(st->enc[i - 1], B, L.ho, L.wo, &err)) return fail(c, RST_ERR_CUDA, err);
+        hc.next_is_conv = true;                                   // the next contract layer or residual_block_0/conv0 follows
     }
     // ---- bottleneck ----
     for (int i = 0; i < 10; ++i) {
