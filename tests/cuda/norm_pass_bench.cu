@@ -1,6 +1,10 @@
 // Microbenchmark of the conditional-instance-norm apply pass (launch_cin_apply_v) on bf16 NHWC tensors of the trunk's shape,
 // in place, back to back, so that the tensor stays in L2 when it fits.  Usage: norm_pass_bench [C] [P] [first batch size]
-// Build: see tools/build_cuda_tests.sh.  Environment switches of the library (RST_NORM_BULK, RST_NORM_PPB, ...) apply.
+// Build (from the repo root, after __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -cudart shared -I realtime_style_transfer_b200/csrc \
+//        -o tests/cuda/norm_pass_bench tests/cuda/norm_pass_bench.cu -L realtime_style_transfer_b200/csrc -lrst_sm100 \
+//        -Xlinker -rpath -Xlinker '$ORIGIN/../../realtime_style_transfer_b200/csrc'
+// (the binary is git- and gpurun-ignored; drop the line from .gpurunignore to run it on a GPU box).  Environment switches of the library (RST_NORM_BULK, RST_NORM_PPB, ...) apply.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
