@@ -338,7 +338,7 @@ def test_fp32_residual_blocks_run_on_the_tensor_cores(cuda_device, monkeypatch, 
     assert groups["1"]["conv_tf32x3"][1] == 10 and "conv_tf32x3" not in groups["0"]        # ten residual convs
     assert groups["1"]["conv_fp32"][1] == groups["0"]["conv_fp32"][1] - 10                 # stem / strided / transposed layers stay
     print("fp32 tensor vs CUDA-core max abs", np.abs(outs["1"] - outs["0"]).max(), "vs oracle", np.abs(outs["1"] - ref).max())
-    assert np.abs(outs["1"] - outs["0"]).max() <= 2e-5
+    assert np.abs(outs["1"] - outs["0"]).max() <= 5e-5                                      # measured 3e-6 (F = 32) / 1.5e-5 (F = 128)
     assert np.abs(outs["1"] - ref).max() <= FP32_TOL and np.abs(outs["0"] - ref).max() <= FP32_TOL
 
 
