@@ -122,17 +122,23 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= A producer: one halo patch per (tile, channel group) =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint64_t pol_first = l2_policy_evict_first();
             for (int t = tile_begin; t < tile_end; ++t) {
                 const int n = t / tiles_per_img, r = t - n * tiles_per_img;
                 const int h0 = (r / p.tiles_w) * 8, w0 = (r % p.tiles_w) * 16;
                 for (int g = 0; g < p.n_groups; ++g) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     mbar_expect_tx(&a_full[stage], halo_bytes);
-                    if (SCH == SCH_S2D) tma_load_5d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], 0, h0, 0, w0, n);
+                    if (SCH == SCH_S2D) {
+                        if (p.l2_hints & 1) tma_load_5d_hint(sA + stage * a_stage_bytes, &tmA, &a_full[stage], 0, h0, 0, w0, n, pol_first);
+                        else tma_load_5d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], 0, h0, 0, w0, n);
+                    }
                     else if ((MODE & MODE_TF32) && p.a_wrap) {
                         // split tf32: one conv over [x_hi | x_lo | x_hi]; the tensor stores [x_hi | x_lo], the third part re-reads the first
                         tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], (g >= p.a_wrap ? g - p.a_wrap : g) * ROW_ELEMS,
                                     h0 + p.oy, w0 * p.a_w_mul + p.ox, n);
+                    } else if (p.l2_hints & 1) {
+                        tma_load_4d_hint(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 * p.a_w_mul + p.ox, n, pol_first);
                     } else tma_load_4d(sA + stage * a_stage_bytes, &tmA, &a_full[stage], g * ROW_ELEMS, h0 + p.oy, w0 * p.a_w_mul + p.ox, n);
                     if (++stage == (uint32_t)p.n_astages) { stage = 0; phase ^= 1; }
                 }
@@ -1113,6 +1119,12 @@ __global__ void __launch_bounds__(256) cin_apply_fast_kernel(const CinApplyV p, 
 constexpr int kBulkMaxStages = 8;
 constexpr int kBulkConsumers = 256;
 
+__device__ __forceinline__ void bulk_load_1d_hint(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     umma::smem_u32(dst_smem)),
+                 "l"((uint64_t)__cvta_generic_to_global(src)), "r"(bytes), "r"(umma::smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      umma::smem_u32(dst_smem)),
@@ -1155,6 +1167,7 @@ __global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(con
         if (tid == kBulkConsumers) {
             const uint4* x4 = reinterpret_cast<const uint4*>(p.x) + base;
             const uint4* r4 = RES ? reinterpret_cast<const uint4*>(p.residual) + base : nullptr;
+            const uint64_t pol_first = umma::l2_policy_evict_first();
             for (int k = 0; k < nchunks; ++k) {
                 const int st = k % stages;
                 if (k >= stages) umma::mbar_wait(&empty[st], ((k / stages) - 1) & 1);
@@ -1162,7 +1175,10 @@ __global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(con
                 const uint32_t bytes = (uint32_t)min((long long)chunk_vecs, v1 - v) * 16u;
                 umma::mbar_expect_tx(&full[st], RES ? 2 * bytes : bytes);
                 bulk_load_1d(xs + (size_t)st * chunk_vecs, x4 + v, bytes, &full[st]);
-                if (RES) bulk_load_1d(rs + (size_t)st * chunk_vecs, r4 + v, bytes, &full[st]);
+                if (RES) {
+                    if (p.l2_hints & 1) bulk_load_1d_hint(rs + (size_t)st * chunk_vecs, r4 + v, bytes, &full[st], pol_first);
+                    else bulk_load_1d(rs + (size_t)st * chunk_vecs, r4 + v, bytes, &full[st]);
+                }
             }
         }
         return;

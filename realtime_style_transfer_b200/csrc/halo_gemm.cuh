@@ -158,6 +158,7 @@ struct HaloGemmParams {
     long long fin_param_bstride = 0;
     int fin_scale_off = 0, fin_bias_off = 0;
     float fin_eps = 1e-5f;
+    int l2_hints = 0;                          // trunk kernel: bit 0 = activation loads evict_first, bit 1 = output stores evict_last
     int pdl_trigger = 0;                       // pdl only: let the successor be staged early (set when the successor is another
                                                // convolution: its CTAs cannot park beside this kernel's, they need the shared memory)
     int pdl = 0;                               // launch with the programmatic-dependent-launch attribute (rst_internal.cuh): the weights,
@@ -268,6 +269,7 @@ struct CinApplyV {
     long long param_bstride = 0, param_sstride = 0; int scale_off = 0, bias_off = 0;
     const float* weights = nullptr;    // (B,P,2) or null
     int B = 0, P = 0, C = 0, num_styles = 1, act = ACT_NONE; float eps = 1e-5f;
+    int l2_hints = 0;                  // bulk kernel: bit 0 = the skip tensor is read evict_first (dead after this pass)
 };
 cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s);
 

@@ -153,6 +153,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ================= A producer (both CTAs): own halo patch, transactions land on the leader's barrier ====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint64_t pol_first = l2_policy_evict_first();
             for (int pr = pair_begin; pr < pair_end; ++pr) {
                 int n, h0, w0;
                 if (pr + kPrefetchPairs < pair_end) {            // pull a later tile's halo into L2 while this one is consumed
@@ -163,7 +164,8 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int g = 0; g < p.n_groups; ++g) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     if (leader_cta) mbar_expect_tx(&a_full[stage], 2 * kHalo2);
-                    tma_load_4d_2sm(sA + stage * kAStage2, &tmA, &a_full[stage], g * 64, h0 - 1, w0 - 1, n);
+                    if (p.l2_hints & 1) tma_load_4d_2sm_hint(sA + stage * kAStage2, &tmA, &a_full[stage], g * 64, h0 - 1, w0 - 1, n, pol_first);
+                    else tma_load_4d_2sm(sA + stage * kAStage2, &tmA, &a_full[stage], g * 64, h0 - 1, w0 - 1, n);
                     if (++stage == kAStages2) { stage = 0; phase ^= 1; }
                 }
             }
@@ -348,6 +350,7 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float* my_sum = stat_s + q * 2 * N;
         float* my_sq = my_sum + N;
         const bool do_stats = p.stats != nullptr;
+        const uint64_t pol_last = l2_policy_evict_last();
         int cur_n = -1;
         auto flush = [&]() {
             if (do_stats && cur_n >= 0 && cur_n < p.B) {
@@ -389,7 +392,10 @@ halo_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) +
                                        (((size_t)n * p.out_H + gh) * p.out_W + gw) * p.out_C + c * CW;
 #pragma unroll
-                    for (int j = 0; j < CW / 16; ++j) st_global_v8(o + 16 * j, packed + 8 * j);      // full sectors per lane
+                    for (int j = 0; j < CW / 16; ++j) {                                              // full sectors per lane
+                        if (p.l2_hints & 2) st_global_v8_hint(o + 16 * j, packed + 8 * j, pol_last);
+                        else st_global_v8(o + 16 * j, packed + 8 * j);
+                    }
                 }
                 if (do_stats) {
                     float sq[32];

@@ -88,7 +88,8 @@ halo_stem2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tile_coords(2 * pr + (int)rank, n, h0, w0);
                 mbar_wait(&a_empty[stage], phase ^ 1);
                 if (leader_cta) mbar_expect_tx(&a_full[stage], 2 * kSHalo);
-                tma_load_4d_2sm(sA + stage * kSAStage, &tmA, &a_full[stage], 0, h0 + p.oy, w0 + p.ox, n);
+                if (p.l2_hints & 1) tma_load_4d_2sm_hint(sA + stage * kSAStage, &tmA, &a_full[stage], 0, h0 + p.oy, w0 + p.ox, n, l2_policy_evict_first());
+                else tma_load_4d_2sm(sA + stage * kSAStage, &tmA, &a_full[stage], 0, h0 + p.oy, w0 + p.ox, n);
                 if (++stage == kSAStages) { stage = 0; phase ^= 1; }
             }
         }

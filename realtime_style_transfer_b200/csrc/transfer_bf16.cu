@@ -78,6 +78,7 @@ struct HaloConv {
         return halo_gemm_plan(&launch, &p, err);
     }
 
+    int l2_hints = 0;               // HaloGemmParams::l2_hints (RST_L2_HINTS, read when the plan is built)
     bool next_is_conv = false;      // the kernel launched after this one in the forward is a convolution (HaloGemmParams::pdl_trigger)
     // fin (optional): fused input transform of the 2-CTA trunk kernel, fields fuse / fin_* of HaloGemmParams
     cudaError_t run(void* y, bool y_f32, double* stats, int batch, int num_sms, cudaStream_t s, const HaloGemmParams* fin = nullptr) {
@@ -85,6 +86,7 @@ struct HaloConv {
         q.B = batch; q.y = y; q.y_f32 = y_f32 ? 1 : 0; q.stats = stats;
         q.pdl = 1;                      // inference: weights / bias / folded BN were packed at commit time, long before this launch
         q.pdl_trigger = next_is_conv ? 1 : 0;
+        q.l2_hints = l2_hints;
         if (fin) {
             if (!two_cta || y_f32) return cudaErrorInvalidValue;
             q.fuse = fin->fuse; q.fin_x = fin->fin_x; q.fin_skip = fin->fin_skip; q.fin_out = fin->fin_out; q.fin_stats = fin->fin_stats;
@@ -348,6 +350,7 @@ struct Bf16State {
     int num_sms = 148;
     bool tc_decoder = false;            // expand layers on tensor cores (standard 2-expand geometry)
     bool fuse1 = false;                 // first norm of every residual block applied by the consuming conv's loader warps
+    int l2_hints = 0;                   // RST_L2_HINTS (A/B): bits 0-1 trunk conv (loads evict_first / stores evict_last), bit 2 norm pass skip loads
     StemLayout stem_layout{};
     HaloConv stem, contract[4], trunk[10], e0, e1, head;
     __nv_bfloat16 *s_in = nullptr;      // packed stem input
@@ -377,6 +380,11 @@ int bf16_create(rst_ctx* c) {
     cudaDeviceProp prop;
     RST_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
     st->num_sms = prop.multiProcessorCount;
+    // L2 eviction priorities (B200, profiles/r02_05_l2_hints.md): every convolution's activation loads and the norm pass's skip
+    // loads are evict_first -- those tensors are dead (or not needed for two kernels) once read, and the tensor the next kernel
+    // reads, this kernel's output, stays in L2 instead.  RST_L2_HINTS=<bits> for A/B: 1 trunk loads, 2 trunk stores evict_last
+    // (no gain, off), 4 skip loads, 8 the other convolutions' loads.
+    st->l2_hints = ab_env("RST_L2_HINTS") ? atoi(ab_env("RST_L2_HINTS")) : 13;
     const size_t B = g.max_batch;
     const size_t pin = B * g.in_h * g.in_w, pb = B * c->bott_h * c->bott_w;
     RST_CUDA(c, cudaMalloc(&st->s_in, pin * st->stem_layout.row_elems * 2));
@@ -431,6 +439,7 @@ int bf16_commit(rst_ctx* c) {
         st->stem.p.out_H = L.ho; st->stem.p.out_W = pairs ? L.wo / 2 : L.wo;
         if (!st->stem.bind_input(st->s_in, B, L.hi, pairs ? L.wi / 2 : L.wi, &err)) return fail(c, RST_ERR_CUDA, err);
         st->stem.next_is_conv = true;                            // contract_0 follows
+        st->stem.l2_hints = (st->l2_hints >> 3) & 1;
     }
     // ---- strided encoder convs ----
     for (size_t i = 1; i < c->contract.size(); ++i) {
@@ -446,6 +455,7 @@ int bf16_commit(rst_ctx* c) {
         hc.p.out_H = L.ho; hc.p.out_W = L.wo;
         if (!hc.bind_input(st->enc[i - 1], B, L.ho, L.wo, &err)) return fail(c, RST_ERR_CUDA, err);
         hc.next_is_conv = true;                                   // the next contract layer or residual_block_0/conv0 follows
+        hc.l2_hints = (st->l2_hints >> 3) & 1;
     }
     // ---- bottleneck ----
     for (int i = 0; i < 10; ++i) {
@@ -453,6 +463,7 @@ int bf16_commit(rst_ctx* c) {
         const Weight* k = c->find_weight(L.name + "/kernel");
         const Weight* b = c->find_weight(L.name + "/bias");
         HaloConv& hc = st->trunk[i];
+        hc.l2_hints = st->l2_hints & 3;
         setup_conv3x3(&hc, L.ci, F, k->host.data(), b->host.data(), ACT_RELU, &packed, &cb);
         RST_CUDA(c, hc.upload(packed, cb, nullptr, nullptr));
         hc.p.out_H = L.ho; hc.p.out_W = L.wo;
@@ -484,11 +495,13 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, st->e0.upload(packed, cb, nullptr, nullptr));
         st->e0.p.out_H = L0.ho; st->e0.p.out_W = L0.wo;
         if (!st->e0.bind_input(st->bz, B, L0.hi, L0.wi, &err)) return fail(c, RST_ERR_CUDA, err);   // block 4 (even) leaves its output in bz
+        st->e0.l2_hints = (st->l2_hints >> 3) & 1;
         setup_convt2(&st->e1, L1.ci, L1.co, c->find_weight(L1.name + "/conv/kernel")->host.data(),
                      c->find_weight(L1.name + "/conv/bias")->host.data(), &packed, &cb);
         RST_CUDA(c, st->e1.upload(packed, cb, nullptr, nullptr));
         st->e1.p.out_H = L1.ho; st->e1.p.out_W = L1.wo;
         if (!st->e1.bind_input(st->ye0, B, L1.hi, L1.wi, &err)) return fail(c, RST_ERR_CUDA, err);
+        st->e1.l2_hints = (st->l2_hints >> 3) & 1;
         const char* env8 = ab_env("RST_HEAD8");
         const bool head8 = L2.wi % 8 == 0 && !(env8 && env8[0] == '0');
         (head8 ? setup_head8 : setup_head)(&st->head, c->find_weight(L2.name + "/conv/kernel")->host.data(),
@@ -496,6 +509,7 @@ int bf16_commit(rst_ctx* c) {
         RST_CUDA(c, st->head.upload(packed, cb, nullptr, nullptr));
         st->head.p.out_H = L2.ho; st->head.p.out_W = L2.wo;
         if (!st->head.bind_input(st->ye1, B, L2.hi, L2.wi / (head8 ? 8 : 4), &err)) return fail(c, RST_ERR_CUDA, err);
+        st->head.l2_hints = (st->l2_hints >> 3) & 1;
     }
     return RST_OK;
 }
@@ -511,6 +525,7 @@ static int norm_pass(rst_ctx* c, const void* x, bool x_f32, void* y, bool y_f32,
     a.scale_off = param_off; a.bias_off = param_off + C;
     a.weights = c->cfg.num_styles == 2 ? mip_for_width(c, width) : nullptr;
     a.B = batch; a.P = P; a.C = C; a.num_styles = c->cfg.num_styles; a.act = act;
+    a.l2_hints = c->bf16 ? c->bf16->l2_hints >> 2 : 0;
     if (c->cfg.num_styles == 2 && !a.weights) return fail(c, RST_ERR_STATE, "no style-weight mip for this layer width");
     LaunchScope ls(c, s, "cin_apply_bf16");
     RST_CUDA(c, launch_cin_apply_v(a, s));
