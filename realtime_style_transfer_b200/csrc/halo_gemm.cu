@@ -1255,12 +1255,8 @@ __global__ void __launch_bounds__(kBulkConsumers + 32) cin_apply_bulk_kernel(con
 template <bool BLEND, bool RES>
 static cudaError_t launch_cin_apply_bulk(const CinApplyV& p, int pix_per_block, int stages, int chunk_vecs, cudaStream_t s) {
     const size_t smem = (size_t)stages * chunk_vecs * 16 * (RES ? 2 : 1);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(cin_apply_bulk_kernel<BLEND, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemAttrCache configured;                               // per device: a process may drive several GPUs
+    if (cudaError_t e = ensure_dynamic_smem(cin_apply_bulk_kernel<BLEND, RES>, 200 * 1024, configured)) return e;
     dim3 grid((unsigned)ceil_div(p.P, pix_per_block), (unsigned)p.B);
     (void)launch_pdl(true, cin_apply_bulk_kernel<BLEND, RES>, dim3(grid), dim3(kBulkConsumers + 32), smem, s, p, pix_per_block, stages, chunk_vecs);
     return cudaGetLastError();
@@ -1372,11 +1368,13 @@ cudaError_t launch_cin_apply_v(const CinApplyV& p, cudaStream_t s) {
             if (stages < 1 || stages > kBulkMaxStages || chunk_vecs % kBulkConsumers || chunk_vecs < kBulkConsumers ||
                 chunk_vecs > 8 * kBulkConsumers || (size_t)stages * chunk_vecs * 32 > 200 * 1024)
                 return cudaErrorInvalidValue;
-            static int num_sms = 0;
-            if (!num_sms) {
-                int dev = 0;
-                if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-                    num_sms = 148;
+            static int sms_of_device[64] = {};
+            int dev = 0, num_sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+                if (!sms_of_device[dev] &&
+                    cudaDeviceGetAttribute(&sms_of_device[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+                    sms_of_device[dev] = 148;
+                num_sms = sms_of_device[dev];
             }
             const int chunk_pix = chunk_vecs / (p.C >> 3);
             int pix_per_block = ppb_env ? max(chunk_pix, ppb_env / p.C)

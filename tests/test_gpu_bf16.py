@@ -396,3 +396,18 @@ def test_two_devices_in_one_process(cuda_device):
         outs.append(ctx.transfer_forward_host(content, params))
         ctx.close()
     assert np.isfinite(outs[1]).all() and np.array_equal(outs[0], outs[1])
+    # the benchmark geometry at batch 4: tensors of 29.5 MB take the bulk-copy norm kernel (64 - 96 KB of dynamic shared memory)
+    cfg = ShapeConfig.from_spec("rst-960-120-128-17")
+    spec = O.TransferSpec(cfg.input_shape["content"], cfg.output_shape, 120, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(4, 480, 960, cfg.channels, seed=0, unit_depth=True)
+    params = np.random.default_rng(2).uniform(0.3, 1.2, (4, 1, spec.num_style_parameters)).astype(np.float32)
+    outs = []
+    for device in (0, 1):
+        ctx = _native.NativeContext(in_shape=cfg.input_shape["content"], out_shape=cfg.output_shape, bottleneck_res_y=120,
+                                    bottleneck_num_filters=128, num_styles=1, max_batch=4, precision=_native.PRECISION_BF16,
+                                    device=device)
+        ctx.set_weights(weights)
+        outs.append(ctx.transfer_forward_host(content, params))
+        ctx.close()
+    assert np.isfinite(outs[1]).all() and np.abs(outs[0] - outs[1]).max() < 5e-3     # atomically accumulated statistics
