@@ -38,10 +38,12 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 // when the predecessor grid has completed and its memory is visible; without the launch attribute it is a no-op).  The
 // HBM-bound pass kernels (norm apply, input packing) also execute pdl_trigger() right after their wait: the convolution that
 // follows is then staged while the pass runs, and its CTAs allocate TMEM and pull their weights into shared memory as soon as
-// an SM drains.  The convolution kernels do NOT trigger: pass CTAs parked in their wait next to running convolution CTAs cost
-// 6 % of the step on B200 (profiles/r02_04_pdl_and_bulk_norm.md); their successor starts when they complete (the implicit trigger), which
-// still hides the launch latency.  Triggering only after the wait keeps the look-ahead at one kernel, so "predecessor complete"
-// stays transitive along the chain.
+// an SM drains.  A convolution triggers only when its successor is another convolution (HaloGemmParams::pdl_trigger: stem ->
+// contract_0 -> contract_1 -> residual_block_0/conv0).  A convolution followed by a pass does NOT: pass CTAs parked in their
+// wait while the convolution still runs cost 3 - 6 % of the step on B200, even when they sit on other SMs
+// (profiles/r02_04_pdl_and_bulk_norm.md); the pass then starts when the convolution completes (the implicit trigger), which still
+// hides the launch latency.  Triggering only after the wait keeps the look-ahead at one kernel, so "predecessor complete" stays
+// transitive along the chain.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
