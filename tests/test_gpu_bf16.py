@@ -336,6 +336,27 @@ def test_back_to_back_replays_agree_under_programmatic_dependent_launch(cuda_dev
     ctx.close()
 
 
+def test_l2_eviction_hints_do_not_change_results(cuda_device, monkeypatch):
+    """RST_L2_HINTS (read when the context is created) only changes cache priorities of loads: the image must be the same up to
+    the rounding of the atomically accumulated statistics, at a size where the hinted kernels (2-CTA trunk, bulk norm pass with
+    the skip tensor) are the ones that run."""
+    cfg = ShapeConfig.from_spec("rst-960-120-128-17")
+    in_shape, out_shape = cfg.input_shape["content"], cfg.output_shape
+    spec = O.TransferSpec(in_shape, out_shape, 120, 128, 1)
+    weights = O.init_transfer_weights(spec, seed=1)
+    content = O.synthetic_content(4, 480, 960, cfg.channels, seed=2, unit_depth=True)
+    params = np.random.default_rng(4).uniform(0.3, 1.2, (4, 1, spec.num_style_parameters)).astype(np.float32)
+    outs = {}
+    for hints in ("0", "13"):
+        monkeypatch.setenv("RST_L2_HINTS", hints)
+        ctx = _native.NativeContext(in_shape=in_shape, out_shape=out_shape, bottleneck_res_y=120, bottleneck_num_filters=128,
+                                    num_styles=1, max_batch=4, precision=_native.PRECISION_BF16)
+        ctx.set_weights(weights)
+        outs[hints] = ctx.transfer_forward_host(content, params)
+        ctx.close()
+    assert np.isfinite(outs["13"]).all() and np.abs(outs["0"] - outs["13"]).max() < 5e-3
+
+
 def test_mixed_precision_policy_selects_tensor_core_path(cuda_device):
     mixed_precision.set_global_policy("mixed_bfloat16")
     try:
