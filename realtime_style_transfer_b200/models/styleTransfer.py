@@ -111,6 +111,162 @@ def calc_next_conv_dims(initial, filters, mult) -> typing.Tuple:
     return (initial[0], initial[1] * mult, initial[2] * mult, filters)
 
 
+# ---- the reference's sub-model builders (styleTransfer.py:95-205, :335-345) -----------------------------------------------------
+# create_style_transfer_model runs the whole network natively; these stand-alone builders exist for callers that assemble or
+# inspect single blocks as the reference module allows.  Each returns a callable with the reference's name, variables drawn from
+# the reference's initialisers and input dictionary; the arithmetic runs through the operator-level C ABI (rst_op_conv2d,
+# rst_op_cin), BatchNorm in inference mode on the host (one affine per channel).
+_ACT_CODES = {None: _native.ACT_NONE, "linear": _native.ACT_NONE, "relu": _native.ACT_RELU, "sigmoid": _native.ACT_SIGMOID}
+
+
+def _act_code(activation):
+    if activation is None or isinstance(activation, str):
+        if activation not in _ACT_CODES:
+            raise ValueError(f"unsupported activation {activation!r}: relu, sigmoid or None")
+        return _ACT_CODES[activation]
+    name = getattr(activation, "__name__", str(activation)).lower()          # tf.nn.relu / tf.nn.sigmoid style callables
+    for key in ("relu", "sigmoid"):
+        if key in name:
+            return _ACT_CODES[key]
+    raise ValueError(f"unsupported activation {activation!r}: relu, sigmoid or None")
+
+
+def _conv_op(x: np.ndarray, kernel: np.ndarray, bias: np.ndarray, stride: int, transposed: bool, act: int) -> np.ndarray:
+    """Conv2D / Conv2DTranspose with padding='same' on the GPU (rst_op_conv2d)."""
+    import torch
+    b, h, w, ci = x.shape
+    kh, kw = kernel.shape[:2]
+    co = kernel.shape[2] if transposed else kernel.shape[3]
+    ho, wo = (h * stride, w * stride) if transposed else (-(-h // stride), -(-w // stride))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_x, d_k, d_b = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev) for a in (x, kernel, bias))
+    d_y = torch.empty((b, ho, wo, co), dtype=torch.float32, device=dev)
+    _native.op_conv2d(d_x.data_ptr(), d_k.data_ptr(), d_b.data_ptr(), d_y.data_ptr(), b, h, w, ci, co, kh, kw, stride,
+                      transposed, act, _native.PRECISION_FP32, torch.cuda.current_stream().cuda_stream)
+    return d_y.cpu().numpy()
+
+
+class _Block:
+    """A sub-model of the transfer network: name, ``variables`` (name -> float32 array, reference layouts), input / output shape."""
+
+    def __init__(self, name, input_shape, output_shape, variables):
+        self.name, self.input_shape, self.output_shape, self.variables = name, tuple(input_shape), tuple(output_shape), variables
+
+    @property
+    def weights(self):
+        return list(self.variables.values())
+
+    def get_weights(self):
+        return [v.copy() for v in self.variables.values()]
+
+    def set_weights(self, values):
+        values = list(values)
+        if len(values) != len(self.variables):
+            raise ValueError(f"{self.name}: expected {len(self.variables)} arrays, got {len(values)}")
+        for (k, old), new in zip(list(self.variables.items()), values):
+            new = np.asarray(new, dtype=np.float32)
+            if new.shape != old.shape:
+                raise ValueError(f"{self.name}/{k}: shape {new.shape} != {old.shape}")
+            self.variables[k] = new
+
+
+class _ContractBlock(_Block):
+    def __init__(self, input_shape, filters, size, strides, name, rng):
+        h, w, ci = input_shape
+        variables = {"conv/kernel": rng.normal(0.0, 0.02, (size, size, ci, filters)).astype(np.float32),
+                     "conv/bias": np.zeros(filters, np.float32), "bn/gamma": np.ones(filters, np.float32),
+                     "bn/beta": np.zeros(filters, np.float32), "bn/moving_mean": np.zeros(filters, np.float32),
+                     "bn/moving_variance": np.ones(filters, np.float32)}
+        super().__init__(f"contract_{name}", input_shape, (-(-h // strides), -(-w // strides), filters), variables)
+        self.strides = strides
+
+    def __call__(self, x):
+        """ReLU(BN(ReLU(conv(x) + b))) with the moving statistics (styleTransfer.py:194-203; Keras BN eps 1e-3)."""
+        v = self.variables
+        y = _conv_op(as_numpy(x), v["conv/kernel"], v["conv/bias"], self.strides, False, _native.ACT_RELU)
+        scale = v["bn/gamma"] / np.sqrt(v["bn/moving_variance"] + np.float32(1e-3))
+        return np.maximum(y * scale + (v["bn/beta"] - v["bn/moving_mean"] * scale), 0.0).astype(np.float32)
+
+
+class _StyledBlock(_Block):
+    def _cin(self, x, params, style_weights, act, name):
+        layer = ConditionalInstanceNormalization(x.shape[-1], self.num_styles, name)
+        inputs = {"content": x, "style_params": params}
+        if self.num_styles > 1:
+            inputs["style_weights"] = style_weights
+        return layer(inputs, activation=act)
+
+
+class _ResidualBlock(_StyledBlock):
+    def __init__(self, input_shape, num_styles, filters, size, strides, name, is_first, rng):
+        h, w, ci = input_shape
+        variables = {"conv0/kernel": rng.uniform(0.0, 0.05, (size, size, ci, filters)).astype(np.float32),
+                     "conv0/bias": np.zeros(filters, np.float32),
+                     "conv1/kernel": rng.uniform(0.0, 0.05, (size, size, filters, filters)).astype(np.float32),
+                     "conv1/bias": np.zeros(filters, np.float32)}
+        super().__init__(f"residual_block_{name}", input_shape, (h, w, filters), variables)
+        self.num_styles, self.filters, self.strides, self.is_first = num_styles, filters, strides, is_first
+        self.num_style_parameters = 2 * NUM_PARAMS_PER_FEATURE * filters          # [scale0 | bias0 | scale1 | bias1]
+
+    def __call__(self, inputs):
+        """fx = CIN_i(ReLU(conv_i(fx) + b)) for i in 0, 1 with a ReLU after the first CIN only; + x unless is_first
+        (styleTransfer.py:167-184).  inputs: {'content', 'style_params' (B,1,S,4F)[, 'style_weights' (B,H,W,S)]}."""
+        x = as_numpy(inputs["content"])
+        params = as_numpy(inputs["style_params"])
+        sw = inputs.get("style_weights")
+        f, v = self.filters, self.variables
+        fx = x
+        for i in range(2):
+            fx = _conv_op(fx, v[f"conv{i}/kernel"], v[f"conv{i}/bias"], self.strides, False, _native.ACT_RELU)
+            fx = self._cin(fx, params[..., 2 * f * i:2 * f * (i + 1)], sw, _native.ACT_RELU if i == 0 else _native.ACT_NONE,
+                           f"{self.name}_{i}")
+        return fx if self.is_first else (x + fx).astype(np.float32)
+
+
+class _ExpandBlock(_StyledBlock):
+    def __init__(self, input_shape, num_styles, filters, size, strides, name, activation, rng):
+        h, w, ci = input_shape
+        variables = {"conv/kernel": rng.normal(0.0, 0.02, (size, size, filters, ci)).astype(np.float32),      # (kh,kw,out,in)
+                     "conv/bias": np.zeros(filters, np.float32)}
+        super().__init__(f"expand_{name}", input_shape, (h * strides, w * strides, filters), variables)
+        self.num_styles, self.filters, self.strides, self.act = num_styles, filters, strides, _act_code(activation)
+        self.num_style_parameters = NUM_PARAMS_PER_FEATURE * filters
+
+    def __call__(self, inputs):
+        """act(CIN(convT(x) + b)) (styleTransfer.py:115-139).  inputs as for residual_block, 'style_params' (B,1,S,2F); the
+        style weights are those of the OUTPUT resolution."""
+        v = self.variables
+        y = _conv_op(as_numpy(inputs["content"]), v["conv/kernel"], v["conv/bias"], self.strides, True, _native.ACT_NONE)
+        return self._cin(y, as_numpy(inputs["style_params"]), inputs.get("style_weights"), self.act, self.name)
+
+
+def expand(input_shape: typing.Tuple, num_styles, filters, size, strides, name, activation="relu", seed=None):
+    """styleTransfer.py:95-141: Conv2DTranspose('same') -> ConditionalInstanceNormalization -> activation."""
+    return _ExpandBlock(input_shape, num_styles, filters, size, strides, name, activation, np.random.default_rng(seed))
+
+
+def residual_block(input_shape: typing.Tuple, num_styles, filters, size, strides, name, is_first=False, seed=None):
+    """styleTransfer.py:144-185."""
+    return _ResidualBlock(input_shape, num_styles, filters, size, strides, name, is_first, np.random.default_rng(seed))
+
+
+def contract(input_shape, filters, size, strides, name, seed=None):
+    """styleTransfer.py:188-205: Conv2D('same') -> ReLU -> BatchNormalization -> ReLU."""
+    return _ContractBlock(input_shape, filters, size, strides, name, np.random.default_rng(seed))
+
+
+def _get_style_weight_mips(style_weights, num_mips):
+    """styleTransfer.py:335-345: {width: weights}, each level AvgPool2D(2) ('valid': odd trailing rows / columns dropped) of the
+    one above; host arithmetic (the native forward builds the same pyramid on the device, rst_api.cu::build_mips)."""
+    level = np.asarray(as_numpy(style_weights), dtype=np.float32)
+    mips = {level.shape[-2]: level}
+    for _ in range(num_mips):
+        b, h, w, c = level.shape
+        level = level[:, :h // 2 * 2, :w // 2 * 2].reshape(b, h // 2, 2, w // 2, 2, c).mean(axis=(2, 4), dtype=np.float32)
+        mips[level.shape[-2]] = level
+    return mips
+
+
 class StyleTransferModel(NativeModel):
     """Object returned by create_style_transfer_model; inputs dict {'content','style_params'[,'style_weights']}."""
 

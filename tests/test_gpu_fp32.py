@@ -315,6 +315,53 @@ def test_config1_rst_960_120_32_3_fp32(cuda_device):
     assert out.min() > 0 and out.max() < 1
 
 
+@pytest.mark.parametrize("styles", [1, 2])
+def test_reference_builder_blocks_match_the_oracle(cuda_device, styles):
+    """contract / residual_block / expand (styleTransfer.py:95-205) as stand-alone callables against the oracle's primitives."""
+    from realtime_style_transfer_b200.models import styleTransfer as ST
+    rng = np.random.default_rng(7 + styles)
+    t = torch.as_tensor
+    x = rng.standard_normal((2, 12, 20, 8)).astype(np.float32)
+    # contract: ReLU(BN(ReLU(conv + b))), stride 2, non-trivial moving statistics
+    c = ST.contract((12, 20, 8), 16, 3, 2, "0", seed=3)
+    c.variables["conv/bias"] = rng.normal(0, 0.1, 16).astype(np.float32)
+    c.variables["bn/moving_mean"] = rng.normal(0, 0.05, 16).astype(np.float32)
+    c.variables["bn/moving_variance"] = rng.uniform(0.5, 1.5, 16).astype(np.float32)
+    c.variables["bn/gamma"] = rng.uniform(0.5, 1.5, 16).astype(np.float32)
+    v = {k: t(a) for k, a in c.variables.items()}
+    ref = torch.relu(O.batchnorm(torch.relu(O.conv2d_same(t(x), v["conv/kernel"], v["conv/bias"], 2)), v["bn/gamma"], v["bn/beta"],
+                                 v["bn/moving_mean"], v["bn/moving_variance"]))
+    got = c(x)
+    assert got.shape == (2,) + c.output_shape and np.abs(got - ref.numpy()).max() < 1e-5
+    # residual block with skip, and expand with sigmoid
+    sw = rng.uniform(0, 1, (2, 12, 20, 2)).astype(np.float32) if styles == 2 else None
+    sw2 = rng.uniform(0, 1, (2, 24, 40, 2)).astype(np.float32) if styles == 2 else None
+
+    def cin_ref(y, params, weights, f):
+        p = t(params)
+        w = t(weights) if weights is not None else None
+        return O.cin(y, O.apply_style_weights(w, p[..., :f]), O.apply_style_weights(w, p[..., f:]))
+
+    r = ST.residual_block((12, 20, 8), styles, 8, 3, 1, "1", seed=4)
+    params = rng.uniform(0.3, 1.2, (2, 1, styles, 32)).astype(np.float32)
+    inputs = {"content": x, "style_params": params}
+    if styles == 2:
+        inputs["style_weights"] = sw
+    v = {k: t(a) for k, a in r.variables.items()}
+    fx = torch.relu(cin_ref(torch.relu(O.conv2d_same(t(x), v["conv0/kernel"], v["conv0/bias"], 1)), params[..., :16], sw, 8))
+    fx = cin_ref(torch.relu(O.conv2d_same(fx, v["conv1/kernel"], v["conv1/bias"], 1)), params[..., 16:], sw, 8)
+    assert np.abs(r(inputs) - (t(x) + fx).numpy()).max() < 2e-5
+    e = ST.expand((12, 20, 8), styles, 4, 3, 2, "0", activation="sigmoid", seed=5)
+    eparams = rng.uniform(0.3, 1.2, (2, 1, styles, 8)).astype(np.float32)
+    einputs = {"content": x, "style_params": eparams}
+    if styles == 2:
+        einputs["style_weights"] = sw2
+    v = {k: t(a) for k, a in e.variables.items()}
+    ref = torch.sigmoid(cin_ref(O.conv2d_transpose_same(t(x), v["conv/kernel"], v["conv/bias"], 2), eparams, sw2, 4))
+    got = e(einputs)
+    assert got.shape == (2,) + e.output_shape and np.abs(got - ref.numpy()).max() < 2e-5
+
+
 @pytest.mark.parametrize("filters", [32, 128])
 def test_fp32_residual_blocks_run_on_the_tensor_cores(cuda_device, monkeypatch, filters):
     """RST_PRECISION_FP32: the residual 3x3 convolutions are split-tf32 tcgen05 GEMMs (rst_api.cu::fp32_tensor_commit); the

@@ -513,3 +513,34 @@ def test_checkpoint_duplicate_keras_names_prefer_the_inference_model(tmp_path):
         }
         assignment, _missing, _unused = ck.match_checkpoint_to_model(ckpt, model)
         assert np.array_equal(assignment["mobilenet/Conv/kernel"], good)
+
+
+def test_reference_builder_helpers_exist_with_the_reference_shapes():
+    """styleTransfer.py:95, :144, :188, :335: expand / residual_block / contract / _get_style_weight_mips are part of the module the
+    reference exposes; the mirror provides them with the reference's names, variable layouts, initialiser ranges and shapes."""
+    import torch
+    from oracle import rst_oracle as O
+    from realtime_style_transfer_b200.models import styleTransfer as ST
+    c = ST.contract((480, 960, 17), 32, 9, 1, "start", seed=0)
+    assert c.name == "contract_start" and c.output_shape == (480, 960, 32)
+    assert [v.shape for v in c.weights] == [(9, 9, 17, 32), (32,), (32,), (32,), (32,), (32,)]
+    assert abs(float(c.variables["conv/kernel"].std()) - 0.02) < 2e-3                     # N(0, 0.02)
+    c2 = ST.contract((480, 960, 32), 16, 3, 2, "0")
+    assert c2.output_shape == (240, 480, 16)
+    r = ST.residual_block((120, 240, 32), 1, 128, 3, 1, "0", is_first=True, seed=0)
+    assert r.name == "residual_block_0" and r.output_shape == (120, 240, 128) and r.num_style_parameters == 4 * 128
+    k = r.variables["conv1/kernel"]
+    assert k.shape == (3, 3, 128, 128) and k.min() >= 0.0 and k.max() <= 0.05               # U(0, 0.05)
+    e = ST.expand((120, 240, 128), 2, 32, 3, 2, "0")
+    assert e.name == "expand_0" and e.output_shape == (240, 480, 32) and e.num_style_parameters == 2 * 32
+    assert e.variables["conv/kernel"].shape == (3, 3, 32, 128)                              # Conv2DTranspose: (kh, kw, out, in)
+    with pytest.raises(ValueError):
+        ST.expand((8, 8, 4), 1, 3, 3, 2, "x", activation="tanh")
+    with pytest.raises(ValueError):
+        r.set_weights(r.get_weights()[:2])
+    w = np.random.default_rng(1).uniform(0, 1, (2, 20, 36, 2)).astype(np.float32)
+    mips = ST._get_style_weight_mips(w, 3)
+    ref = O.style_weight_mips(torch.as_tensor(w), 3)
+    assert sorted(mips) == sorted(ref) == [4, 9, 18, 36]
+    for width, level in mips.items():
+        np.testing.assert_allclose(level, ref[width].numpy(), atol=1e-6)
