@@ -289,9 +289,20 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         };
         uint32_t cs = 0, cph = 0;
+        // tile coordinates advance incrementally: the two integer divisions per tile were on this warp's per-tile latency chain
+        int n = tile_begin / tiles_per_img, tile_h, tile_w;
+        {
+            const int r0 = tile_begin - n * tiles_per_img;
+            tile_h = r0 / p.tiles_w; tile_w = r0 - tile_h * p.tiles_w;
+        }
+        auto next_tile = [&]() {
+            if (++tile_w == p.tiles_w) {
+                tile_w = 0;
+                if (++tile_h == p.tiles_h) { tile_h = 0; ++n; }
+            }
+        };
         for (int t = tile_begin; t < tile_end; ++t) {
-            const int n = t / tiles_per_img, r = t - n * tiles_per_img;
-            const int gh = (r / p.tiles_w) * 8 + h_l, gw = (r % p.tiles_w) * 16 + w_l;
+            const int gh = tile_h * 8 + h_l, gw = tile_w * 16 + w_l;
             const bool valid = gh < p.H && gw < p.WRU;
             if (n != cur_n) { flush(); cur_n = n; }
             mbar_wait(&acc_full[cs], cph);
@@ -426,6 +437,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 32; ++j) va[j] += part[j];
                 process(va, c_begin);
                 if (++cs == 2) { cs = 0; cph ^= 1; }
+                next_tile();
                 continue;
             }
             if (CW == 32) tmem_ld_32x32(taddr + c_begin * 32, va);
@@ -442,6 +454,7 @@ halo_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             process(va, c_begin);
             if (CPW == 2) process(vb, c_begin + 1);
             if (++cs == 2) { cs = 0; cph ^= 1; }
+            next_tile();
         }
         flush();
     }
